@@ -1,0 +1,442 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// Thin extern "C" harness around the UNMODIFIED reference sources compiled where they
+// lie under /root/reference (recipe: oracle/Makefile, output: oracle/_ref/).  It exists so
+// that (1) the plain-C restatement in oracle/cfr_oracle.c can be pinned against the real
+// reference, (2) golden fixtures under tests/golden/ can be generated (oracle/make_golden.py)
+// and (3) bench.py's `--impl reference` / `cpu_baseline` leg can time the reference's own
+// CPU implementation of the hot path on the host cores.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load the resulting library.  Nothing in rebel_b200/ links or dlopens it.
+//
+// The CFR solver class lives in an anonymous namespace of subgame_solving.cc
+// (subgame_solving.cc:508-715) with private state, so this TU #includes that .cc file
+// verbatim (no copy is made) with private/protected opened up to be able to dump
+// regrets / sum_strategies / leaf values for teacher-forced parity tests.
+
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <queue>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <torch/script.h>
+#include <torch/torch.h>
+
+#define private public
+#define protected public
+#include "subgame_solving.cc"  // reference source, found through -I$(REF)/csrc/liars_dice
+#undef private
+#undef protected
+
+#include "real_net.h"
+#include "recursive_solving.h"
+
+using namespace liars_dice;
+
+namespace {
+
+thread_local std::string g_err;
+
+SubgameSolvingParams make_params(int num_iters, int max_depth, int linear_update, int dcfr,
+                                 double dcfr_alpha, double dcfr_beta, double dcfr_gamma) {
+  SubgameSolvingParams p;
+  p.num_iters = num_iters;
+  p.max_depth = max_depth;
+  p.linear_update = linear_update != 0;
+  p.use_cfr = true;
+  p.dcfr = dcfr != 0;
+  p.dcfr_alpha = dcfr_alpha;
+  p.dcfr_beta = dcfr_beta;
+  p.dcfr_gamma = dcfr_gamma;
+  return p;
+}
+
+// Value net that evaluates Net2 (models.py:64-94) with ATen CPU ops from a flat fp32
+// weight buffer in state_dict order.  Same ATen kernels the TorchScript module dispatches to.
+class FlatNet2 : public IValueNet {
+ public:
+  FlatNet2(const float* w, int Q, int hidden, int H) {
+    auto take = [&](std::vector<int64_t> shape) {
+      int64_t n = 1;
+      for (auto s : shape) n *= s;
+      auto t = torch::from_blob(const_cast<float*>(w), shape, torch::kFloat32).clone();
+      w += n;
+      return t;
+    };
+    w1 = take({hidden, Q}); b1 = take({hidden}); g1 = take({hidden}); be1 = take({hidden});
+    w2 = take({hidden, hidden}); b2 = take({hidden}); g2 = take({hidden}); be2 = take({hidden});
+    w3 = take({H, hidden}); b3 = take({H});
+    hidden_ = hidden;
+  }
+  torch::Tensor compute_values(const torch::Tensor q) override {
+    torch::NoGradGuard ng;
+    auto x = torch::gelu(torch::layer_norm(torch::linear(q, w1, b1), {hidden_}, g1, be1, 1e-5));
+    x = torch::gelu(torch::layer_norm(torch::linear(x, w2, b2), {hidden_}, g2, be2, 1e-5));
+    return torch::linear(x, w3, b3);
+  }
+  void add_training_example(const torch::Tensor q, const torch::Tensor v) override {
+    std::lock_guard<std::mutex> lk(m_);
+    const float* qp = q.data_ptr<float>();
+    const float* vp = v.data_ptr<float>();
+    examples_q.insert(examples_q.end(), qp, qp + q.numel());
+    examples_v.insert(examples_v.end(), vp, vp + v.numel());
+    ++n_examples;
+  }
+  std::vector<float> examples_q, examples_v;
+  std::atomic<int64_t> n_examples{0};
+
+ private:
+  torch::Tensor w1, b1, g1, be1, w2, b2, g2, be2, w3, b3;
+  int64_t hidden_;
+  std::mutex m_;
+};
+
+// Zero net that records the training examples (real_net.cc:30-55 drops them).
+class RecordingZeroNet : public IValueNet {
+ public:
+  explicit RecordingZeroNet(int H) : H_(H) {}
+  torch::Tensor compute_values(const torch::Tensor q) override {
+    return torch::zeros({q.size(0), H_});
+  }
+  void add_training_example(const torch::Tensor q, const torch::Tensor v) override {
+    std::lock_guard<std::mutex> lk(m_);
+    const float* qp = q.data_ptr<float>();
+    const float* vp = v.data_ptr<float>();
+    examples_q.insert(examples_q.end(), qp, qp + q.numel());
+    examples_v.insert(examples_v.end(), vp, vp + v.numel());
+  }
+  std::vector<float> examples_q, examples_v;
+
+ private:
+  int64_t H_;
+  std::mutex m_;
+};
+
+// TorchScript net on CPU that also counts examples (for the timed baseline: identical code
+// path to rela::ModelLocker::forward on device "cpu", model_locker.h:85-95).
+class CountingScriptNet : public IValueNet {
+ public:
+  explicit CountingScriptNet(const std::string& path) : module_(torch::jit::load(path)) {
+    module_.eval();
+  }
+  torch::Tensor compute_values(const torch::Tensor q) override {
+    torch::NoGradGuard ng;
+    std::vector<torch::jit::IValue> in = {q};
+    return torch::detach(module_.forward(in).toTensor());
+  }
+  void add_training_example(const torch::Tensor, const torch::Tensor) override { ++n_examples; }
+  std::atomic<int64_t> n_examples{0};
+
+ private:
+  torch::jit::script::Module module_;
+};
+
+void dump_dense(const TreeStrategy& s, double* out) {
+  if (!out) return;
+  size_t k = 0;
+  for (auto& n : s)
+    for (auto& h : n)
+      for (double v : h) out[k++] = v;
+}
+
+Pair<std::vector<double>> to_beliefs(const double* b, int H) {
+  Pair<std::vector<double>> beliefs;
+  beliefs[0].assign(b, b + H);
+  beliefs[1].assign(b + H, b + 2 * H);
+  return beliefs;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+// tree.h:51-70.  out rows: last_bid, player_id, children_begin, children_end, parent, depth.
+int ref_unroll_tree(int D, int F, int last_bid, int player_id, int max_depth, int32_t* out,
+                    int cap_nodes) {
+  Game game(D, F);
+  PartialPublicState root{last_bid, player_id};
+  auto tree = unroll_tree(game, root, max_depth);
+  if ((int)tree.size() > cap_nodes) return -(int)tree.size();
+  for (size_t i = 0; i < tree.size(); ++i) {
+    int32_t* r = out + 6 * i;
+    r[0] = tree[i].state.last_bid;
+    r[1] = tree[i].state.player_id;
+    r[2] = tree[i].children_begin;
+    r[3] = tree[i].children_end;
+    r[4] = tree[i].parent;
+    r[5] = tree[i].depth;
+  }
+  return (int)tree.size();
+}
+
+int ref_num_matches(int D, int F, int hand, int face) { return Game(D, F).num_matches(hand, face); }
+
+// subgame_solving.cc:765-789
+void ref_win_probability(int D, int F, int bet, const double* beliefs, double* out) {
+  Game game(D, F);
+  std::vector<double> b(beliefs, beliefs + game.num_hands());
+  auto v = compute_win_probability(game, bet, b);
+  std::copy(v.begin(), v.end(), out);
+}
+
+// subgame_solving.cc:104-123 via get_query
+int ref_query(int D, int F, int traverser, int last_bid, int player_id, const double* r0,
+              const double* r1, float* out) {
+  Game game(D, F);
+  std::vector<double> a(r0, r0 + game.num_hands()), b(r1, r1 + game.num_hands());
+  auto q = get_query(game, traverser, PartialPublicState{last_bid, player_id}, a, b);
+  std::copy(q.begin(), q.end(), out);
+  return (int)q.size();
+}
+
+// Runs CFR (subgame_solving.cc:508-715) on one subgame and dumps the complete solver state at the
+// requested checkpoints.  net_w == nullptr -> zero net if the tree has pseudo-leaves, else no net.
+// Dense dumps are [N][H][A] doubles.  checkpoints[] are iteration counts (state AFTER that many
+// steps), increasing.  leaf_values_out (optional) receives, for every checkpoint c>0, the
+// [L][H] float leaf values (already multiplied by the scaler) that step c-1 consumed, and
+// queries_out the [L][Q] float query rows of that step.
+int ref_cfr_solve(int D, int F, int last_bid, int player_id, const double* beliefs, int num_iters,
+                  int max_depth, int linear_update, int dcfr, double dcfr_alpha, double dcfr_beta,
+                  double dcfr_gamma, const float* net_w, int hidden, int n_checkpoints,
+                  const int32_t* checkpoints, double* regrets, double* last, double* sum,
+                  double* avg, double* root_means /*[C][2][H]*/, float* leaf_values_out,
+                  float* queries_out, double* traverser_values_out /*[C][N][H]*/) {
+  try {
+    Game game(D, F);
+    const int H = game.num_hands(), A = game.num_actions();
+    auto params = make_params(num_iters, max_depth, linear_update, dcfr, dcfr_alpha, dcfr_beta,
+                              dcfr_gamma);
+    PartialPublicState root{last_bid, player_id};
+    auto tree = unroll_tree(game, root, max_depth);
+    bool has_pleaf = false;
+    for (auto& n : tree) has_pleaf |= (!n.num_children() && !game.is_terminal(n.state));
+    std::shared_ptr<IValueNet> net;
+    if (net_w) {
+      net = std::make_shared<FlatNet2>(net_w, 2 + A + 2 * H, hidden, H);
+    } else if (has_pleaf) {
+      net = create_zero_net(H, false);
+    }
+    CFR cfr(game, root, net, to_beliefs(beliefs, H), params);
+    const size_t N = cfr.tree.size();
+    const size_t dense = N * H * A;
+    const size_t L = cfr.pseudo_leaves_indices.size();
+    const size_t Q = cfr.query_size;
+    int done = 0;
+    for (int c = 0; c < n_checkpoints; ++c) {
+      for (; done < checkpoints[c]; ++done) cfr.step(done % 2);
+      dump_dense(cfr.regrets, regrets ? regrets + c * dense : nullptr);
+      dump_dense(cfr.last_strategies, last ? last + c * dense : nullptr);
+      dump_dense(cfr.sum_strategies, sum ? sum + c * dense : nullptr);
+      dump_dense(cfr.average_strategies, avg ? avg + c * dense : nullptr);
+      if (root_means) {
+        for (int p = 0; p < 2; ++p)
+          for (int h = 0; h < H; ++h)
+            root_means[(c * 2 + p) * H + h] =
+                (int)cfr.root_values_means[p].size() == H ? cfr.root_values_means[p][h] : 0.0;
+      }
+      if (leaf_values_out && L && done > 0) {
+        auto lv = cfr.leaf_values.contiguous();
+        std::memcpy(leaf_values_out + c * L * H, lv.data_ptr<float>(), L * H * sizeof(float));
+      }
+      if (queries_out && L && done > 0) {
+        std::memcpy(queries_out + c * L * Q, cfr.net_query_buffer.data(), L * Q * sizeof(float));
+      }
+      if (traverser_values_out) {
+        for (size_t n = 0; n < N; ++n)
+          for (int h = 0; h < H; ++h)
+            traverser_values_out[(c * N + n) * H + h] = cfr.traverser_values[n][h];
+      }
+    }
+    return (int)N;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// Full-tree exploitability of a dense [N][H][A] strategy (subgame_solving.cc:802-816).
+int ref_exploitability(int D, int F, const double* strategy, double* out2) {
+  try {
+    Game game(D, F);
+    auto tree = unroll_tree(game);
+    TreeStrategy s;
+    init_nd(tree.size(), game.num_hands(), game.num_actions(), 0.0, &s);
+    size_t k = 0;
+    for (auto& n : s)
+      for (auto& h : n)
+        for (double& v : h) v = strategy[k++];
+    auto e = compute_exploitability2(game, s);
+    out2[0] = e[0];
+    out2[1] = e[1];
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// Runs RlRunner::step (recursive_solving.cc:160-182) `n_games` times with seed, recording every
+// training example.  net_w == nullptr -> zero net.  Returns #examples, fills up to cap.
+int ref_rl_runner(int D, int F, int num_iters, int max_depth, int linear_update,
+                  float random_action_prob, int sample_leaf, int seed, int n_games,
+                  const float* net_w, int hidden, float* q_out, float* v_out, int cap) {
+  try {
+    Game game(D, F);
+    const int H = game.num_hands(), A = game.num_actions(), Q = 2 + A + 2 * H;
+    RecursiveSolvingParams cfg;
+    cfg.num_dice = D;
+    cfg.num_faces = F;
+    cfg.random_action_prob = random_action_prob;
+    cfg.sample_leaf = sample_leaf != 0;
+    cfg.subgame_params = make_params(num_iters, max_depth, linear_update, 0, 0, 0, 0);
+    std::vector<float>*eq, *ev;
+    std::shared_ptr<IValueNet> net;
+    if (net_w) {
+      auto n = std::make_shared<FlatNet2>(net_w, Q, hidden, H);
+      eq = &n->examples_q;
+      ev = &n->examples_v;
+      net = n;
+    } else {
+      auto n = std::make_shared<RecordingZeroNet>(H);
+      eq = &n->examples_q;
+      ev = &n->examples_v;
+      net = n;
+    }
+    RlRunner runner(cfg, net, seed);
+    for (int g = 0; g < n_games; ++g) runner.step();
+    int n = (int)(ev->size() / H);
+    int m = std::min(n, cap);
+    std::memcpy(q_out, eq->data(), sizeof(float) * m * Q);
+    std::memcpy(v_out, ev->data(), sizeof(float) * m * H);
+    return n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// Synthetic bench/parity inputs, shared definition with rebel_b200:
+// beliefs b_p[h] = u/sum(u), u ~ U(0,1) drawn from mt19937(seed) via
+// uniform_real_distribution<double>, player 0 first.
+void ref_synthetic_beliefs(int H, int seed, double* out /*[2][H]*/) {
+  std::mt19937 gen(seed);
+  std::uniform_real_distribution<double> U(0.0, 1.0);
+  for (int p = 0; p < 2; ++p) {
+    double s = 0;
+    for (int h = 0; h < H; ++h) s += (out[p * H + h] = U(gen));
+    for (int h = 0; h < H; ++h) out[p * H + h] /= s;
+  }
+}
+
+// CPU baseline for the bench workload: `n_subgames` root subgames (seeds seed0..), each
+// build_solver + multistep (subgame_solving.cc:791,666) with a TorchScript Net2 on CPU, spread
+// over `threads` std::threads (one solver at a time per thread, like DataThreadLoop).
+// Returns wall seconds; the caller converts to subgame-iters/s.  root_means_out optional
+// [n][2][H].
+double ref_bench_solve(int D, int F, int last_bid, int player_id, int num_iters, int max_depth,
+                       int n_subgames, int seed0, const char* script_path, int threads,
+                       double* root_means_out) {
+  try {
+    torch::set_num_threads(1);
+    Game game(D, F);
+    const int H = game.num_hands();
+    auto params = make_params(num_iters, max_depth, 1, 0, 0, 0, 0);
+    std::vector<std::shared_ptr<IValueNet>> nets;
+    for (int t = 0; t < threads; ++t) {
+      if (script_path && script_path[0])
+        nets.push_back(std::make_shared<CountingScriptNet>(script_path));
+      else
+        nets.push_back(create_zero_net(H, false));
+    }
+    std::atomic<int> next{0};
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+      pool.emplace_back([&, t]() {
+        at::set_num_threads(1);
+        for (;;) {
+          int i = next.fetch_add(1);
+          if (i >= n_subgames) break;
+          std::vector<double> b(2 * H);
+          ref_synthetic_beliefs(H, seed0 + i, b.data());
+          auto solver = build_solver(game, PartialPublicState{last_bid, player_id},
+                                     to_beliefs(b.data(), H), params, nets[t]);
+          solver->multistep();
+          if (root_means_out) {
+            for (int p = 0; p < 2; ++p) {
+              auto v = solver->get_hand_values(p);
+              for (int h = 0; h < H; ++h) root_means_out[(i * 2 + p) * H + h] = v[h];
+            }
+          }
+        }
+      });
+    }
+    for (auto& th : pool) th.join();
+    std::chrono::duration<double> dt = std::chrono::steady_clock::now() - t0;
+    return dt.count();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+}
+
+// CPU baseline for self-play data generation: `threads` RlRunner loops (what
+// DataThreadLoop::mainLoop does, data_loop.h:67-76) with seeds seed0+i, TorchScript Net2 on
+// CPU, for `seconds` wall seconds.  Returns examples added (2 per solved subgame).
+int64_t ref_bench_datagen(int D, int F, int num_iters, int max_depth, float random_action_prob,
+                          int sample_leaf, const char* script_path, int threads, int seed0,
+                          double seconds, double* elapsed_out) {
+  try {
+    torch::set_num_threads(1);
+    RecursiveSolvingParams cfg;
+    cfg.num_dice = D;
+    cfg.num_faces = F;
+    cfg.random_action_prob = random_action_prob;
+    cfg.sample_leaf = sample_leaf != 0;
+    cfg.subgame_params = make_params(num_iters, max_depth, 1, 0, 0, 0, 0);
+    std::vector<std::shared_ptr<CountingScriptNet>> nets;
+    for (int t = 0; t < threads; ++t) nets.push_back(std::make_shared<CountingScriptNet>(script_path));
+    std::atomic<bool> stop{false};
+    std::vector<std::thread> pool;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < threads; ++t) {
+      pool.emplace_back([&, t]() {
+        at::set_num_threads(1);
+        RlRunner runner(cfg, nets[t], seed0 + t);
+        while (!stop.load()) runner.step();
+      });
+    }
+    // Sample the counter at the deadline (games in flight are not waited for in the rate).
+    std::this_thread::sleep_for(std::chrono::duration<double>(seconds));
+    int64_t n = 0;
+    for (auto& net : nets) n += net->n_examples.load();
+    std::chrono::duration<double> dt = std::chrono::steady_clock::now() - t0;
+    if (elapsed_out) *elapsed_out = dt.count();
+    stop = true;
+    for (auto& th : pool) th.join();
+    return n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+}  // extern "C"
