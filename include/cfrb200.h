@@ -1,0 +1,166 @@
+/*
+ * cfrb200 — C ABI of the B200-native CFR subgame-wave solver (libcfrb200.so).
+ *
+ * This is the drop-in boundary beneath the reference's pybind11 module `cfvpy.rela`
+ * (csrc/liars_dice/rela/pybind.cc:119-213): host orchestration (rebel_b200/csrc/rela/*.cc, the
+ * re-implemented `rela` module) calls ONLY these entry points; they replace, on the GPU and for
+ * thousands of subgames at a time, what one reference CPU thread does for one subgame at a time:
+ *
+ *   cfrb_create / cfrb_begin_wave   <-  build_solver + CFR ctor        (subgame_solving.cc:791-800, 509-534)
+ *                                       unroll_tree                    (tree.h:51-70)
+ *   cfrb_run                        <-  CFR::step / multistep          (subgame_solving.cc:577-670) including
+ *                                       the per-iteration value-net call the reference makes through
+ *                                       IValueNet::compute_values      (net_interface.h:28-32,
+ *                                       rela/data_loop.h:29-48, rela/model_locker.h:85-95)
+ *   cfrb_set_weights                <-  ModelLocker::updateModel       (rela/model_locker.h:69-79)
+ *   cfrb_fetch                      <-  ISubgameSolver::get_strategy / get_sampling_strategy /
+ *                                       get_hand_values                (subgame_solving.h:60-88)
+ *   cfrb_examples                   <-  CFR::update_value_network      (subgame_solving.cc:672-676, 220-226)
+ *   cfrb_tree_template              <-  unroll_tree, for bit-exact infoset-index checks (tree_test.cc)
+ *   cfrb_exploitability             <-  compute_exploitability2        (subgame_solving.cc:802-816)
+ *
+ * Conventions: plain C, no exceptions across the boundary; every function returns 0 on success or a
+ * negative CFRB_E* code (cfrb_last_error() gives the message for the calling thread); all buffers are
+ * caller-owned HOST memory (pinned preferred); one handle per GPU; a handle is not thread-safe (one
+ * orchestrator thread per handle).  There is NO CPU fallback: without a CUDA device cfrb_create fails.
+ *
+ * Layouts (all row-major, fp32 unless noted):
+ *   beliefs            [n][2][H]          root beliefs of player 0 then player 1 (Pair<vector<double>> in the reference)
+ *   dense strategy     [n][Nmax][H][A]    the reference's TreeStrategy = [node][hand][action] (subgame_solving.h:39),
+ *                                         padded to Nmax = cfrb_max_nodes() nodes per subgame; entries of illegal
+ *                                         actions, leaves and padding are 0
+ *   root_value_means   [n][2][H]          CFR::root_values_means (subgame_solving.cc:702-703)
+ *   queries            [..][Q]            value-net query rows, Q = 2 + A + 2H (subgame_solving.cc:100-123)
+ *   weights            flat fp32 in Net2 state_dict order (cfvpy/models.py:64-94):
+ *                      body.0.weight[hid,Q] body.0.bias[hid] body.1.weight[hid] body.1.bias[hid]
+ *                      body.4.weight[hid,hid] body.4.bias body.5.weight body.5.bias output.weight[H,hid] output.bias[H]
+ */
+#ifndef CFRB200_H_
+#define CFRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cfrb_handle cfrb_handle;
+
+enum {
+  CFRB_OK = 0,
+  CFRB_EINVAL = -1,   /* bad argument */
+  CFRB_ECUDA = -2,    /* CUDA runtime error (message has the cudaError string) */
+  CFRB_ENODEV = -3,   /* no CUDA device / wrong architecture */
+  CFRB_ESTATE = -4,   /* call sequence error (e.g. run before begin_wave, net needed but no weights) */
+  CFRB_ENOMEM = -5
+};
+
+/* How the leaf value net (Net2 forward) is evaluated. */
+enum {
+  CFRB_NET_ZERO = 0,      /* leaf values are 0 (reference: create_zero_net, real_net.cc:30-55) */
+  CFRB_NET_FP32 = 1,      /* fp32 SIMT kernel: parity path, matches libtorch fp32 to ~1e-6 */
+  CFRB_NET_TC_F16 = 2     /* tcgen05 tensor-core kernel: fp16 operands, fp32 accumulate/LayerNorm/GELU
+                             (the reference's own `half_inference` option, selfplay.py:42-43,211) */
+};
+
+/* SubgameSolvingParams (subgame_solving.h:43-58) + game shape + capacity. */
+typedef struct {
+  int32_t num_dice;
+  int32_t num_faces;
+  int32_t max_depth;        /* depth of every subgame tree */
+  int32_t num_iters;        /* iterations per subgame (only used for default graphs/snapshots) */
+  int32_t linear_update;
+  int32_t dcfr;
+  double dcfr_alpha, dcfr_beta, dcfr_gamma;
+  int32_t max_subgames;     /* wave capacity K */
+  int32_t device;           /* CUDA ordinal */
+  int32_t net_mode;         /* CFRB_NET_* */
+  int32_t hidden;           /* Net2 n_hidden (256); n_layers = 2, LayerNorm on */
+} cfrb_config;
+
+/* One node of an unrolled subgame tree: UnrolledTreeNode (tree.h:31-47). */
+typedef struct {
+  int32_t last_bid, player_id, children_begin, children_end, parent, depth;
+} cfrb_node;
+
+const char* cfrb_last_error(void);
+/* Number of CUDA devices visible (0 if none / driver missing). */
+int cfrb_device_count(void);
+
+int cfrb_create(const cfrb_config* cfg, cfrb_handle** out);
+int cfrb_destroy(cfrb_handle* h);
+
+/* Shape queries. */
+int cfrb_num_actions(const cfrb_handle* h);   /* A */
+int cfrb_num_hands(const cfrb_handle* h);     /* H */
+int cfrb_query_size(const cfrb_handle* h);    /* Q */
+int cfrb_max_nodes(const cfrb_handle* h);     /* Nmax over all root templates */
+
+/* Host-only (no device needed): unroll_tree(game, {last_bid, player_id}, max_depth) (tree.h:51-70) through the same
+ * template builder the kernels index with.  Returns the node count or a negative error; writes min(count, cap). */
+int cfrb_unroll_tree(int32_t num_dice, int32_t num_faces, int32_t last_bid, int32_t player_id, int32_t max_depth,
+                     cfrb_node* out, int32_t cap);
+
+/* Tree of the subgame rooted at (last_bid, player_id) with the handle's max_depth, in the reference's BFS
+ * node order.  Returns the node count (>0) or a negative error; writes min(count, cap) nodes. */
+int cfrb_tree_template(const cfrb_handle* h, int32_t last_bid, int32_t player_id, cfrb_node* out, int32_t cap);
+
+/* Install value-net weights (flat fp32, `n` floats, layout above).  `version` is remembered and returned by
+ * cfrb_weights_version.  Takes effect for kernels enqueued after the call. */
+int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t version);
+uint64_t cfrb_weights_version(const cfrb_handle* h);
+
+/* Start a wave of n <= max_subgames subgames.  Subgame k is rooted at (last_bid[k], player_id[k]) with
+ * root beliefs beliefs[k][2][H]; state is initialised exactly like the CFR constructor
+ * (uniform strategies, reach-weighted uniform sum, zero regrets, subgame_solving.cc:509-524,125-149).
+ * act_iteration[k] (may be NULL) is the iteration count after which the sampling strategy
+ * (CFR::last_strategies) of subgame k is snapshotted for RlRunner's state sampling
+ * (recursive_solving.cc:168-174); -1 = no snapshot. */
+int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const int32_t* player_id,
+                    const float* beliefs, const int32_t* act_iteration);
+
+/* Advance every subgame of the wave by `iters` CFR iterations (iteration i has traverser i % 2,
+ * CFR::multistep subgame_solving.cc:666-670), asynchronously on `cuda_stream` (a cudaStream_t; NULL = the
+ * handle's own stream). */
+int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream);
+/* Block until everything enqueued by this handle has finished. */
+int cfrb_sync(cfrb_handle* h);
+/* Iterations done so far in the current wave. */
+int cfrb_iterations_done(const cfrb_handle* h);
+
+/* Copy results to the host (any pointer may be NULL).  Synchronises.
+ *   root_value_means [n][2][H]; snapshot / last / avg / sum / regrets: dense [n][Nmax][H][A]. */
+int cfrb_fetch(cfrb_handle* h, float* root_value_means, float* snapshot_strategy, float* last_strategy,
+               float* avg_strategy, float* sum_strategy, float* regrets);
+
+/* Training examples of the finished wave: for each subgame and traverser t in {0,1} the query row of the
+ * subgame root as seen by t and the target root_value_means[t].  queries [n][2][Q], values [n][2][H]. */
+int cfrb_examples(cfrb_handle* h, float* queries, float* values);
+
+/* Teacher forcing (tests): overwrite solver state of the current wave from dense host arrays
+ * [n][Nmax][H][A] (NULL = keep), root_value_means [n][2][H], num_steps [n][2], and set the wave's
+ * iteration counter. */
+int cfrb_load_state(cfrb_handle* h, const float* regrets, const float* last_strategy, const float* sum_strategy,
+                    const float* root_value_means, const int32_t* num_steps, int32_t iterations_done);
+
+/* Debug/parity taps of the most recent iteration: query rows [rows][Q] and the (unscaled) net outputs
+ * [rows][H] for all pseudo-leaves of the wave in (subgame, leaf) order; returns the number of rows,
+ * writes at most cap_rows. */
+int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, float* scalers, int32_t cap_rows);
+
+/* Exploitability (best-response values of both players, compute_exploitability2) of a full-tree strategy
+ * given as dense [N_full][H][A] fp32, evaluated on the GPU. out2 = {br0, br1}. */
+int cfrb_exploitability(cfrb_handle* h, const float* full_strategy, float* out2);
+
+/* Counters for bench.py: kernels launched by this handle since creation, and leaf rows of the wave. */
+int64_t cfrb_kernel_launches(const cfrb_handle* h);
+int64_t cfrb_wave_leaf_rows(const cfrb_handle* h);
+/* Device time in ms of the most recent cfrb_run, and of its value-net kernels only (CUDA events on
+ * the launching stream; valid after cfrb_sync). */
+int cfrb_last_run_ms(cfrb_handle* h, float* total_ms, float* net_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFRB200_H_ */

@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz from the REFERENCE itself (oracle/_ref, built from
+/root/reference by oracle/Makefile).  Run in the build container only:
+
+    make -C oracle ref && python oracle/make_golden.py
+
+The fixtures are what travels to the GPU box (where /root/reference does not exist).  Net weights are NOT stored:
+they are re-created from the seed with rebel_b200.models.make_selfplay_net and pinned by a checksum in the fixture.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.oracle import Oracle, game_dims  # noqa: E402
+from rebel_b200.models import flatten_state_dict, make_selfplay_net  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+SHAPES = [(1, 4), (1, 6), (2, 3)]
+
+
+def weights(D, F):
+    return flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    R = Oracle("ref_nofma")
+    RF = Oracle("ref_fast")
+
+    # ---- trees (bit-exact contract)
+    trees = {}
+    for (D, F, lb, pl, md) in [(1, 2, -1, 0, 1000), (2, 6, 22, 0, 0), (2, 6, 22, 0, 1), (2, 6, 22, 0, 2), (2, 6, 21, 0, 2),
+                               (1, 4, -1, 0, 2), (1, 4, 3, 1, 2), (1, 6, -1, 0, 2), (1, 6, 5, 1, 2), (1, 6, 10, 0, 2),
+                               (2, 3, -1, 1, 2), (2, 3, 7, 0, 2), (1, 5, -1, 0, 3), (1, 4, -1, 0, 1000)]:
+        trees[f"t_{D}_{F}_{lb}_{pl}_{md}"] = R.unroll_tree(D, F, lb, pl, md)
+    np.savez_compressed(os.path.join(OUT, "trees.npz"), **trees)
+
+    # ---- zero-net depth-2 CFR trajectories (deterministic: -ffp-contract=off build)
+    cps = [0, 1, 2, 3, 17, 64]
+    for (D, F) in SHAPES:
+        A, H, Q = game_dims(D, F)
+        roots = [(-1, 0), (2, 1), (A - 3, 0)]
+        out = {"checkpoints": np.array(cps), "roots": np.array(roots)}
+        for i, (lb, pl) in enumerate(roots):
+            b = R.synthetic_beliefs(H, 1000 + i)
+            s = R.cfr_solve(D, F, b, cps, lb, pl, num_iters=64)
+            out[f"beliefs{i}"] = b
+            for k in ("regrets", "last", "sum", "avg", "root_means"):
+                out[f"{k}{i}"] = s[k]
+        np.savez_compressed(os.path.join(OUT, f"cfr_zero_{D}x{F}.npz"), **out)
+
+    # ---- Net2 depth-2 trajectories: short horizon states + long-horizon root means from both builds
+    cps_net = [1, 2, 16]
+    for (D, F) in SHAPES:
+        A, H, Q = game_dims(D, F)
+        w = weights(D, F)
+        out = {"checkpoints": np.array(cps_net), "w_checksum": np.array([w.astype(np.float64).sum(), np.abs(w).astype(np.float64).sum()]),
+               "w_head": w[:8].copy()}
+        roots = [(-1, 0), (1, 1)]
+        out["roots"] = np.array(roots)
+        for i, (lb, pl) in enumerate(roots):
+            b = R.synthetic_beliefs(H, 2000 + i)
+            s = R.cfr_solve(D, F, b, cps_net, lb, pl, num_iters=16, net_w=w)
+            out[f"beliefs{i}"] = b
+            for k in ("regrets", "last", "sum", "avg", "root_means", "queries", "leaf_values"):
+                out[f"{k}{i}"] = s[k]
+            long_a = R.cfr_solve(D, F, b, [1024], lb, pl, num_iters=1024, net_w=w, want=("avg",))
+            long_b = RF.cfr_solve(D, F, b, [1024], lb, pl, num_iters=1024, net_w=w, want=("avg",))
+            out[f"mu1024_nofma{i}"] = long_a["root_means"][0]
+            out[f"mu1024_fast{i}"] = long_b["root_means"][0]
+        np.savez_compressed(os.path.join(OUT, f"cfr_net_{D}x{F}.npz"), **out)
+
+    # ---- full-tree linear CFR (BASELINE config 0): exploitability after 1024 iterations, both builds
+    out = {}
+    for (D, F) in [(1, 2), (1, 3), (1, 4)]:
+        A, H, Q = game_dims(D, F)
+        b = np.full((2, H), 1.0 / H)
+        for name, lib in (("nofma", R), ("fast", RF)):
+            s = lib.cfr_solve(D, F, b, [16, 1024], num_iters=1024, max_depth=100000, want=("avg",))
+            out[f"expl_{D}x{F}_{name}"] = np.stack([lib.exploitability(D, F, s["avg"][c]) for c in range(2)])
+            if name == "nofma":
+                out[f"avg16_{D}x{F}"] = s["avg"][0]
+                out[f"mu_{D}x{F}"] = s["root_means"]
+    np.savez_compressed(os.path.join(OUT, "fulltree.npz"), **out)
+
+    # ---- self-play walk (RlRunner::step) with the zero net: exact example streams
+    out = {}
+    for (D, F) in SHAPES:
+        for sl in (1, 0):
+            q, v = R.rl_runner(D, F, seed=7, n_games=4, num_iters=32, sample_leaf=bool(sl))
+            out[f"q_{D}x{F}_{sl}"] = q
+            out[f"v_{D}x{F}_{sl}"] = v
+    np.savez_compressed(os.path.join(OUT, "selfplay_zero.npz"), **out)
+
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

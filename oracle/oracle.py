@@ -73,18 +73,18 @@ class Oracle:
     def unroll_tree(self, D, F, last_bid=-1, player_id=0, max_depth=1000000):
         cap = 1 << 16
         out = np.zeros((cap, 6), np.int32)
-        n = self._f("unroll_tree")(D, F, last_bid, player_id, max_depth, _ptr(out, _ip), cap)
+        n = self._f("unroll_tree")(int(D), int(F), int(last_bid), int(player_id), int(max_depth), _ptr(out, _ip), cap)
         assert n > 0, n
         return out[:n].copy()
 
     def num_matches(self, D, F, hand, face):
-        return self._f("num_matches")(D, F, hand, face)
+        return self._f("num_matches")(int(D), int(F), int(hand), int(face))
 
     # -- small fp ---------------------------------------------------------------------------
     def win_probability(self, D, F, bet, beliefs):
         b = np.ascontiguousarray(beliefs, np.float64)
         out = np.zeros(F ** D, np.float64)
-        self._f("win_probability")(D, F, bet, _ptr(b, _dp), _ptr(out, _dp))
+        self._f("win_probability")(int(D), int(F), int(bet), _ptr(b, _dp), _ptr(out, _dp))
         return out
 
     def query(self, D, F, traverser, last_bid, player_id, r0, r1):
@@ -92,13 +92,14 @@ class Oracle:
         r0 = np.ascontiguousarray(r0, np.float64)
         r1 = np.ascontiguousarray(r1, np.float64)
         out = np.zeros(Q, np.float32)
-        n = self._f("query")(D, F, traverser, last_bid, player_id, _ptr(r0, _dp), _ptr(r1, _dp), _ptr(out, _fp))
+        n = self._f("query")(int(D), int(F), int(traverser), int(last_bid), int(player_id), _ptr(r0, _dp), _ptr(r1, _dp),
+                             _ptr(out, _fp))
         assert n == Q
         return out
 
     def synthetic_beliefs(self, H, seed):
         out = np.zeros((2, H), np.float64)
-        self._f("synthetic_beliefs")(H, seed, _ptr(out, _dp))
+        self._f("synthetic_beliefs")(int(H), int(seed), _ptr(out, _dp))
         return out
 
     # -- CFR --------------------------------------------------------------------------------
@@ -123,7 +124,7 @@ class Oracle:
         f = self._f("cfr_solve")
         f.argtypes = [C.c_int] * 4 + [_dp] + [C.c_int] * 4 + [C.c_double] * 3 + [_fp, C.c_int, C.c_int, _ip] + \
             [_dp] * 5 + [_fp, _fp, _dp]
-        n = f(D, F, last_bid, player_id, _ptr(b, _dp), num_iters, max_depth, int(linear_update), int(dcfr),
+        n = f(int(D), int(F), int(last_bid), int(player_id), _ptr(b, _dp), int(num_iters), int(max_depth), int(linear_update), int(dcfr),
               dcfr_alpha, dcfr_beta, dcfr_gamma, _ptr(w, _fp), hidden, Cn, _ptr(cps, _ip),
               _ptr(bufs.get("regrets"), _dp), _ptr(bufs.get("last"), _dp), _ptr(bufs.get("sum"), _dp),
               _ptr(bufs.get("avg"), _dp), _ptr(rm, _dp), _ptr(lv, _fp), _ptr(qs, _fp), _ptr(tv, _dp))

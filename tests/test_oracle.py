@@ -1,0 +1,185 @@
+"""CPU tests (no GPU): pin the plain-C oracle (oracle/cfr_oracle.c) against
+ (a) the known answers in the reference's own gtests (cited file:line, /root/reference/csrc/liars_dice/),
+ (b) golden fixtures generated from the compiled reference (oracle/make_golden.py), and
+ (c) the compiled reference itself when oracle/_ref is present (this container only).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle, available, game_dims
+
+SHAPES = [(1, 4), (1, 6), (2, 3)]
+
+
+def children(tree, i):
+    return list(range(tree[i, 2], tree[i, 3]))
+
+
+# ---------------------------------------------------------------- liars_dice_test.cc (2x6f)
+def test_game_integers(port):
+    D, F = 2, 6
+    A, H, Q = game_dims(D, F)
+    import ctypes as C
+    q, f = C.c_int(), C.c_int()
+    for a, (eq, ef) in {0: (1, 0), 1: (1, 1), 6: (2, 0)}.items():      # liars_dice_test.cc:46-62
+        port.lib.orc_unpack_action(D, F, a, C.byref(q), C.byref(f))
+        assert (q.value, f.value) == (eq, ef)
+    lo, hi = C.c_int(), C.c_int()
+    for lb, exp in {-1: (0, 24), 0: (1, 25), 11: (12, 25), 24: (25, 25)}.items():   # :64-94
+        port.lib.orc_bid_range(D, F, lb, C.byref(lo), C.byref(hi))
+        assert (lo.value, hi.value) == exp
+    assert [port.num_matches(D, F, 0, f) for f in range(6)] == [2, 0, 0, 0, 0, 0]          # :104-108
+    assert [port.num_matches(D, F, H - 1, f) for f in range(6)] == [2] * 6                  # :110-115
+    assert [port.num_matches(D, F, 5, f) for f in range(6)] == [2, 1, 1, 1, 1, 1]           # :117-121
+    tree = port.unroll_tree(D, F, -1, 0, 3)                                  # player alternation :96-102
+    for n in range(1, len(tree)):
+        assert tree[n, 1] == 1 - tree[tree[n, 4], 1]
+
+
+# ---------------------------------------------------------------- tree_test.cc
+def test_tree_known_answers(port):
+    t = port.unroll_tree(1, 2)                                     # tree_test.cc:20-34
+    assert len(t) == 31
+    assert children(t, 0) == [1, 2, 3, 4] and children(t, 1) == [5, 6, 7, 8] and children(t, 2) == [9, 10, 11]
+    assert children(t, 15) == [25, 26] and children(t, 16) == [27] and children(t, 25) == [30]
+    t = port.unroll_tree(2, 6, 22, 0, 0)                           # :36-52
+    assert len(t) == 1 and t[0, 4] == -1 and children(t, 0) == []
+    t = port.unroll_tree(2, 6, 22, 0, 1)                           # :54-70
+    assert len(t) == 3 and children(t, 0) == [1, 2] and t[1, 4] == 0 and t[2, 4] == 0
+    t = port.unroll_tree(2, 6, 22, 0, 2)                           # :72-89
+    assert len(t) == 4 and t[3, 4] == 1
+    t = port.unroll_tree(2, 6, 21, 0, 2)                           # :91-105
+    assert len(t) == 7 and children(t, 0) == [1, 2, 3] and children(t, 1) == [4, 5] and children(t, 2) == [6]
+
+
+def test_tree_is_breadth_first_prefix(port):                       # tree_test.cc:107-125
+    full = port.unroll_tree(1, 5)
+    for d in range(20):
+        sub = port.unroll_tree(1, 5, -1, 0, d)
+        assert (full[:len(sub), :2] == sub[:, :2]).all()
+        has = sub[:, 3] > sub[:, 2]
+        assert (full[:len(sub)][has] == sub[has]).all()
+
+
+def test_trees_match_golden(port, golden):
+    g = golden("trees.npz")
+    for key in g.files:
+        _, D, F, lb, pl, md = key.split("_")
+        t = port.unroll_tree(int(D), int(F), int(lb), int(pl), int(md))
+        assert t.shape == g[key].shape and (t == g[key]).all(), key
+
+
+# ---------------------------------------------------------------- subgame_solving_test.cc:48-104
+@pytest.mark.parametrize("D,F", [(1, 6), (2, 3)])
+def test_win_probability_one_hot(port, D, F):
+    A, H, Q = game_dims(D, F)
+    for op in range(H):
+        b = np.zeros(H); b[op] = 1
+        for bet in range(A - 1):
+            quantity, face = 1 + bet // F, bet % F
+            v = port.win_probability(D, F, bet, b)
+            for my in range(H):
+                m = port.num_matches(D, F, my, face) + port.num_matches(D, F, op, face)
+                assert v[my] == (1.0 if m >= quantity else 0.0)
+
+
+def test_prob_normalisation_tiny(port):                           # subgame_solving_test.cc:298-310
+    probs = np.array([2.93185e-81, 3.00956e-81, 3.17805e-81, 8.80785e-81])
+    q = port.query(1, 4, 0, -1, 0, probs, probs)
+    assert abs(q[2 + 9:2 + 9 + 4].astype(np.float64).sum() - 1.0) < 1e-6
+
+
+def test_query_layout_roundtrip(port):                            # subgame_solving_test.cc:267-296
+    D, F = 1, 3
+    A, H, Q = game_dims(D, F)
+    b1 = np.arange(H, dtype=np.float64); b1 /= b1.sum()
+    b2 = np.arange(H) + 0.5; b2 /= b2.sum()
+    tree = port.unroll_tree(D, F)
+    for trav in (0, 1):
+        for node in tree:
+            if node[0] == A - 1:
+                continue
+            q = port.query(D, F, trav, node[0], node[1], b1, b2)
+            assert q[0] == node[1] and q[1] == trav
+            onehot = q[2:2 + A]
+            assert onehot.sum() == (0 if node[0] < 0 else 1) and (node[0] < 0 or onehot[node[0]] == 1)
+            assert np.allclose(q[2 + A:2 + A + H], b1, atol=1e-6) and np.allclose(q[2 + A + H:], b2, atol=1e-6)
+
+
+# ---------------------------------------------------------------- CFR convergence thresholds of the reference tests
+def test_cfr_1x2f_linear_exploitability(port):                    # subgame_solving_test.cc:162-179
+    b = np.full((2, 2), 0.5)
+    s = port.cfr_solve(1, 2, b, [180], num_iters=180, max_depth=1000, want=("avg",))
+    e = port.exploitability(1, 2, s["avg"][0])
+    assert 0.0 <= e.mean() < 1e-3
+
+
+def test_fulltree_golden(port, golden):
+    g = golden("fulltree.npz")
+    for (D, F) in [(1, 2), (1, 3), (1, 4)]:
+        A, H, Q = game_dims(D, F)
+        b = np.full((2, H), 1.0 / H)
+        s = port.cfr_solve(D, F, b, [16, 1024], num_iters=1024, max_depth=100000, want=("avg",))
+        assert np.array_equal(s["avg"][0], g[f"avg16_{D}x{F}"])              # bit-exact vs reference (-ffp-contract=off)
+        assert np.array_equal(s["root_means"], g[f"mu_{D}x{F}"])
+        e = np.stack([port.exploitability(D, F, s["avg"][c]) for c in range(2)])
+        assert np.array_equal(e, g[f"expl_{D}x{F}_nofma"])
+        # the reference's own two builds bracket the self-noise
+        assert abs(e[1].mean() - g[f"expl_{D}x{F}_fast"][1].mean()) < 5e-4
+
+
+# ---------------------------------------------------------------- golden trajectories from the compiled reference
+@pytest.mark.parametrize("D,F", SHAPES)
+def test_cfr_zero_net_bit_exact_vs_golden(port, golden, D, F):
+    g = golden(f"cfr_zero_{D}x{F}.npz")
+    cps = list(g["checkpoints"])
+    for i, (lb, pl) in enumerate(g["roots"]):
+        s = port.cfr_solve(D, F, g[f"beliefs{i}"], cps, lb, pl, num_iters=64)
+        for k in ("regrets", "last", "sum", "avg", "root_means"):
+            assert np.array_equal(s[k], g[f"{k}{i}"]), (k, i)
+
+
+@pytest.mark.parametrize("D,F", SHAPES)
+def test_cfr_net_short_horizon_vs_golden(port, golden, net_weights, D, F):
+    g = golden(f"cfr_net_{D}x{F}.npz")
+    w = net_weights(D, F)
+    assert np.allclose([w.astype(np.float64).sum(), np.abs(w).astype(np.float64).sum()], g["w_checksum"], rtol=1e-9)
+    assert np.array_equal(w[:8], g["w_head"])
+    cps = list(g["checkpoints"])
+    for i, (lb, pl) in enumerate(g["roots"]):
+        s = port.cfr_solve(D, F, g[f"beliefs{i}"], cps, lb, pl, num_iters=16, net_w=w)
+        # C fp32 MLP vs ATen fp32 MLP: 1e-6-level leaf differences, amplified by regret matching over iterations
+        assert np.abs(s["queries"][0] - g[f"queries{i}"][0]).max() < 1e-6
+        assert np.abs(s["leaf_values"][0] - g[f"leaf_values{i}"][0]).max() < 2e-6
+        for k in ("regrets", "sum", "avg", "last", "root_means"):
+            assert np.abs(s[k][0] - g[f"{k}{i}"][0]).max() < 1e-5, (k, i)     # after 1 step
+            assert np.abs(s[k][1] - g[f"{k}{i}"][1]).max() < 1e-4, (k, i)     # after 2 steps
+        assert np.abs(s["root_means"][2] - g[f"root_means{i}"][2]).max() < 1e-3
+
+
+def test_selfplay_walk_bit_exact_vs_golden(port, golden):
+    g = golden("selfplay_zero.npz")
+    for (D, F) in SHAPES:
+        for sl in (1, 0):
+            q, v = port.rl_runner(D, F, seed=7, n_games=4, num_iters=32, sample_leaf=bool(sl))
+            assert np.array_equal(q, g[f"q_{D}x{F}_{sl}"]) and np.array_equal(v, g[f"v_{D}x{F}_{sl}"])
+
+
+# ---------------------------------------------------------------- live cross-check with the compiled reference
+@pytest.mark.skipif(not available("ref_nofma"), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_vs_compiled_reference_live():
+    P, R = Oracle("port"), Oracle("ref_nofma")
+    for (D, F) in SHAPES:
+        A, H, Q = game_dims(D, F)
+        assert np.array_equal(P.synthetic_beliefs(H, 11), R.synthetic_beliefs(H, 11))
+        b = P.synthetic_beliefs(H, 5)
+        for lb, pl in [(-1, 0), (4, 1)]:
+            x = P.cfr_solve(D, F, b, [0, 1, 5, 40], lb, pl, num_iters=40)
+            y = R.cfr_solve(D, F, b, [0, 1, 5, 40], lb, pl, num_iters=40)
+            for k in ("regrets", "last", "sum", "avg", "root_means", "traverser_values"):
+                assert np.array_equal(x[k], y[k]), (D, F, lb, k)
+        qa, va = P.rl_runner(D, F, seed=3, n_games=2, num_iters=24)
+        qb, vb = R.rl_runner(D, F, seed=3, n_games=2, num_iters=24)
+        assert np.array_equal(qa, qb) and np.array_equal(va, vb)
