@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — CFR subgame-iters/sec on the BASELINE.json workload.
+
+One "step" = one wave: K concurrent 1x6f depth-2 root subgames (last_bid = -1, random beliefs) each solved with 1024 CFR
+iterations, the leaf value net (Net2 256x2 + LayerNorm, random init seed 0) evaluated on every iteration — the reference's
+`build_solver` + `multistep` + `update_value_network` for every subgame of the wave (subgame_solving.cc:791,666,672).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                      # this repo's CUDA path (1 GPU)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...              # N GPUs, K subgames per GPU (weak scaling)
+    python bench.py --impl reference ...                               # the reference's own CPU path on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = device-resident wave solve (state re-initialised on the device each step);
+`e2e` = the same through the host-buffer C-ABI calls (cfrb_begin_wave H2D + cfrb_run + cfrb_examples D2H, + NCCL gather
+of the examples to rank 0 when N > 1) timed end to end.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cfr_subgame_iters_per_sec"
+UNIT = "subgame-iters/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--subgames", type=int, default=8192, help="concurrent subgames per GPU")
+    ap.add_argument("--iters", type=int, default=1024)
+    ap.add_argument("--dice", type=int, default=1)
+    ap.add_argument("--faces", type=int, default=6)
+    ap.add_argument("--net", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="subgames in the CPU-baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def dims(D, F):
+    A = 1 + 2 * D * F
+    H = F ** D
+    return A, H, 2 + A + 2 * H
+
+
+def workload_beliefs(n, H, first):
+    """Synthetic random beliefs b_p[h] = u / sum(u), u ~ U(0,1); subgame g of the whole job uses counter-based stream g."""
+    out = np.empty((n, 2, H), np.float64)
+    for i in range(n):
+        out[i] = np.random.Generator(np.random.Philox(key=first + i)).random((2, H))
+    out /= out.sum(-1, keepdims=True)
+    return out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def script_net_file(D, F):
+    import torch
+    from rebel_b200.models import make_selfplay_net
+    path = os.path.join(tempfile.mkdtemp(prefix="cfrb_bench_"), "net2.torchscript")
+    torch.jit.script(make_selfplay_net(D, F, seed=0)).save(path)
+    return path
+
+
+def cpu_reference_rate(D, F, iters, n, beliefs, threads=None):
+    """The reference's CPU implementation of the same workload sample (oracle/_ref when the reference compiled, else the
+    C port) on the host cores.  Returns (rate, info)."""
+    from oracle.oracle import Oracle, available
+    cores = os.cpu_count() or 1
+    if available("ref_fast"):
+        threads = threads or cores
+        ref = Oracle("ref_fast")
+        secs = ref.bench_solve(D, F, n, script_path=script_net_file(D, F), threads=threads, num_iters=iters, beliefs=beliefs[:n])
+        kind = "reference"
+    else:
+        import torch  # noqa: F401
+        from rebel_b200.models import flatten_state_dict, make_selfplay_net
+        port = Oracle("port")
+        w = flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict())
+        secs = port.bench_solve(D, F, n, net_w=w, num_iters=iters, beliefs=beliefs[:n])
+        kind, threads = "port", 1
+    rate = n * iters / secs
+    return rate, {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                  "sample": f"{n} of the workload's root subgames x {iters} iters, build_solver+multistep with TorchScript Net2 on CPU, "
+                            f"{secs:.1f} s wall" if kind == "reference" else f"{n} root subgames x {iters} iters, C port, {secs:.1f} s wall"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    D, F = args.dice, args.faces
+    A, H, Q = dims(D, F)
+    from oracle.oracle import available
+    cores = os.cpu_count() or 1
+    per_core = 6 if available("ref_fast") else 1
+    n = args.cpu_sample or max(cores * per_core if available("ref_fast") else 2, 2)
+    beliefs = workload_beliefs(n, H, 0)
+    for _ in range(args.warmup):
+        cpu_reference_rate(D, F, args.iters, min(n, cores if available("ref_fast") else 1), beliefs)
+    t0 = time.time()
+    rates, info = [], None
+    for _ in range(args.steps):
+        r, info = cpu_reference_rate(D, F, args.iters, n, beliefs)
+        rates.append(r)
+    wall = time.time() - t0
+    value = n * args.iters * args.steps / sum(n * args.iters / r for r in rates)
+    info["value"] = value
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 (CFR) / f32 (value net)", "data": "synthetic",
+        "config": workload_config(args, n), "cpu_baseline": info,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def workload_config(args, k):
+    return {"workload": f"{args.dice}x{args.faces}f Liar's Dice, depth-2 root subgames (last_bid=-1), {k} concurrent subgames per GPU, "
+                        f"{args.iters} linear-CFR iterations each, Net2(256x2,LayerNorm) leaf value net every iteration",
+            "subgames_per_gpu": k, "cfr_iters": args.iters, "max_depth": 2, "value_net": "Net2 n_hidden=256 n_layers=2 layer_norm, random init seed 0",
+            "beliefs": "random (Philox counter streams)"}
+
+
+def run_b200(args):
+    import torch
+    import rebel_b200 as rb
+    from rebel_b200.models import flatten_state_dict, make_selfplay_net
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun on this node
+        port = 29500 + os.getpid() % 1000
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", str(port)] + sys.argv)
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    D, F, K, iters = args.dice, args.faces, args.subgames, args.iters
+    A, H, Q = dims(D, F)
+
+    # ---- value-net weights: rank 0 owns them, NCCL broadcast to the other ranks (ModelLocker::updateModel analogue)
+    nflat = 256 * Q + 3 * 256 + 256 * 256 + 3 * 256 + H * 256 + H
+    if rank == 0:
+        wt = torch.from_numpy(flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict())).to(dev)
+    else:
+        wt = torch.empty(nflat, dtype=torch.float32, device=dev)
+    if dist:
+        dist.broadcast(wt, src=0)
+    w = wt.cpu().numpy()
+
+    mode, mode_name = rb.NET_FP32, "fp32"
+    if args.net in ("auto", "tc"):
+        try:
+            rb.WaveSolver(D, F, 1, net_mode=rb.NET_TC_F16, device=local).close()
+            mode, mode_name = rb.NET_TC_F16, "tc_f16"
+        except rb.CfrbError:
+            if args.net == "tc":
+                raise
+    S = rb.WaveSolver(D, F, K, num_iters=iters, net_mode=mode, device=local)
+    S.set_weights(w, version=1)
+
+    # ---- this rank's shard of the job: subgames [rank*K, (rank+1)*K); inputs staged in pinned host memory
+    beliefs64 = workload_beliefs(K, H, rank * K)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+    t_b = pin((K, 2, H), torch.float32); t_b.numpy()[:] = beliefs64
+    t_lb = pin((K,), torch.int32); t_lb.fill_(-1)
+    t_pl = pin((K,), torch.int32); t_pl.zero_()
+    t_act = pin((K,), torch.int32); t_act.numpy()[:] = np.random.RandomState(rank).randint(0, iters + 1, size=K)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if not dist:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ================= device-resident throughput (`value`) =================
+    S.begin(t_lb.numpy(), t_pl.numpy(), t_b.numpy(), t_act.numpy())
+    for _ in range(args.warmup):
+        S.reset(stream); S.run(iters, stream)
+    S.set_profiling(True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = S.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    net_ms = 0.0
+    e0.record()
+    for _ in range(args.steps):
+        flush.fill_(1)                      # evict L2 between steps (inside the timed region)
+        S.reset(stream)
+        S.run(iters, stream)
+        net_ms += S.last_run_ms()[1]        # waits for this step; value-net kernel time from per-launch CUDA events
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = S.kernel_launches - launches0
+    S.set_profiling(False)
+    value = world * K * iters * args.steps / (ms * 1e-3)
+
+    # ================= end to end through the host-buffer C ABI (`e2e`) =================
+    ex_all = None
+    def e2e_step():
+        S.begin(t_lb.numpy(), t_pl.numpy(), t_b.numpy(), t_act.numpy())      # H2D from pinned memory
+        S.run(iters, stream)
+        q, v = S.examples()                                                   # D2H: training examples of the wave
+        if dist:                                                              # gather example blocks on rank 0 (NCCL)
+            blk = torch.from_numpy(np.concatenate([q.reshape(2 * K, Q), v.reshape(2 * K, H)], 1)).to(dev)
+            out = [torch.empty_like(blk) for _ in range(world)] if rank == 0 else None
+            dist.gather(blk, out, dst=0)
+            return out
+        return q, v
+    for _ in range(min(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        ex_all = e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+    e2e_value = world * K * iters * args.steps / (ms_e2e * 1e-3)
+    h2d = K * 2 * H * 4 + 3 * K * 4
+    d2h = K * 2 * H * 4
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    # ================= roofline of the dominant kernel (value net) + CPU baseline =================
+    peaks = load_peaks()
+    rows = S.leaf_rows
+    n_net = args.steps * iters
+    flops_launch = 2.0 * rows * (256 * Q + 256 * 256 + 256 * H)
+    avg_net_ms = net_ms / max(n_net, 1)
+    achieved = flops_launch / (avg_net_ms * 1e-3) / 1e12 if avg_net_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "leaf value net (Net2 forward over all pseudo-leaf rows of the wave)",
+                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                "traffic": None, "peak_source": peaks["src"], "avg_launch_ms": avg_net_ms, "rows_per_launch": rows,
+                "flops_per_launch": flops_launch, "share_of_step": net_ms / ms if ms > 0 else None,
+                "cfr_tables_algorithmic_GBps": (4 * H * (90 + 6 * 45) + 4 * 66 * (Q + H) + 8 * H) * K * iters * args.steps / max(ms - net_ms, 1e-9) / 1e6
+                if (D, F) == (1, 6) else None}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (CFR tables) / " + ("f16 operands, f32 accumulate (value net, tcgen05)" if mode == rb.NET_TC_F16 else "f32 (value net)"),
+        "data": "synthetic", "config": dict(workload_config(args, K), value_net_kernel=mode_name, parallelism=f"dp{world}",
+                                           l2="256 MiB memset between steps, inside the timed region"),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.oracle import available
+        cores = os.cpu_count() or 1
+        n = args.cpu_sample or (cores * 8 if available("ref_fast") else 3)
+        _, info = cpu_reference_rate(D, F, iters, n, beliefs64)
+        out["cpu_baseline"] = info
+    print(json.dumps(out), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

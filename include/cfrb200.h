@@ -120,6 +120,14 @@ uint64_t cfrb_weights_version(const cfrb_handle* h);
 int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const int32_t* player_id,
                     const float* beliefs, const int32_t* act_iteration);
 
+/* Re-initialise the solver state of the CURRENT wave on the device (same roots, beliefs and act_iterations; no
+ * host->device traffic): what constructing fresh CFR solvers for the same subgames would do. */
+int cfrb_reset_wave(cfrb_handle* h, void* cuda_stream);
+
+/* Profiling switch: when on, cfrb_run brackets every value-net launch with CUDA events on the launching stream
+ * so that cfrb_last_run_ms can report the summed device time of the value-net kernels of the last run. */
+int cfrb_set_profiling(cfrb_handle* h, int32_t on);
+
 /* Advance every subgame of the wave by `iters` CFR iterations (iteration i has traverser i % 2,
  * CFR::multistep subgame_solving.cc:666-670), asynchronously on `cuda_stream` (a cudaStream_t; NULL = the
  * handle's own stream). */
@@ -148,6 +156,10 @@ int cfrb_load_state(cfrb_handle* h, const float* regrets, const float* last_stra
  * [rows][H] for all pseudo-leaves of the wave in (subgame, leaf) order; returns the number of rows,
  * writes at most cap_rows. */
 int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, float* scalers, int32_t cap_rows);
+
+/* Debug taps of the tensor-core value net (CFRB_NET_TC_F16 only): re-runs it on the current query tiles and returns
+ * the raw fp32 accumulators of layer 1 and layer 2 for the first 128 rows, each [128][256]. */
+int cfrb_debug_net_taps(cfrb_handle* h, float* d1, float* d2);
 
 /* Exploitability (best-response values of both players, compute_exploitability2) of a full-tree strategy
  * given as dense [N_full][H][A] fp32, evaluated on the GPU. out2 = {br0, br1}. */

@@ -654,14 +654,15 @@ void orc_synthetic_beliefs(int H, int seed, double* out) {
 
 /* Single-thread port baseline (kind "port"): n root subgames, build + multistep.  Returns seconds. */
 double orc_bench_solve(int D, int F, int last_bid, int player_id, int num_iters, int max_depth, int n_subgames, int seed0,
-                       const float* net_w, int hidden, double* root_means_out) {
+                       const float* net_w, int hidden, double* root_means_out, const double* beliefs_in) {
   orc_game g = game_make(D, F);
   int H = g.H;
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
   double* b = (double*)malloc(sizeof(double) * 2 * H);
   for (int i = 0; i < n_subgames; ++i) {
-    orc_synthetic_beliefs(H, seed0 + i, b);
+    if (beliefs_in) memcpy(b, beliefs_in + (size_t)i * 2 * H, sizeof(double) * 2 * H);
+    else orc_synthetic_beliefs(H, seed0 + i, b);
     orc_cfr* s = orc_cfr_create(D, F, last_bid, player_id, b, num_iters, max_depth, 1, 0, 0, 0, 0, net_w, hidden);
     for (int it = 0; it < num_iters; ++it) orc_cfr_step(s, it % 2);
     if (root_means_out)

@@ -165,21 +165,25 @@ class Oracle:
 
     # -- timed baselines --------------------------------------------------------------------
     def bench_solve(self, D, F, n_subgames, seed0=0, last_bid=-1, player_id=0, num_iters=1024, max_depth=2,
-                    net_w=None, hidden=256, script_path=None, threads=1, want_means=False):
+                    net_w=None, hidden=256, script_path=None, threads=1, want_means=False, beliefs=None):
         """Seconds to solve n root subgames with synthetic beliefs.  port: single thread, C Net2 from flat
         weights.  ref_*: `threads` std::threads, TorchScript Net2 from script_path (zero net if None)."""
         A, H, Q = game_dims(D, F)
         rm = np.zeros((n_subgames, 2, H), np.float64) if want_means else None
+        bl = None
+        if beliefs is not None:
+            bl = np.ascontiguousarray(beliefs, np.float64)
+            assert bl.shape == (n_subgames, 2, H)
         f = self._f("bench_solve")
         if self.kind == "port":
             w = None if net_w is None else np.ascontiguousarray(net_w, np.float32)
-            f.argtypes = [C.c_int] * 8 + [_fp, C.c_int, _dp]
+            f.argtypes = [C.c_int] * 8 + [_fp, C.c_int, _dp, _dp]
             secs = f(D, F, last_bid, player_id, num_iters, max_depth, n_subgames, seed0, _ptr(w, _fp), hidden,
-                     _ptr(rm, _dp))
+                     _ptr(rm, _dp), _ptr(bl, _dp))
         else:
-            f.argtypes = [C.c_int] * 8 + [C.c_char_p, C.c_int, _dp]
+            f.argtypes = [C.c_int] * 8 + [C.c_char_p, C.c_int, _dp, _dp]
             secs = f(D, F, last_bid, player_id, num_iters, max_depth, n_subgames, seed0,
-                     (script_path or "").encode(), threads, _ptr(rm, _dp))
+                     (script_path or "").encode(), threads, _ptr(rm, _dp), _ptr(bl, _dp))
             if secs < 0:
                 raise RuntimeError(self._f("last_error")().decode())
         return (secs, rm) if want_means else secs

@@ -353,7 +353,7 @@ void ref_synthetic_beliefs(int H, int seed, double* out /*[2][H]*/) {
 // [n][2][H].
 double ref_bench_solve(int D, int F, int last_bid, int player_id, int num_iters, int max_depth,
                        int n_subgames, int seed0, const char* script_path, int threads,
-                       double* root_means_out) {
+                       double* root_means_out, const double* beliefs_in /*[n][2][H] or NULL*/) {
   try {
     torch::set_num_threads(1);
     Game game(D, F);
@@ -376,7 +376,8 @@ double ref_bench_solve(int D, int F, int last_bid, int player_id, int num_iters,
           int i = next.fetch_add(1);
           if (i >= n_subgames) break;
           std::vector<double> b(2 * H);
-          ref_synthetic_beliefs(H, seed0 + i, b.data());
+          if (beliefs_in) std::copy(beliefs_in + (size_t)i * 2 * H, beliefs_in + (size_t)(i + 1) * 2 * H, b.begin());
+          else ref_synthetic_beliefs(H, seed0 + i, b.data());
           auto solver = build_solver(game, PartialPublicState{last_bid, player_id},
                                      to_beliefs(b.data(), H), params, nets[t]);
           solver->multistep();

@@ -55,11 +55,14 @@ def lib():
     L.cfrb_weights_version.restype = C.c_uint64
     L.cfrb_begin_wave.argtypes = [vp, C.c_int32, _ip, _ip, _fp, _ip]
     L.cfrb_run.argtypes = [vp, C.c_int32, vp]
+    L.cfrb_reset_wave.argtypes = [vp, vp]
+    L.cfrb_set_profiling.argtypes = [vp, C.c_int32]
     L.cfrb_fetch.argtypes = [vp] + [_fp] * 6
     L.cfrb_examples.argtypes = [vp, _fp, _fp]
     L.cfrb_load_state.argtypes = [vp, _fp, _fp, _fp, _fp, _ip, C.c_int32]
     L.cfrb_debug_leaf_io.argtypes = [vp, _fp, _fp, _fp, C.c_int32]
     L.cfrb_exploitability.argtypes = [vp, _fp, _fp]
+    L.cfrb_debug_net_taps.argtypes = [vp, _fp, _fp]
     L.cfrb_kernel_launches.argtypes = [vp]
     L.cfrb_kernel_launches.restype = C.c_int64
     L.cfrb_wave_leaf_rows.argtypes = [vp]
@@ -134,6 +137,12 @@ class WaveSolver:
         _check(lib().cfrb_begin_wave(self._h, n, _p(lb, _ip), _p(pl, _ip), _p(b, _fp), _p(act, _ip)))
         self.n = n
 
+    def reset(self, stream=None):
+        _check(lib().cfrb_reset_wave(self._h, C.c_void_p(stream) if stream else None))
+
+    def set_profiling(self, on):
+        _check(lib().cfrb_set_profiling(self._h, int(on)))
+
     def run(self, iters, stream=None):
         _check(lib().cfrb_run(self._h, iters, C.c_void_p(stream) if stream else None))
 
@@ -176,6 +185,12 @@ class WaveSolver:
         s = np.zeros(max(rows, 1), np.float32)
         _check(lib().cfrb_debug_leaf_io(self._h, _p(q, _fp), _p(o, _fp), _p(s, _fp), rows))
         return q[:rows], o[:rows], s[:rows]
+
+    def net_taps(self):
+        d1 = np.zeros((128, 256), np.float32)
+        d2 = np.zeros((128, 256), np.float32)
+        _check(lib().cfrb_debug_net_taps(self._h, _p(d1, _fp), _p(d2, _fp)))
+        return d1, d2
 
     def exploitability(self, full_strategy):
         s = np.ascontiguousarray(full_strategy, np.float32)

@@ -14,6 +14,7 @@
 // average-strategy accumulation) fused with the forward half of iteration i (reach -> value-net query rows,
 // scalers, terminal payoffs).  The value-net kernel runs between two launches.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -106,7 +107,7 @@ __device__ void cfr_forward(const CfrDev& p, int k, int trav, float* reach0, flo
   group_sync<G>();
   // ---- query rows (write_query_to, subgame_solving.cc:104-123).  eps = 1e-80 of the reference underflows in
   // fp32; its only effect in fp64 is "all-zero reach -> uniform", which is reproduced explicitly.
-  if (p.X != nullptr) {
+  if (p.X != nullptr || p.Xh != nullptr) {
     const int Qp = p.Qpad;
     for (int it = lane; it < t.L * Qp; it += G) {
       const int r = it / Qp, q = it % Qp;
@@ -127,7 +128,14 @@ __device__ void cfr_forward(const CfrDev& p, int k, int trav, float* reach0, flo
         const float s = lsum[2 * r + 1];
         v = s > 0.f ? reach1[n * H + (q - 2 - A - H)] / s : 1.f / H;
       }
-      p.X[(size_t)(row0 + r) * Qp + q] = v;
+      if (p.X != nullptr) {
+        p.X[(size_t)(row0 + r) * Qp + q] = v;
+      } else {
+        // fp16 tile in UMMA K-major core-matrix order (leaf_mlp_tc.cuh umma_kmajor_offset_halves, R = 128)
+        const int R = row0 + r, rr = R & 127;
+        reinterpret_cast<__half*>(p.Xh)[(size_t)(R >> 7) * 128 * Qp + (q >> 3) * 1024 + (rr >> 3) * 64 + (rr & 7) * 8 + (q & 7)] =
+            __float2half_rn(v);
+      }
     }
   }
   // ---- terminals (compute_expected_terminal_values, subgame_solving.cc:80-98; win probability :765-789)

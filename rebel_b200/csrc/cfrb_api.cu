@@ -15,6 +15,7 @@
 #include "cfr_kernels.cuh"
 #include "cfr_tree.h"
 #include "leaf_mlp_simt.cuh"
+#include "leaf_mlp_tc.cuh"
 
 namespace {
 
@@ -60,6 +61,9 @@ struct cfrb_handle {
   int table_stride = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  bool profiling = false;
+  std::vector<cudaEvent_t> net_ev;   // pairs around value-net launches (profiling mode)
+  int net_ev_used = 0;
   // device: templates
   DevBuf<cfrb::TemplateDev> d_tmpl;
   DevBuf<int> d_child_begin, d_nchild, d_last_bid, d_kind, d_slot, d_level_begin, d_pleaf_node, d_term_node;
@@ -72,6 +76,10 @@ struct cfrb_handle {
   DevBuf<float> d_R, d_Sg, d_S, d_Snap, d_vterm, d_X, d_out, d_scaler, d_scratch;
   // device: weights
   DevBuf<float> d_w;
+  DevBuf<uint8_t> d_blob;      // tensor-core weight blob (leaf_mlp_tc.cuh BlobLayout)
+  DevBuf<__half> d_Xh;         // fp16 query tiles in UMMA order
+  DevBuf<float> d_dbg;         // [2][128][256] debug taps
+  int num_sms = 0;
   cfrb::NetDev net{};
   bool have_weights = false;
   uint64_t weights_version = 0;
@@ -106,7 +114,8 @@ int cfrb_destroy(cfrb_handle* h) {
   h->d_sg_player.release(); h->d_sg_row_off.release(); h->d_sg_act.release(); h->d_beliefs.release();
   h->d_mu.release(); h->d_steps.release(); h->d_R.release(); h->d_Sg.release(); h->d_S.release();
   h->d_Snap.release(); h->d_vterm.release(); h->d_X.release(); h->d_out.release(); h->d_scaler.release();
-  h->d_scratch.release(); h->d_w.release();
+  h->d_scratch.release(); h->d_w.release(); h->d_blob.release(); h->d_Xh.release(); h->d_dbg.release();
+  for (auto e : h->net_ev) cudaEventDestroy(e);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -126,7 +135,6 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   if (cfg->num_dice < 1 || cfg->num_faces < 1 || cfg->max_depth < 1 || cfg->max_subgames < 1)
     return fail(CFRB_EINVAL, "num_dice, num_faces, max_depth, max_subgames must be >= 1");
   if (cfg->net_mode < CFRB_NET_ZERO || cfg->net_mode > CFRB_NET_TC_F16) return fail(CFRB_EINVAL, "bad net_mode");
-  if (cfg->net_mode == CFRB_NET_TC_F16) return fail(CFRB_EINVAL, "CFRB_NET_TC_F16 is not built into this library yet");
   if (cfg->net_mode != CFRB_NET_ZERO && cfg->hidden != 256) return fail(CFRB_EINVAL, "only hidden == 256 is built");
   h->g = cfrb::GameShape(cfg->num_dice, cfg->num_faces);
   const auto& g = h->g;
@@ -194,7 +202,19 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   CK(h->d_R.alloc(tab)); CK(h->d_Sg.alloc(tab)); CK(h->d_S.alloc(tab)); CK(h->d_Snap.alloc(tab));
   CK(h->d_vterm.alloc((size_t)K * std::max(h->Tmax, 1) * g.H));
   const size_t rows_cap = (size_t)K * std::max(h->Lmax, 1);
-  CK(h->d_X.alloc(rows_cap * h->Qpad)); CK(h->d_out.alloc(rows_cap * h->Hout)); CK(h->d_scaler.alloc(rows_cap));
+  CK(h->d_X.alloc(cfg->net_mode == CFRB_NET_TC_F16 ? 1 : rows_cap * h->Qpad));
+  CK(h->d_out.alloc(rows_cap * h->Hout)); CK(h->d_scaler.alloc(rows_cap));
+  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  if (cfg->net_mode == CFRB_NET_TC_F16) {
+    if (g.H > cfrb::tc::kNout) return fail(CFRB_EINVAL, "CFRB_NET_TC_F16 supports num_hands <= 16");
+    const size_t tiles = (rows_cap + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
+    CK(h->d_Xh.alloc(tiles * cfrb::tc::kTileM * h->Qpad));
+    CK(cudaMemset(h->d_Xh.p, 0, tiles * cfrb::tc::kTileM * h->Qpad * sizeof(__half)));
+    CK(h->d_dbg.alloc(2 * cfrb::tc::kTileM * cfrb::tc::kHid));
+    const cfrb::tc::BlobLayout L(h->Qpad);
+    if (L.smem_bytes > max_optin) return fail(CFRB_EINVAL, "tensor-core value net does not fit shared memory for this game shape");
+    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+  }
   CK(cudaMemset(h->d_wave.p, 0, 2 * sizeof(int)));
   CK(cudaMemset(h->d_Snap.p, 0, tab * sizeof(float)));
   CK(cudaMemset(h->d_out.p, 0, rows_cap * h->Hout * sizeof(float)));
@@ -220,7 +240,7 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   d.sg_act_iter = h->d_sg_act.p; d.beliefs = h->d_beliefs.p; d.mu = h->d_mu.p; d.steps = h->d_steps.p;
   d.R = h->d_R.p; d.Sg = h->d_Sg.p; d.S = h->d_S.p; d.Snap = h->d_Snap.p; d.table_stride = h->table_stride;
   d.vterm = h->d_vterm.p; d.vterm_stride = std::max(h->Tmax, 1) * g.H;
-  d.X = h->d_X.p; d.Xh = nullptr; d.net_out = h->d_out.p; d.scaler = h->d_scaler.p;
+  d.X = cfg->net_mode == CFRB_NET_TC_F16 ? nullptr : h->d_X.p; d.Xh = h->d_Xh.p; d.net_out = h->d_out.p; d.scaler = h->d_scaler.p;
   d.scratch = h->group == 32 ? nullptr : h->d_scratch.p; d.scratch_stride = h->smem_per_group;
   d.linear = cfg->linear_update; d.dcfr = cfg->dcfr;
   d.dcfr_alpha = (float)cfg->dcfr_alpha; d.dcfr_beta = (float)cfg->dcfr_beta; d.dcfr_gamma = (float)cfg->dcfr_gamma;
@@ -257,8 +277,10 @@ int cfrb_unroll_tree(int32_t num_dice, int32_t num_faces, int32_t last_bid, int3
   for (int n = 0; n < t.N && n < cap; ++n) {
     out[n].last_bid = t.last_bid[n];
     out[n].player_id = player_id ^ (t.depth[n] & 1);
-    out[n].children_begin = t.nchild[n] ? t.child_begin[n] : 0;
-    out[n].children_end = t.nchild[n] ? t.child_begin[n] + t.nchild[n] : 0;
+    // like the reference, a processed node with an empty bid range (terminal above the depth limit) keeps
+    // children_begin == children_end == (tree size at that moment); unprocessed nodes keep 0/0 (tree.h:59-62)
+    out[n].children_begin = t.child_begin[n];
+    out[n].children_end = t.child_begin[n] + t.nchild[n];
     out[n].parent = t.parent[n];
     out[n].depth = t.depth[n];
   }
@@ -271,8 +293,10 @@ int cfrb_tree_template(const cfrb_handle* h, int32_t last_bid, int32_t player_id
   for (int n = 0; n < t.N && n < cap; ++n) {
     out[n].last_bid = t.last_bid[n];
     out[n].player_id = player_id ^ (t.depth[n] & 1);
-    out[n].children_begin = t.nchild[n] ? t.child_begin[n] : 0;
-    out[n].children_end = t.nchild[n] ? t.child_begin[n] + t.nchild[n] : 0;
+    // like the reference, a processed node with an empty bid range (terminal above the depth limit) keeps
+    // children_begin == children_end == (tree size at that moment); unprocessed nodes keep 0/0 (tree.h:59-62)
+    out[n].children_begin = t.child_begin[n];
+    out[n].children_end = t.child_begin[n] + t.nchild[n];
     out[n].parent = t.parent[n];
     out[n].depth = t.depth[n];
   }
@@ -314,6 +338,26 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
   nd.w1t = h->d_w.p + o_w1; nd.b1 = h->d_w.p + o_b1; nd.g1 = h->d_w.p + o_g1; nd.be1 = h->d_w.p + o_be1;
   nd.w2t = h->d_w.p + o_w2; nd.b2 = h->d_w.p + o_b2; nd.g2 = h->d_w.p + o_g2; nd.be2 = h->d_w.p + o_be2;
   nd.w3t = h->d_w.p + o_w3; nd.b3 = h->d_w.p + o_b3;
+  if (h->cfg.net_mode == CFRB_NET_TC_F16) {
+    // tensor-core blob: fp16 weights in UMMA K-major core-matrix order + fp32 {bias, gamma, beta} per feature
+    const cfrb::tc::BlobLayout L(Qp);
+    std::vector<uint8_t> blob(L.blob_bytes, 0);
+    __half* hw1 = reinterpret_cast<__half*>(blob.data() + L.off_w1);
+    __half* hw2 = reinterpret_cast<__half*>(blob.data() + L.off_w2);
+    __half* hw3 = reinterpret_cast<__half*>(blob.data() + L.off_w3);
+    for (int j = 0; j < hid; ++j) for (int k = 0; k < Q; ++k) hw1[cfrb::tc::umma_kmajor_offset_halves(j, k, hid)] = __float2half_rn(w1[(size_t)j * Q + k]);
+    for (int j = 0; j < hid; ++j) for (int k = 0; k < hid; ++k) hw2[cfrb::tc::umma_kmajor_offset_halves(j, k, hid)] = __float2half_rn(w2[(size_t)j * hid + k]);
+    for (int j = 0; j < H; ++j) for (int k = 0; k < hid; ++k) hw3[cfrb::tc::umma_kmajor_offset_halves(j, k, cfrb::tc::kNout)] = __float2half_rn(w3[(size_t)j * hid + k]);
+    float* ln1 = reinterpret_cast<float*>(blob.data() + L.off_ln1);
+    float* ln2 = reinterpret_cast<float*>(blob.data() + L.off_ln2);
+    for (int j = 0; j < hid; ++j) {
+      ln1[4 * j] = b1[j]; ln1[4 * j + 1] = g1[j]; ln1[4 * j + 2] = be1[j];
+      ln2[4 * j] = b2[j]; ln2[4 * j + 1] = g2[j]; ln2[4 * j + 2] = be2[j];
+    }
+    std::copy(b3, b3 + H, reinterpret_cast<float*>(blob.data() + L.off_b3));
+    if (!h->d_blob.p) CK(h->d_blob.alloc(L.blob_bytes));
+    CK(cudaMemcpy(h->d_blob.p, blob.data(), L.blob_bytes, cudaMemcpyHostToDevice));
+  }
   h->have_weights = true;
   h->weights_version = version;
   return CFRB_OK;
@@ -387,10 +431,43 @@ static int launch_iter(cfrb_handle* h, cudaStream_t st, int iter, int do_b, int 
 
 static int launch_net(cfrb_handle* h, cudaStream_t st) {
   if (h->cfg.net_mode == CFRB_NET_ZERO || h->rows == 0) return CFRB_OK;
-  const int blocks = (h->rows + cfrb::kMlpRows - 1) / cfrb::kMlpRows;
-  cfrb::leaf_mlp_fp32_kernel<256><<<blocks, 256, cfrb::leaf_mlp_fp32_smem(256), st>>>(h->net, h->d_X.p, h->d_wave.p + 1, h->d_out.p);
+  if (h->profiling) {
+    while ((int)h->net_ev.size() < h->net_ev_used + 2) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->net_ev.push_back(e);
+    }
+    CK(cudaEventRecord(h->net_ev[h->net_ev_used], st));
+  }
+  if (h->cfg.net_mode == CFRB_NET_TC_F16) {
+    const cfrb::tc::BlobLayout L(h->Qpad);
+    cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, nullptr, nullptr};
+    const int tiles = (h->rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
+    cfrb::tc::leaf_mlp_tc_kernel<<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+  } else {
+    const int blocks = (h->rows + cfrb::kMlpRows - 1) / cfrb::kMlpRows;
+    cfrb::leaf_mlp_fp32_kernel<256><<<blocks, 256, cfrb::leaf_mlp_fp32_smem(256), st>>>(h->net, h->d_X.p, h->d_wave.p + 1, h->d_out.p);
+  }
   ++h->launches;
   CK(cudaGetLastError());
+  if (h->profiling) {
+    CK(cudaEventRecord(h->net_ev[h->net_ev_used + 1], st));
+    h->net_ev_used += 2;
+  }
+  return CFRB_OK;
+}
+
+int cfrb_reset_wave(cfrb_handle* h, void* cuda_stream) {
+  if (!h) return fail(CFRB_EINVAL, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  h->iters_done = 0;
+  if (h->n == 0) return CFRB_OK;
+  return launch_init(h, cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream);
+}
+
+int cfrb_set_profiling(cfrb_handle* h, int32_t on) {
+  if (!h) return fail(CFRB_EINVAL, "null handle");
+  h->profiling = on != 0;
   return CFRB_OK;
 }
 
@@ -402,6 +479,7 @@ int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream) {
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
   CK(cudaEventRecord(h->ev_a, st));
+  h->net_ev_used = 0;
   const int first = h->iters_done, last = first + iters;
   for (int i = first; i <= last; ++i) {
     const int do_b = i > first, do_f = i < last;
@@ -539,7 +617,15 @@ int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, float* sc
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
   const int rows = std::min<int>(h->rows, cap_rows), Q = h->g.Q;
-  if (rows > 0 && queries) {
+  if (rows > 0 && queries && h->cfg.net_mode == CFRB_NET_TC_F16) {
+    const int tiles = (rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
+    std::vector<__half> x((size_t)tiles * cfrb::tc::kTileM * h->Qpad);
+    CK(cudaMemcpy(x.data(), h->d_Xh.p, x.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < rows; ++r)
+      for (int q = 0; q < Q; ++q)
+        queries[(size_t)r * Q + q] = __half2float(x[(size_t)(r >> 7) * cfrb::tc::kTileM * h->Qpad +
+                                                    cfrb::tc::umma_kmajor_offset_halves(r & 127, q, cfrb::tc::kTileM)]);
+  } else if (rows > 0 && queries) {
     std::vector<float> x((size_t)rows * h->Qpad);
     CK(cudaMemcpy(x.data(), h->d_X.p, x.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int r = 0; r < rows; ++r) std::memcpy(queries + (size_t)r * Q, x.data() + (size_t)r * h->Qpad, Q * sizeof(float));
@@ -551,6 +637,24 @@ int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, float* sc
   }
   if (rows > 0 && scalers) CK(cudaMemcpy(scalers, h->d_scaler.p, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost));
   return h->rows;
+}
+
+int cfrb_debug_net_taps(cfrb_handle* h, float* d1, float* d2) {
+  if (!h || h->cfg.net_mode != CFRB_NET_TC_F16) return fail(CFRB_EINVAL, "taps exist only for CFRB_NET_TC_F16");
+  if (!h->have_weights || h->rows == 0) return fail(CFRB_ESTATE, "no weights or no leaf rows");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  const cfrb::tc::BlobLayout L(h->Qpad);
+  const size_t n = (size_t)cfrb::tc::kTileM * cfrb::tc::kHid;
+  cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, h->d_dbg.p, h->d_dbg.p + n};
+  const int tiles = (h->rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
+  cfrb::tc::leaf_mlp_tc_kernel<<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, h->own_stream>>>(a);
+  ++h->launches;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->own_stream));
+  if (d1) CK(cudaMemcpy(d1, h->d_dbg.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (d2) CK(cudaMemcpy(d2, h->d_dbg.p + n, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return CFRB_OK;
 }
 
 int cfrb_exploitability(cfrb_handle* h, const float* full_strategy, float* out2) {
@@ -568,8 +672,15 @@ int cfrb_last_run_ms(cfrb_handle* h, float* total_ms, float* net_ms) {
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev_a, h->ev_b));
   h->last_total_ms = ms;
+  float net = 0.f;
+  for (int i = 0; i + 1 < h->net_ev_used; i += 2) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, h->net_ev[i], h->net_ev[i + 1]));
+    net += t;
+  }
+  h->last_net_ms = net;
   if (total_ms) *total_ms = ms;
-  if (net_ms) *net_ms = h->last_net_ms;
+  if (net_ms) *net_ms = net;
   return CFRB_OK;
 }
 

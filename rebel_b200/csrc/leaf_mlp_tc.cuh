@@ -1,0 +1,317 @@
+// Tensor-core evaluation of the leaf value net (Net2: Linear -> LayerNorm -> GELU -> Linear -> LayerNorm -> GELU -> Linear,
+// cfvpy/models.py:64-94) for all pseudo-leaf query rows of a wave — the one dense contraction of the CFR hot path and,
+// at 148k FLOP per row, its dominant cost.  Blackwell-native: tcgen05.mma (kind::f16, fp16 operands, fp32 accumulation in
+// TMEM), weights resident in shared memory for the lifetime of a persistent CTA, activations never leave the SM:
+//
+//   X tile [128 x Kp] fp16 (smem, UMMA K-major core-matrix order, written in that order by the CFR forward kernel)
+//     --tcgen05.mma SS-->  D1 [128 x 256] fp32 in TMEM cols [0,256)
+//     --epilogue (tcgen05.ld, +bias, LayerNorm, erf-GELU, ->fp16, tcgen05.st)-->  A2 [128 x 256] fp16 in TMEM cols [256,384)
+//     --tcgen05.mma TS (A from TMEM, W2 from smem)-->  D2 in TMEM cols [0,256)   (reuses D1's columns)
+//     --epilogue-->  A3 in TMEM cols [256,384)
+//     --tcgen05.mma TS (N = 16)-->  D3 [128 x 16] in TMEM cols [384,400)  --epilogue (+bias)-->  out[rows][H] fp32
+//
+// Warp roles (160 threads): warps 0-3 = epilogue (thread == row == TMEM lane), warp 4 = TMEM allocator + single-thread
+// MMA issuer.  mbarriers: x (query tile staged), d1/d2/d3 (accumulator ready, via tcgen05.commit), a2/a3 (A operand ready).
+// Each barrier completes exactly once per tile, so one parity bit per tile iteration serves all of them.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cfrb {
+namespace tc {
+
+constexpr int kHid = 256;
+constexpr int kTileM = 128;
+constexpr int kNout = 16;                 // output features padded to the minimum UMMA N
+constexpr int kThreads = 160;
+constexpr uint32_t kColD = 0, kColA = 256, kColD3 = 384, kTmemCols = 512;
+
+// ---- shared-memory / weight-blob layout (bytes).  The blob in global memory has exactly the smem layout up to kOffX.
+struct BlobLayout {
+  int Kp;            // padded query width (multiple of 16)
+  int off_w1, off_w2, off_w3, off_ln1, off_ln2, off_b3, blob_bytes, off_x, off_bar, smem_bytes;
+  __host__ __device__ explicit BlobLayout(int kp) : Kp(kp) {
+    off_w1 = 0;
+    off_w2 = off_w1 + kHid * kp * 2;
+    off_w3 = off_w2 + kHid * kHid * 2;
+    off_ln1 = off_w3 + kNout * kHid * 2;
+    off_ln2 = off_ln1 + kHid * 16;          // float4 {bias, gamma, beta, 0} per feature
+    off_b3 = off_ln2 + kHid * 16;
+    blob_bytes = off_b3 + kNout * 4;
+    off_x = (blob_bytes + 127) / 128 * 128;
+    off_bar = off_x + kTileM * kp * 2;
+    smem_bytes = off_bar + 64;
+  }
+};
+
+// Element (row r, col k) of a K-major [R x K] fp16 operand in UMMA "no swizzle" core-matrix order:
+// 8x8 core matrices of 128 contiguous bytes; row-groups are 128 B apart (SBO), K-chunks R/8*128 B apart (LBO).
+__host__ __device__ inline int umma_kmajor_offset_halves(int r, int k, int R) {
+  return (k >> 3) * (R >> 3) * 64 + (r >> 3) * 64 + (r & 7) * 8 + (k & 7);
+}
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+      "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc),
+      "r"(accumulate) : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A/B format f16=0 [7,10),[10,13), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define CFRB_TMEM_LD32(taddr, v)                                                                                          \
+  asm volatile(                                                                                                           \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                           \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, " \
+      "[%32];"                                                                                                            \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),      \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),            \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),           \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                         \
+      : "r"(taddr))
+
+#define CFRB_TMEM_LD16(taddr, v)                                                                                          \
+  asm volatile(                                                                                                           \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"           \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),      \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                          \
+      : "r"(taddr))
+
+#define CFRB_TMEM_ST16(taddr, v)                                                                                          \
+  asm volatile(                                                                                                           \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), \
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),       \
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])                                              \
+      : "memory")
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float gelu_erf_tc(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// LayerNorm(eps 1e-5) + GELU over the 256 fp32 accumulators of this thread's row (TMEM lane), result as fp16 into the
+// A-operand columns.  ln: float4 {bias, gamma, beta, -} per feature in smem (broadcast reads).
+__device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, const float4* __restrict__ ln, float* dbg_row) {
+  float sum = 0.f, sumsq = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < kHid / 32; ++c) {
+    uint32_t v[32];
+    CFRB_TMEM_LD32(tmem_row + kColD + c * 32, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float x = __uint_as_float(v[i]) + ln[c * 32 + i].x;
+      sum += x;
+      sumsq = fmaf(x, x, sumsq);
+      if (dbg_row) dbg_row[c * 32 + i] = __uint_as_float(v[i]);
+    }
+  }
+  const float mean = sum * (1.f / kHid);
+  const float var = fmaxf(sumsq * (1.f / kHid) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float shift = -mean * rstd;
+#pragma unroll 1
+  for (int c = 0; c < kHid / 32; ++c) {
+    uint32_t v[32];
+    CFRB_TMEM_LD32(tmem_row + kColD + c * 32, v);
+    tmem_wait_ld();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 p0 = ln[c * 32 + 2 * i], p1 = ln[c * 32 + 2 * i + 1];
+      const float y0 = fmaf(fmaf(__uint_as_float(v[2 * i]) + p0.x, rstd, shift), p0.y, p0.z);
+      const float y1 = fmaf(fmaf(__uint_as_float(v[2 * i + 1]) + p1.x, rstd, shift), p1.y, p1.z);
+      const __half2 h = __floats2half2_rn(gelu_erf_tc(y0), gelu_erf_tc(y1));
+      pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    CFRB_TMEM_ST16(tmem_row + kColA + c * 16, pk);
+  }
+  tmem_wait_st();
+}
+
+struct TcArgs {
+  const uint8_t* blob;      // weights in smem layout (BlobLayout)
+  const __half* Xh;         // [tiles][Kp/8][16][8][8] fp16 query tiles
+  const int* rows_ptr;
+  float* out;               // [rows][Hout]
+  int Kp, H, Hout;
+  float* dbg_d1;            // optional [128][256] raw layer-1 accumulators of tile 0
+  float* dbg_d2;            // optional [128][256] raw layer-2 accumulators of tile 0
+};
+
+__global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const BlobLayout L(a.Kp);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = *a.rows_ptr;
+  const int ntiles = (rows + kTileM - 1) / kTileM;
+  if ((int)blockIdx.x >= ntiles) return;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  const uint32_t bar_x = smem_u32(bars + 0), bar_d1 = smem_u32(bars + 1), bar_d2 = smem_u32(bars + 2), bar_d3 = smem_u32(bars + 3),
+                 bar_a2 = smem_u32(bars + 4), bar_a3 = smem_u32(bars + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  // ---- one-time setup: weights -> smem, barriers, TMEM
+  {
+    const int4* src = reinterpret_cast<const int4*>(a.blob);
+    int4* dst = reinterpret_cast<int4*>(smem);
+    for (int i = tid; i < L.blob_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  if (tid == 0) {
+    mbar_init(bar_x, 128); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_d3, 1);
+    mbar_init(bar_a2, 128); mbar_init(bar_a3, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();          // generic-proxy weight stores -> visible to the tensor-core (async) proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t sx = smem_u32(smem + L.off_x), sw1 = smem_u32(smem + L.off_w1), sw2 = smem_u32(smem + L.off_w2),
+                 sw3 = smem_u32(smem + L.off_w3);
+  const int x_tile_int4 = kTileM * a.Kp * 2 / 16;
+
+  if (warp == 4) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc256 = make_idesc(kTileM, kHid), idesc16 = make_idesc(kTileM, kNout);
+      const uint32_t lbo_x = (kTileM / 8) * 128, lbo_w = (kHid / 8) * 128, lbo_w3 = (kNout / 8) * 128;
+      uint32_t parity = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+        // layer 1: D1 = X * W1^T
+        mbar_wait(bar_x, parity);
+        tc_fence_after();
+        for (int k = 0; k < a.Kp / 16; ++k)
+          mma_ss(tmem_base + kColD, make_desc(sx + k * 2 * lbo_x, lbo_x, 128), make_desc(sw1 + k * 2 * lbo_w, lbo_w, 128), idesc256, k > 0);
+        tc_commit(bar_d1);
+        // layer 2: D2 = A2 * W2^T  (A from TMEM: 16 fp16 = 8 columns per K step)
+        mbar_wait(bar_a2, parity);
+        tc_fence_after();
+        for (int k = 0; k < kHid / 16; ++k)
+          mma_ts(tmem_base + kColD, tmem_base + kColA + k * 8, make_desc(sw2 + k * 2 * lbo_w, lbo_w, 128), idesc256, k > 0);
+        tc_commit(bar_d2);
+        // layer 3: D3 = A3 * W3^T  (N = 16)
+        mbar_wait(bar_a3, parity);
+        tc_fence_after();
+        for (int k = 0; k < kHid / 16; ++k)
+          mma_ts(tmem_base + kColD3, tmem_base + kColA + k * 8, make_desc(sw3 + k * 2 * lbo_w3, lbo_w3, 128), idesc16, k > 0);
+        tc_commit(bar_d3);
+      }
+    }
+  } else {
+    // ===================== epilogue warps: thread == row == TMEM lane =====================
+    const int row_in_tile = tid;                                   // 0..127
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float4* ln1 = reinterpret_cast<const float4*>(smem + L.off_ln1);
+    const float4* ln2 = reinterpret_cast<const float4*>(smem + L.off_ln2);
+    const float* b3 = reinterpret_cast<const float*>(smem + L.off_b3);
+    int4* xdst = reinterpret_cast<int4*>(smem + L.off_x);
+    const int per_thread = x_tile_int4 / 128;                      // Kp/8 int4 per thread (4 or 6)
+    int4 xr[8];
+    {
+      const int4* xsrc = reinterpret_cast<const int4*>(a.Xh) + (size_t)blockIdx.x * x_tile_int4;
+      for (int i = 0; i < per_thread; ++i) xdst[tid + 128 * i] = __ldg(xsrc + tid + 128 * i);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_x);
+    }
+    uint32_t parity = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+      const int next = tile + gridDim.x;
+      const bool dbg = (tile == 0);
+      // ---- layer-1 accumulators ready; the query tile in smem is free again -> start fetching the next one
+      mbar_wait(bar_d1, parity);
+      tc_fence_after();
+      if (next < ntiles) {
+        const int4* xsrc = reinterpret_cast<const int4*>(a.Xh) + (size_t)next * x_tile_int4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i < per_thread) xr[i] = __ldg(xsrc + tid + 128 * i);
+      }
+      epilogue_ln_gelu(tmem_row, ln1, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr);
+      tc_fence_before();
+      mbar_arrive(bar_a2);
+      if (next < ntiles) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i < per_thread) xdst[tid + 128 * i] = xr[i];
+        fence_proxy_async_smem();
+        mbar_arrive(bar_x);
+      }
+      // ---- layer 2
+      mbar_wait(bar_d2, parity);
+      tc_fence_after();
+      epilogue_ln_gelu(tmem_row, ln2, (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr);
+      tc_fence_before();
+      mbar_arrive(bar_a3);
+      // ---- layer 3: raw net outputs (the CFR backward kernel multiplies by the opponent-reach scaler)
+      mbar_wait(bar_d3, parity);
+      tc_fence_after();
+      uint32_t v[16];
+      CFRB_TMEM_LD16(tmem_row + kColD3, v);
+      tmem_wait_ld();
+      const int row = tile * kTileM + row_in_tile;
+      if (row < rows) {
+        float* o = a.out + (size_t)row * a.Hout;
+#pragma unroll
+        for (int h = 0; h < kNout; ++h) if (h < a.H) o[h] = __uint_as_float(v[h]) + b3[h];
+      }
+      tc_fence_before();   // order this tile's TMEM reads before the next tile's MMAs (via the a2/a3/x arrivals that follow)
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace tc
+}  // namespace cfrb
