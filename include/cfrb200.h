@@ -24,7 +24,8 @@
  * caller-owned HOST memory (pinned preferred); one handle per GPU; a handle is not thread-safe (one
  * orchestrator thread per handle).  There is NO CPU fallback: without a CUDA device cfrb_create fails.
  *
- * Layouts (all row-major, fp32 unless noted):
+ * Layouts (all row-major; solver state crosses the boundary as fp64 like the reference's vector<double>, value-net
+ * tensors as fp32 like the reference's float tensors):
  *   beliefs            [n][2][H]          root beliefs of player 0 then player 1 (Pair<vector<double>> in the reference)
  *   dense strategy     [n][Nmax][H][A]    the reference's TreeStrategy = [node][hand][action] (subgame_solving.h:39),
  *                                         padded to Nmax = cfrb_max_nodes() nodes per subgame; entries of illegal
@@ -64,6 +65,12 @@ enum {
                              (the reference's own `half_inference` option, selfplay.py:42-43,211) */
 };
 
+/* Arithmetic type of the per-infoset CFR tables (regrets, strategies, reach, values). */
+enum {
+  CFRB_STATE_F64 = 0,     /* double, like the reference's TreeStrategy (default) */
+  CFRB_STATE_F32 = 1      /* float: half the table traffic; trajectories drift from the fp64 reference sooner */
+};
+
 /* SubgameSolvingParams (subgame_solving.h:43-58) + game shape + capacity. */
 typedef struct {
   int32_t num_dice;
@@ -77,6 +84,7 @@ typedef struct {
   int32_t device;           /* CUDA ordinal */
   int32_t net_mode;         /* CFRB_NET_* */
   int32_t hidden;           /* Net2 n_hidden (256); n_layers = 2, LayerNorm on */
+  int32_t state_dtype;      /* CFRB_STATE_* */
 } cfrb_config;
 
 /* One node of an unrolled subgame tree: UnrolledTreeNode (tree.h:31-47). */
@@ -118,7 +126,7 @@ uint64_t cfrb_weights_version(const cfrb_handle* h);
  * (CFR::last_strategies) of subgame k is snapshotted for RlRunner's state sampling
  * (recursive_solving.cc:168-174); -1 = no snapshot. */
 int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const int32_t* player_id,
-                    const float* beliefs, const int32_t* act_iteration);
+                    const double* beliefs, const int32_t* act_iteration);
 
 /* Re-initialise the solver state of the CURRENT wave on the device (same roots, beliefs and act_iterations; no
  * host->device traffic): what constructing fresh CFR solvers for the same subgames would do. */
@@ -139,8 +147,8 @@ int cfrb_iterations_done(const cfrb_handle* h);
 
 /* Copy results to the host (any pointer may be NULL).  Synchronises.
  *   root_value_means [n][2][H]; snapshot / last / avg / sum / regrets: dense [n][Nmax][H][A]. */
-int cfrb_fetch(cfrb_handle* h, float* root_value_means, float* snapshot_strategy, float* last_strategy,
-               float* avg_strategy, float* sum_strategy, float* regrets);
+int cfrb_fetch(cfrb_handle* h, double* root_value_means, double* snapshot_strategy, double* last_strategy,
+               double* avg_strategy, double* sum_strategy, double* regrets);
 
 /* Training examples of the finished wave: for each subgame and traverser t in {0,1} the query row of the
  * subgame root as seen by t and the target root_value_means[t].  queries [n][2][Q], values [n][2][H]. */
@@ -149,21 +157,21 @@ int cfrb_examples(cfrb_handle* h, float* queries, float* values);
 /* Teacher forcing (tests): overwrite solver state of the current wave from dense host arrays
  * [n][Nmax][H][A] (NULL = keep), root_value_means [n][2][H], num_steps [n][2], and set the wave's
  * iteration counter. */
-int cfrb_load_state(cfrb_handle* h, const float* regrets, const float* last_strategy, const float* sum_strategy,
-                    const float* root_value_means, const int32_t* num_steps, int32_t iterations_done);
+int cfrb_load_state(cfrb_handle* h, const double* regrets, const double* last_strategy, const double* sum_strategy,
+                    const double* root_value_means, const int32_t* num_steps, int32_t iterations_done);
 
 /* Debug/parity taps of the most recent iteration: query rows [rows][Q] and the (unscaled) net outputs
  * [rows][H] for all pseudo-leaves of the wave in (subgame, leaf) order; returns the number of rows,
  * writes at most cap_rows. */
-int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, float* scalers, int32_t cap_rows);
+int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, double* scalers, int32_t cap_rows);
 
 /* Debug taps of the tensor-core value net (CFRB_NET_TC_F16 only): re-runs it on the current query tiles and returns
  * the raw fp32 accumulators of layer 1 and layer 2 for the first 128 rows, each [128][256]. */
 int cfrb_debug_net_taps(cfrb_handle* h, float* d1, float* d2);
 
 /* Exploitability (best-response values of both players, compute_exploitability2) of a full-tree strategy
- * given as dense [N_full][H][A] fp32, evaluated on the GPU. out2 = {br0, br1}. */
-int cfrb_exploitability(cfrb_handle* h, const float* full_strategy, float* out2);
+ * given as dense [N_full][H][A] fp64, evaluated on the GPU. out2 = {br0, br1}. */
+int cfrb_exploitability(cfrb_handle* h, const double* full_strategy, double* out2);
 
 /* Counters for bench.py: kernels launched by this handle since creation, and leaf rows of the wave. */
 int64_t cfrb_kernel_launches(const cfrb_handle* h);

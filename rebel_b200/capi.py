@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfrb200.so")
 
 NET_ZERO, NET_FP32, NET_TC_F16 = 0, 1, 2
+STATE_F64, STATE_F32 = 0, 1
 
 
 class CfrbError(RuntimeError):
@@ -24,10 +25,12 @@ class Config(C.Structure):
         ("linear_update", C.c_int32), ("dcfr", C.c_int32),
         ("dcfr_alpha", C.c_double), ("dcfr_beta", C.c_double), ("dcfr_gamma", C.c_double),
         ("max_subgames", C.c_int32), ("device", C.c_int32), ("net_mode", C.c_int32), ("hidden", C.c_int32),
+        ("state_dtype", C.c_int32),
     ]
 
 
 _fp = C.POINTER(C.c_float)
+_dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _lib = None
 
@@ -53,15 +56,15 @@ def lib():
     L.cfrb_set_weights.argtypes = [vp, _fp, C.c_size_t, C.c_uint64]
     L.cfrb_weights_version.argtypes = [vp]
     L.cfrb_weights_version.restype = C.c_uint64
-    L.cfrb_begin_wave.argtypes = [vp, C.c_int32, _ip, _ip, _fp, _ip]
+    L.cfrb_begin_wave.argtypes = [vp, C.c_int32, _ip, _ip, _dp, _ip]
     L.cfrb_run.argtypes = [vp, C.c_int32, vp]
     L.cfrb_reset_wave.argtypes = [vp, vp]
     L.cfrb_set_profiling.argtypes = [vp, C.c_int32]
-    L.cfrb_fetch.argtypes = [vp] + [_fp] * 6
+    L.cfrb_fetch.argtypes = [vp] + [_dp] * 6
     L.cfrb_examples.argtypes = [vp, _fp, _fp]
-    L.cfrb_load_state.argtypes = [vp, _fp, _fp, _fp, _fp, _ip, C.c_int32]
-    L.cfrb_debug_leaf_io.argtypes = [vp, _fp, _fp, _fp, C.c_int32]
-    L.cfrb_exploitability.argtypes = [vp, _fp, _fp]
+    L.cfrb_load_state.argtypes = [vp, _dp, _dp, _dp, _dp, _ip, C.c_int32]
+    L.cfrb_debug_leaf_io.argtypes = [vp, _fp, _fp, _dp, C.c_int32]
+    L.cfrb_exploitability.argtypes = [vp, _dp, _dp]
     L.cfrb_debug_net_taps.argtypes = [vp, _fp, _fp]
     L.cfrb_kernel_launches.argtypes = [vp]
     L.cfrb_kernel_launches.restype = C.c_int64
@@ -95,10 +98,11 @@ class WaveSolver:
     for a whole wave: begin() ~ constructor, run() ~ step/multistep, getters ~ get_*."""
 
     def __init__(self, num_dice, num_faces, max_subgames, max_depth=2, num_iters=1024, linear_update=True, dcfr=False,
-                 dcfr_alpha=0.0, dcfr_beta=0.0, dcfr_gamma=0.0, net_mode=NET_FP32, hidden=256, device=0):
+                 dcfr_alpha=0.0, dcfr_beta=0.0, dcfr_gamma=0.0, net_mode=NET_FP32, hidden=256, device=0,
+                 state_dtype=STATE_F64):
         L = lib()
         self.cfg = Config(num_dice, num_faces, max_depth, num_iters, int(linear_update), int(dcfr), dcfr_alpha, dcfr_beta,
-                          dcfr_gamma, max_subgames, device, net_mode, hidden)
+                          dcfr_gamma, max_subgames, device, net_mode, hidden, state_dtype)
         self._h = C.c_void_p()
         _check(L.cfrb_create(C.byref(self.cfg), C.byref(self._h)))
         self.A = L.cfrb_num_actions(self._h)
@@ -130,11 +134,11 @@ class WaveSolver:
     def begin(self, last_bid, player_id, beliefs, act_iteration=None):
         lb = np.ascontiguousarray(last_bid, np.int32)
         pl = np.ascontiguousarray(player_id, np.int32)
-        b = np.ascontiguousarray(beliefs, np.float32)
+        b = np.ascontiguousarray(beliefs, np.float64)
         n = lb.shape[0]
         assert pl.shape == (n,) and b.shape == (n, 2, self.H), (pl.shape, b.shape)
         act = None if act_iteration is None else np.ascontiguousarray(act_iteration, np.int32)
-        _check(lib().cfrb_begin_wave(self._h, n, _p(lb, _ip), _p(pl, _ip), _p(b, _fp), _p(act, _ip)))
+        _check(lib().cfrb_begin_wave(self._h, n, _p(lb, _ip), _p(pl, _ip), _p(b, _dp), _p(act, _ip)))
         self.n = n
 
     def reset(self, stream=None):
@@ -158,11 +162,11 @@ class WaveSolver:
         n = self.n
         bufs = {}
         if "root_means" in want:
-            bufs["root_means"] = np.zeros((n, 2, self.H), np.float32)
+            bufs["root_means"] = np.zeros((n, 2, self.H), np.float64)
         for k in ("snapshot", "last", "avg", "sum", "regrets"):
             if k in want:
-                bufs[k] = np.zeros((n, self.Nmax, self.H, self.A), np.float32)
-        g = lambda k: _p(bufs.get(k), _fp)
+                bufs[k] = np.zeros((n, self.Nmax, self.H, self.A), np.float64)
+        g = lambda k: _p(bufs.get(k), _dp)
         _check(lib().cfrb_fetch(self._h, g("root_means"), g("snapshot"), g("last"), g("avg"), g("sum"), g("regrets")))
         return bufs
 
@@ -174,16 +178,16 @@ class WaveSolver:
 
     def load_state(self, regrets=None, last=None, sum=None, root_means=None, num_steps=None, iterations_done=0):
         c = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
-        r, l, s, m, st = c(regrets, np.float32), c(last, np.float32), c(sum, np.float32), c(root_means, np.float32), \
+        r, l, s, m, st = c(regrets, np.float64), c(last, np.float64), c(sum, np.float64), c(root_means, np.float64), \
             c(num_steps, np.int32)
-        _check(lib().cfrb_load_state(self._h, _p(r, _fp), _p(l, _fp), _p(s, _fp), _p(m, _fp), _p(st, _ip), iterations_done))
+        _check(lib().cfrb_load_state(self._h, _p(r, _dp), _p(l, _dp), _p(s, _dp), _p(m, _dp), _p(st, _ip), iterations_done))
 
     def leaf_io(self):
         rows = lib().cfrb_wave_leaf_rows(self._h)
         q = np.zeros((max(rows, 1), self.Q), np.float32)
         o = np.zeros((max(rows, 1), self.H), np.float32)
-        s = np.zeros(max(rows, 1), np.float32)
-        _check(lib().cfrb_debug_leaf_io(self._h, _p(q, _fp), _p(o, _fp), _p(s, _fp), rows))
+        s = np.zeros(max(rows, 1), np.float64)
+        _check(lib().cfrb_debug_leaf_io(self._h, _p(q, _fp), _p(o, _fp), _p(s, _dp), rows))
         return q[:rows], o[:rows], s[:rows]
 
     def net_taps(self):
@@ -193,9 +197,9 @@ class WaveSolver:
         return d1, d2
 
     def exploitability(self, full_strategy):
-        s = np.ascontiguousarray(full_strategy, np.float32)
-        out = np.zeros(2, np.float32)
-        _check(lib().cfrb_exploitability(self._h, _p(s, _fp), _p(out, _fp)))
+        s = np.ascontiguousarray(full_strategy, np.float64)
+        out = np.zeros(2, np.float64)
+        _check(lib().cfrb_exploitability(self._h, _p(s, _dp), _p(out, _dp)))
         return out
 
     @property

@@ -4,13 +4,15 @@
 // compute_reach_probabilities (:54-78), write_query_to (:104-123), query_value_net scaling (:253-269) and
 // compute_expected_terminal_values / compute_win_probability (:80-98, :765-789).
 //
-// Execution model: one thread GROUP (a warp for depth-limited subgames, a whole CTA for full-depth trees)
-// owns one subgame; the group walks the tree template level by level, lanes strided over (node, hand) items.
-// Per-(node,hand,action) tables live in HBM as compact fp32 [edge][hand] arrays (edge = child node - 1) so a
-// group streams its subgame's tables with unit-stride, coalesced accesses; reach probabilities and node
-// values are group-private scratch (shared memory for warps, global for CTA groups).
+// Execution model: one thread GROUP (a warp for depth-limited subgames, a whole CTA for full-depth trees) owns one
+// subgame and walks the tree template level by level.  Every phase is a flat loop over (child node, hand) or
+// (node, hand) items with the lanes strided over the items, so all global accesses of a phase are independent,
+// unit-stride and coalesced: the per-(node,hand,action) tables live in HBM as compact [edge = child-1][hand] arrays
+// (one subgame contiguous), reach / node values / per-edge temporaries in group-private shared memory.
+// `real` is the arithmetic type of the tables: double reproduces the reference's fp64 state (default), float halves
+// the table traffic.
 //
-// One launch = backward half of iteration i-1 (consume leaf values -> regrets, regret matching, discounting,
+// One launch = backward half of iteration i-1 (leaf values -> regrets, regret matching, discounting,
 // average-strategy accumulation) fused with the forward half of iteration i (reach -> value-net query rows,
 // scalers, terminal payoffs).  The value-net kernel runs between two launches.
 #pragma once
@@ -25,30 +27,31 @@ struct TemplateDev {
   int N, L, T, levels;
 };
 
+template <typename real>
 struct CfrDev {
   // game
   int A, H, F, Q, Qpad, Hout;
   // templates (read-only)
   const TemplateDev* tmpl;
-  const int* child_begin; const int* nchild; const int* last_bid; const int* kind; const int* slot;
+  const int* parent; const int* child_begin; const int* nchild; const int* last_bid;
   const int* level_begin; const int* pleaf_node; const int* term_node;
   const unsigned char* matches;   // [H][F] num_matches(hand, face), liars_dice.h:83-91
   // wave
   const int* wave_n;              // [1] number of live subgames
   const int* sg_tmpl; const int* sg_player; const int* sg_row_off; const int* sg_act_iter;
-  const float* beliefs;           // [K][2][H]
-  float* mu;                      // [K][2][H] root_values_means
+  const real* beliefs;            // [K][2][H]
+  real* mu;                       // [K][2][H] root_values_means
   int* steps;                     // [K][2]
-  float* R; float* Sg; float* S; float* Snap;   // [K][table_stride]
+  real* R; real* Sg; real* S; real* Snap;   // [K][table_stride]
   int table_stride;
-  float* vterm; int vterm_stride; // [K][Tmax*H] terminal payoffs of the current iteration
+  real* vterm; int vterm_stride;  // [K][Tmax*H] terminal payoffs of the current iteration
   float* X;                       // [rows][Qpad] fp32 query rows (SIMT net) -- or nullptr
-  void* Xh;                       // fp16 query tiles in UMMA core-matrix order (tensor-core net) -- or nullptr
+  __half* Xh;                     // fp16 query tiles in UMMA core-matrix order (tensor-core net) -- or nullptr
   const float* net_out;           // [rows][Hout] raw net outputs
-  float* scaler;                  // [rows] sum of opponent reach at the pseudo-leaf
-  float* scratch; size_t scratch_stride;   // global scratch (CTA groups), floats per subgame
+  real* scaler;                   // [rows] sum of opponent reach at the pseudo-leaf
+  real* scratch; size_t scratch_stride;   // global scratch (CTA groups), reals per subgame
   // params
-  int linear, dcfr; float dcfr_alpha, dcfr_beta, dcfr_gamma;
+  int linear, dcfr; real dcfr_alpha, dcfr_beta, dcfr_gamma;
   int use_net;
 };
 
@@ -56,109 +59,112 @@ template <int G>
 __device__ __forceinline__ void group_sync() {
   if (G == 32) __syncwarp(); else __syncthreads();
 }
+__device__ __forceinline__ float rmax0(float x) { return fmaxf(x, 0.f); }
+__device__ __forceinline__ double rmax0(double x) { return fmax(x, 0.0); }
+__device__ __forceinline__ float rpow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double rpow(double a, double b) { return pow(a, b); }
 
-// Top-down reach of both players under Sg (subgame_solving.cc:54-78), level by level.
-template <int G>
-__device__ __forceinline__ void reach_pass(const CfrDev& p, const TemplateDev& t, int rp, const float* __restrict__ Sg,
-                                           const float* __restrict__ b, float* reach0, float* reach1, int lane) {
-  const int H = p.H;
-  for (int h = lane; h < H; h += G) { reach0[h] = b[h]; reach1[h] = b[H + h]; }
-  group_sync<G>();
-  for (int d = 0; d + 1 < t.levels; ++d) {
-    const int nb = p.level_begin[t.level_off + d], ne = p.level_begin[t.level_off + d + 1];
-    const int actor = rp ^ (d & 1);
-    float* ra = actor ? reach1 : reach0;   // acting player's reach gets multiplied
-    float* ro = actor ? reach0 : reach1;   // the other player's reach is copied
-    for (int it = lane; it < (ne - nb) * H; it += G) {
-      const int n = nb + it / H, h = it % H;
-      const int nc = p.nchild[t.node_off + n];
-      if (!nc) continue;
-      const int c0 = p.child_begin[t.node_off + n];
-      const float a = ra[n * H + h], o = ro[n * H + h];
-      for (int j = 0; j < nc; ++j) {
-        const int c = c0 + j;
-        ra[c * H + h] = a * Sg[(c - 1) * H + h];
-        ro[c * H + h] = o;
-      }
-    }
-    group_sync<G>();
-  }
+// Scratch layout of a group (reals): bufA[N*H] | bufB[N*H] | tmp[N*H] | lsum[2*L]
+__host__ __device__ inline int cfr_scratch_reals(int N, int H, int L) { return 3 * N * H + 2 * (L > 0 ? L : 1); }
+
+// Value of query column q of a pseudo-leaf row (write_query_to, subgame_solving.cc:104-123).  The reference's eps =
+// 1e-80 only matters when a reach vector is all zero (-> uniform); that case is reproduced explicitly.
+template <typename real>
+__device__ __forceinline__ float query_value(const CfrDev<real>& p, int q, int leaf_player, int trav, int leaf_bid, const real* r0,
+                                             const real* r1, real s0, real s1) {
+  const int A = p.A, H = p.H;
+  if (q == 0) return (float)leaf_player;
+  if (q == 1) return (float)trav;
+  if (q < 2 + A) return (q - 2 == leaf_bid) ? 1.f : 0.f;
+  if (q < 2 + A + H) return s0 > 0 ? (float)(r0[q - 2 - A] / s0) : 1.f / H;
+  if (q < 2 + A + 2 * H) return s1 > 0 ? (float)(r1[q - 2 - A - H] / s1) : 1.f / H;
+  return 0.f;
 }
 
 // Forward half of iteration `iter`: reach, query rows + scalers for pseudo-leaves, payoffs for terminals.
-template <int G>
-__device__ void cfr_forward(const CfrDev& p, int k, int trav, float* reach0, float* reach1, float* lsum, int lane) {
+template <typename real, int G>
+__device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0, real* reach1, real* lsum, int lane) {
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
-  const int H = p.H, A = p.A;
+  const int H = p.H;
   const int rp = p.sg_player[k];
-  const float* Sg = p.Sg + (size_t)k * p.table_stride;
-  const float* b = p.beliefs + (size_t)k * 2 * H;
-  reach_pass<G>(p, t, rp, Sg, b, reach0, reach1, lane);
-
+  const real* __restrict__ Sg = p.Sg + (size_t)k * p.table_stride;
+  const real* __restrict__ b = p.beliefs + (size_t)k * 2 * H;
+  const int* __restrict__ parent = p.parent + t.node_off;
+  // ---- top-down reach of both players under Sg (compute_reach_probabilities, subgame_solving.cc:54-78)
+  for (int h = lane; h < H; h += G) { reach0[h] = b[h]; reach1[h] = b[H + h]; }
+  group_sync<G>();
+  for (int d = 1; d < t.levels; ++d) {
+    const int nb = p.level_begin[t.level_off + d], ne = p.level_begin[t.level_off + d + 1];
+    const int actor = rp ^ ((d - 1) & 1);              // who moved into level d
+    for (int it = lane; it < (ne - nb) * H; it += G) {
+      const int c = nb + it / H, h = it % H;
+      const int par = parent[c];
+      const real s = Sg[(c - 1) * H + h];
+      const real a0 = reach0[par * H + h], a1 = reach1[par * H + h];
+      reach0[c * H + h] = actor == 0 ? a0 * s : a0;
+      reach1[c * H + h] = actor == 1 ? a1 * s : a1;
+    }
+    group_sync<G>();
+  }
   // ---- pseudo-leaves: normalisation sums + scaler (subgame_solving.cc:257-265)
   const int row0 = p.sg_row_off[k];
   for (int r = lane; r < t.L; r += G) {
     const int n = p.pleaf_node[t.pleaf_off + r];
-    float s0 = 0.f, s1 = 0.f;
+    real s0 = 0, s1 = 0;
     for (int h = 0; h < H; ++h) { s0 += reach0[n * H + h]; s1 += reach1[n * H + h]; }
     lsum[2 * r] = s0; lsum[2 * r + 1] = s1;
     p.scaler[row0 + r] = trav == 0 ? s1 : s0;
   }
   group_sync<G>();
-  // ---- query rows (write_query_to, subgame_solving.cc:104-123).  eps = 1e-80 of the reference underflows in
-  // fp32; its only effect in fp64 is "all-zero reach -> uniform", which is reproduced explicitly.
-  if (p.X != nullptr || p.Xh != nullptr) {
-    const int Qp = p.Qpad;
+  // ---- query rows.  All pseudo-leaves sit on the last level, so their acting player is rp ^ ((levels-1)&1).
+  const int leaf_player = rp ^ ((t.levels - 1) & 1);
+  const int Qp = p.Qpad;
+  if (p.Xh != nullptr) {
+    // fp16 tile in UMMA K-major core-matrix order (leaf_mlp_tc.cuh umma_kmajor_offset_halves, R = 128):
+    // one lane produces the 8 contiguous halves of a (row, k-chunk) and stores them with a single 16-byte write
+    const int kc = Qp >> 3;
+    for (int it = lane; it < t.L * kc; it += G) {
+      const int r = it / kc, k8 = it % kc;
+      const int n = p.pleaf_node[t.pleaf_off + r];
+      const int bid = p.last_bid[t.node_off + n];
+      const real s0 = lsum[2 * r], s1 = lsum[2 * r + 1];
+      __align__(16) __half hv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        hv[j] = __float2half_rn(query_value(p, k8 * 8 + j, leaf_player, trav, bid, reach0 + n * H, reach1 + n * H, s0, s1));
+      const int Rr = row0 + r, rr = Rr & 127;
+      *reinterpret_cast<int4*>(p.Xh + (size_t)(Rr >> 7) * 128 * Qp + k8 * 1024 + (rr >> 3) * 64 + (rr & 7) * 8) =
+          *reinterpret_cast<const int4*>(hv);
+    }
+  } else if (p.X != nullptr) {
     for (int it = lane; it < t.L * Qp; it += G) {
       const int r = it / Qp, q = it % Qp;
       const int n = p.pleaf_node[t.pleaf_off + r];
-      const int nd = t.node_off + n;
-      float v = 0.f;
-      if (q == 0) {
-        // depth parity of a pseudo-leaf: all pseudo-leaves sit on the last level
-        v = (float)(rp ^ ((t.levels - 1) & 1));
-      } else if (q == 1) {
-        v = (float)trav;
-      } else if (q < 2 + A) {
-        v = (q - 2 == p.last_bid[nd]) ? 1.f : 0.f;
-      } else if (q < 2 + A + H) {
-        const float s = lsum[2 * r];
-        v = s > 0.f ? reach0[n * H + (q - 2 - A)] / s : 1.f / H;
-      } else if (q < 2 + A + 2 * H) {
-        const float s = lsum[2 * r + 1];
-        v = s > 0.f ? reach1[n * H + (q - 2 - A - H)] / s : 1.f / H;
-      }
-      if (p.X != nullptr) {
-        p.X[(size_t)(row0 + r) * Qp + q] = v;
-      } else {
-        // fp16 tile in UMMA K-major core-matrix order (leaf_mlp_tc.cuh umma_kmajor_offset_halves, R = 128)
-        const int R = row0 + r, rr = R & 127;
-        reinterpret_cast<__half*>(p.Xh)[(size_t)(R >> 7) * 128 * Qp + (q >> 3) * 1024 + (rr >> 3) * 64 + (rr & 7) * 8 + (q & 7)] =
-            __float2half_rn(v);
-      }
+      p.X[(size_t)(row0 + r) * Qp + q] = query_value(p, q, leaf_player, trav, p.last_bid[t.node_off + n], reach0 + n * H,
+                                                     reach1 + n * H, lsum[2 * r], lsum[2 * r + 1]);
     }
   }
   // ---- terminals (compute_expected_terminal_values, subgame_solving.cc:80-98; win probability :765-789)
   // term_node holds three lists of length T: node id, challenged bid (= parent's last_bid, :287), node depth.
-  float* vt = p.vterm + (size_t)k * p.vterm_stride;
-  const float* ropp = trav == 0 ? reach1 : reach0;
+  real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
+  const real* ropp = trav == 0 ? reach1 : reach0;
   for (int it = lane; it < t.T * H; it += G) {
     const int z = it / H, h = it % H;
     const int n = p.term_node[t.term_off + z];
     const int pbid = p.term_node[t.term_off + t.T + z];
     const int ndepth = p.term_node[t.term_off + 2 * t.T + z];
     const int quantity = 1 + pbid / p.F, face = pbid % p.F;   // unpack_action, liars_dice.h:74-80
-    const float* ro = ropp + n * H;
+    const real* ro = ropp + n * H;
     // P(h) = sum of opponent reach over hands g with matches(g) >= quantity - matches(h): the suffix sum of
-    // the match-count histogram the reference builds (:770-779), evaluated directly.
+    // the match-count histogram the reference builds (:770-779), evaluated directly; float-rounded like :785.
     const int need = quantity - (int)p.matches[h * p.F + face];
-    float win = 0.f, tot = 0.f;
+    real win = 0, tot = 0;
     for (int g = 0; g < H; ++g) {
-      const float r = ro[g];
+      const real r = ro[g];
       tot += r;
       if ((int)p.matches[g * p.F + face] >= need) win += r;
     }
-    const float v = win * 2.f - tot;
+    const real v = (real)(float)win * 2 - tot;
     // state.player_id of a terminal = the bidder; payoff is negated iff that is not the traverser (:290)
     const int pl = rp ^ (ndepth & 1);
     vt[z * H + h] = (pl != trav) ? -v : v;
@@ -166,98 +172,115 @@ __device__ void cfr_forward(const CfrDev& p, int k, int trav, float* reach0, flo
 }
 
 // Backward half of iteration with traverser `trav` (update_regrets :538-575 and step :577-664).
-template <int G>
-__device__ void cfr_backward(const CfrDev& p, int k, int trav, float* reach0, float* reach1, float* val, int lane) {
+template <typename real, int G>
+__device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, real* rt, real* tmp, int lane) {
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int H = p.H;
   const int rp = p.sg_player[k];
-  float* R = p.R + (size_t)k * p.table_stride;
-  float* Sg = p.Sg + (size_t)k * p.table_stride;
-  float* S = p.S + (size_t)k * p.table_stride;
+  real* __restrict__ R = p.R + (size_t)k * p.table_stride;
+  real* __restrict__ Sg = p.Sg + (size_t)k * p.table_stride;
+  real* __restrict__ S = p.S + (size_t)k * p.table_stride;
+  const int* __restrict__ parent = p.parent + t.node_off;
+  const int* __restrict__ nchild = p.nchild + t.node_off;
+  const int* __restrict__ child_begin = p.child_begin + t.node_off;
   const int row0 = p.sg_row_off[k];
-  // leaf values = net(query) * scaler (subgame_solving.cc:266-282); terminals from the forward half
+  // leaf values = (float)(net(query) * scaler) (subgame_solving.cc:266-282); terminals from the forward half
   for (int it = lane; it < t.L * H; it += G) {
     const int r = it / H, h = it % H;
     const int n = p.pleaf_node[t.pleaf_off + r];
-    val[n * H + h] = p.use_net ? p.net_out[(size_t)(row0 + r) * p.Hout + h] * p.scaler[row0 + r] : 0.f;
+    val[n * H + h] = p.use_net ? (real)(float)((real)p.net_out[(size_t)(row0 + r) * p.Hout + h] * p.scaler[row0 + r]) : (real)0;
   }
-  const float* vt = p.vterm + (size_t)k * p.vterm_stride;
+  const real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
   for (int it = lane; it < t.T * H; it += G) {
     const int z = it / H, h = it % H;
     val[p.term_node[t.term_off + z] * H + h] = vt[z * H + h];
   }
   group_sync<G>();
-  // bottom-up (reverse BFS order == decreasing level)
+  // ---- bottom-up (reverse BFS order == decreasing level)
   for (int d = t.levels - 2; d >= 0; --d) {
     const int nb = p.level_begin[t.level_off + d], ne = p.level_begin[t.level_off + d + 1];
+    const int cb = ne, ce = p.level_begin[t.level_off + d + 2];
     const bool mine = (rp ^ (d & 1)) == trav;
+    if (mine) {   // per-edge products value * sigma
+      for (int it = lane; it < (ce - cb) * H; it += G) {
+        const int c = cb + it / H, h = it % H;
+        tmp[(c - 1) * H + h] = val[c * H + h] * Sg[(c - 1) * H + h];
+      }
+      group_sync<G>();
+    }
     for (int it = lane; it < (ne - nb) * H; it += G) {
       const int n = nb + it / H, h = it % H;
-      const int nc = p.nchild[t.node_off + n];
+      const int nc = nchild[n];
       if (!nc) continue;
-      const int c0 = p.child_begin[t.node_off + n];
-      float v = 0.f;
-      if (mine) {
-        for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h] * Sg[(c0 + j - 1) * H + h];
-        for (int j = 0; j < nc; ++j) {
-          const int e = (c0 + j - 1) * H + h;
-          R[e] = (R[e] + val[(c0 + j) * H + h]) - v;
-        }
-      } else {
-        for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h];
-      }
+      const int c0 = child_begin[n];
+      real v = 0;
+      if (mine) { for (int j = 0; j < nc; ++j) v += tmp[(c0 + j - 1) * H + h]; }
+      else      { for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h]; }
       val[n * H + h] = v;
     }
     group_sync<G>();
-  }
-  // root value running mean (:579-590) and discounts (:592-617)
-  const int s = p.steps[2 * k + trav];
-  {
-    const float alpha = p.linear ? 2.f / (s + 2) : 1.f / (s + 1);
-    float* mu = p.mu + ((size_t)k * 2 + trav) * H;
-    for (int h = lane; h < H; h += G) mu[h] += (val[h] - mu[h]) * alpha;
-  }
-  float pos = 1.f, neg = 1.f, strat = 1.f;
-  {
-    const float ns = (float)(s + 1);
-    if (p.linear) {
-      pos = neg = strat = ns / (ns + 1.f);
-    } else if (p.dcfr) {
-      pos = p.dcfr_alpha >= 5.f ? 1.f : powf(ns, p.dcfr_alpha) / (powf(ns, p.dcfr_alpha) + 1.f);
-      neg = p.dcfr_beta <= -5.f ? 0.f : powf(ns, p.dcfr_beta) / (powf(ns, p.dcfr_beta) + 1.f);
-      strat = powf(ns / (ns + 1.f), p.dcfr_gamma);
+    if (mine) {   // regrets += action value - node value (kept in tmp; written back once, discounted, below)
+      for (int it = lane; it < (ce - cb) * H; it += G) {
+        const int c = cb + it / H, h = it % H;
+        const int e = (c - 1) * H + h;
+        tmp[e] = (R[e] + val[c * H + h]) - val[parent[c] * H + h];
+      }
+      group_sync<G>();
     }
   }
-  // regret matching (:619-634), traverser reach under the new strategy (:636-638), regret discount,
-  // sum-strategy update (:639-661); top-down so reach of the parent is ready.
-  float* rt = trav ? reach1 : reach0;
-  const float* b = p.beliefs + ((size_t)k * 2 + trav) * H;
+  // ---- root value running mean (:579-590) and discounts (:592-617)
+  const int s = p.steps[2 * k + trav];
+  {
+    const real alpha = p.linear ? (real)2 / (s + 2) : (real)1 / (s + 1);
+    real* mu = p.mu + ((size_t)k * 2 + trav) * H;
+    for (int h = lane; h < H; h += G) mu[h] += (val[h] - mu[h]) * alpha;
+  }
+  real pos = 1, neg = 1, strat = 1;
+  {
+    const real ns = (real)(s + 1);
+    if (p.linear) {
+      pos = neg = strat = ns / (ns + 1);
+    } else if (p.dcfr) {
+      pos = p.dcfr_alpha >= 5 ? (real)1 : rpow(ns, p.dcfr_alpha) / (rpow(ns, p.dcfr_alpha) + 1);
+      neg = p.dcfr_beta <= -5 ? (real)0 : rpow(ns, p.dcfr_beta) / (rpow(ns, p.dcfr_beta) + 1);
+      strat = rpow(ns / (ns + 1), p.dcfr_gamma);
+    }
+  }
+  // ---- top-down: regret matching (:619-634), traverser reach under the new strategy (:636-638), regret
+  // discount and sum-strategy update (:639-661).  val[] is reused for the per-(node,hand) positive-regret sums.
+  const real* __restrict__ b = p.beliefs + ((size_t)k * 2 + trav) * H;
+  group_sync<G>();
   for (int h = lane; h < H; h += G) rt[h] = b[h];
   group_sync<G>();
   for (int d = 0; d + 1 < t.levels; ++d) {
     const int nb = p.level_begin[t.level_off + d], ne = p.level_begin[t.level_off + d + 1];
+    const int cb = ne, ce = p.level_begin[t.level_off + d + 2];
     const bool mine = (rp ^ (d & 1)) == trav;
-    for (int it = lane; it < (ne - nb) * H; it += G) {
-      const int n = nb + it / H, h = it % H;
-      const int nc = p.nchild[t.node_off + n];
-      if (!nc) continue;
-      const int c0 = p.child_begin[t.node_off + n];
-      const float rn = rt[n * H + h];
-      if (mine) {
-        float sum = 0.f;
-        for (int j = 0; j < nc; ++j) sum += fmaxf(R[(c0 + j - 1) * H + h], 0.f);
-        const float inv = sum > 0.f ? 1.f / sum : 0.f, uni = 1.f / nc;
-        for (int j = 0; j < nc; ++j) {
-          const int e = (c0 + j - 1) * H + h;
-          const float r = R[e];
-          const float sg = sum > 0.f ? fmaxf(r, 0.f) * inv : uni;
-          Sg[e] = sg;
-          R[e] = r * (r > 0.f ? pos : neg);
-          S[e] = S[e] * strat + rn * sg;
-          rt[(c0 + j) * H + h] = rn * sg;
-        }
-      } else {
-        for (int j = 0; j < nc; ++j) rt[(c0 + j) * H + h] = rn;
+    if (mine) {
+      for (int it = lane; it < (ne - nb) * H; it += G) {
+        const int n = nb + it / H, h = it % H;
+        const int nc = nchild[n];
+        if (!nc) continue;
+        const int c0 = child_begin[n];
+        real sum = 0;
+        for (int j = 0; j < nc; ++j) sum += rmax0(tmp[(c0 + j - 1) * H + h]);
+        val[n * H + h] = sum;
+      }
+      group_sync<G>();
+      for (int it = lane; it < (ce - cb) * H; it += G) {
+        const int c = cb + it / H, h = it % H;
+        const int e = (c - 1) * H + h, par = parent[c];
+        const real r = tmp[e], sum = val[par * H + h], rn = rt[par * H + h];
+        const real sg = sum > 0 ? rmax0(r) / sum : (real)1 / nchild[par];
+        Sg[e] = sg;
+        R[e] = r * (r > 0 ? pos : neg);
+        S[e] = S[e] * strat + rn * sg;
+        rt[c * H + h] = rn * sg;
+      }
+    } else {
+      for (int it = lane; it < (ce - cb) * H; it += G) {
+        const int c = cb + it / H, h = it % H;
+        rt[c * H + h] = rt[parent[c] * H + h];
       }
     }
     group_sync<G>();
@@ -266,69 +289,71 @@ __device__ void cfr_backward(const CfrDev& p, int k, int trav, float* reach0, fl
 }
 
 // iter: global iteration index of the forward half.  do_b: run backward half of iteration iter-1 first.
-template <int G>
-__global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev p, int iter, int do_b, int do_f, int smem_floats_per_group) {
-  extern __shared__ float smem[];
+template <typename real, int G>
+__global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* smem = reinterpret_cast<real*>(smem_raw);
   const int groups_per_cta = blockDim.x / G;
   const int gid = threadIdx.x / G, lane = threadIdx.x % G;
   const int k = blockIdx.x * groups_per_cta + gid;
-  const int n = *p.wave_n;
-  if (k >= n) return;   // uniform per group (and per CTA when G == blockDim.x)
+  if (k >= *p.wave_n) return;   // uniform per group (and per CTA when G == blockDim.x)
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int NH = t.N * p.H;
-  float* base = (p.scratch != nullptr) ? p.scratch + (size_t)k * p.scratch_stride : smem + (size_t)gid * smem_floats_per_group;
-  float* reach0 = base; float* reach1 = base + NH; float* val = base + 2 * NH; float* lsum = base + 3 * NH;
+  real* base = (G == 32) ? smem + (size_t)gid * scratch_per_group : p.scratch + (size_t)k * p.scratch_stride;
+  real* bufA = base; real* bufB = base + NH; real* tmp = base + 2 * NH; real* lsum = base + 3 * NH;
   if (do_b) {
-    cfr_backward<G>(p, k, (iter - 1) & 1, reach0, reach1, val, lane);
+    cfr_backward<real, G>(p, k, (iter - 1) & 1, bufA, bufB, tmp, lane);
     group_sync<G>();
   }
   // sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
   if (p.sg_act_iter[k] == iter) {
-    const float* Sg = p.Sg + (size_t)k * p.table_stride;
-    float* Sn = p.Snap + (size_t)k * p.table_stride;
+    const real* __restrict__ Sg = p.Sg + (size_t)k * p.table_stride;
+    real* __restrict__ Sn = p.Snap + (size_t)k * p.table_stride;
     for (int i = lane; i < (t.N - 1) * p.H; i += G) Sn[i] = Sg[i];
   }
-  if (do_f) cfr_forward<G>(p, k, iter & 1, reach0, reach1, lsum, lane);
+  if (do_f) cfr_forward<real, G>(p, k, iter & 1, bufA, bufB, lsum, lane);
 }
 
 // Wave initialisation == CFR constructor (subgame_solving.cc:509-524): uniform last strategy, zero regrets,
 // sum = uniform * reach-under-uniform of the acting player (get_uniform_reach_weigted_strategy :125-149).
-template <int G>
-__global__ void __launch_bounds__(256) cfr_init_kernel(CfrDev p, int smem_floats_per_group) {
-  extern __shared__ float smem[];
+template <typename real, int G>
+__global__ void __launch_bounds__(256) cfr_init_kernel(CfrDev<real> p, int scratch_per_group) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* smem = reinterpret_cast<real*>(smem_raw);
   const int groups_per_cta = blockDim.x / G;
   const int gid = threadIdx.x / G, lane = threadIdx.x % G;
   const int k = blockIdx.x * groups_per_cta + gid;
   if (k >= *p.wave_n) return;
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int H = p.H, NH = t.N * H;
-  float* base = (p.scratch != nullptr) ? p.scratch + (size_t)k * p.scratch_stride : smem + (size_t)gid * smem_floats_per_group;
-  float* reach0 = base; float* reach1 = base + NH;
-  float* R = p.R + (size_t)k * p.table_stride;
-  float* Sg = p.Sg + (size_t)k * p.table_stride;
-  float* S = p.S + (size_t)k * p.table_stride;
+  real* base = (G == 32) ? smem + (size_t)gid * scratch_per_group : p.scratch + (size_t)k * p.scratch_stride;
+  real* reach0 = base; real* reach1 = base + NH;
+  real* __restrict__ R = p.R + (size_t)k * p.table_stride;
+  real* __restrict__ Sg = p.Sg + (size_t)k * p.table_stride;
+  real* __restrict__ S = p.S + (size_t)k * p.table_stride;
+  const int* __restrict__ parent = p.parent + t.node_off;
+  const int* __restrict__ nchild = p.nchild + t.node_off;
+  const real* __restrict__ b = p.beliefs + (size_t)k * 2 * H;
   const int rp = p.sg_player[k];
-  for (int n = 0; n < t.N; ++n) {
-    const int nc = p.nchild[t.node_off + n];
-    if (!nc) continue;
-    const int c0 = p.child_begin[t.node_off + n];
-    const float u = 1.f / nc;
-    for (int it = lane; it < nc * H; it += G) { Sg[(c0 - 1) * H + it] = u; R[(c0 - 1) * H + it] = 0.f; }
-  }
+  for (int h = lane; h < H; h += G) { reach0[h] = b[h]; reach1[h] = b[H + h]; }
   group_sync<G>();
-  reach_pass<G>(p, t, rp, Sg, p.beliefs + (size_t)k * 2 * H, reach0, reach1, lane);
-  for (int d = 0; d + 1 < t.levels; ++d) {
+  for (int d = 1; d < t.levels; ++d) {
     const int nb = p.level_begin[t.level_off + d], ne = p.level_begin[t.level_off + d + 1];
-    const float* ra = (rp ^ (d & 1)) ? reach1 : reach0;
+    const int actor = rp ^ ((d - 1) & 1);
     for (int it = lane; it < (ne - nb) * H; it += G) {
-      const int n = nb + it / H, h = it % H;
-      const int nc = p.nchild[t.node_off + n];
-      if (!nc) continue;
-      const int c0 = p.child_begin[t.node_off + n];
-      for (int j = 0; j < nc; ++j) S[(c0 + j - 1) * H + h] = Sg[(c0 + j - 1) * H + h] * ra[n * H + h];
+      const int c = nb + it / H, h = it % H;
+      const int par = parent[c], e = (c - 1) * H + h;
+      const real u = (real)1 / nchild[par];
+      const real a0 = reach0[par * H + h], a1 = reach1[par * H + h];
+      Sg[e] = u;
+      R[e] = 0;
+      S[e] = u * (actor == 0 ? a0 : a1);
+      reach0[c * H + h] = actor == 0 ? a0 * u : a0;
+      reach1[c * H + h] = actor == 1 ? a1 * u : a1;
     }
+    group_sync<G>();
   }
-  for (int i = lane; i < 2 * H; i += G) p.mu[(size_t)k * 2 * H + i] = 0.f;
+  for (int i = lane; i < 2 * H; i += G) p.mu[(size_t)k * 2 * H + i] = 0;
   if (lane < 2) p.steps[2 * k + lane] = 0;
 }
 

@@ -2,13 +2,13 @@
 // Plain CUDA runtime; no torch, no CPU fallback: every entry point that computes needs the device.
 #include "../../include/cfrb200.h"
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
-#include <map>
 #include <string>
 #include <vector>
 
@@ -47,6 +47,17 @@ struct DevBuf {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Typed (fp32 / fp64) part of the solver state.
+template <typename real>
+struct WaveState {
+  DevBuf<real> beliefs, mu, R, Sg, S, Snap, vterm, scaler, scratch;
+  cfrb::CfrDev<real> dev{};
+  void release() {
+    beliefs.release(); mu.release(); R.release(); Sg.release(); S.release(); Snap.release(); vterm.release();
+    scaler.release(); scratch.release();
+  }
+};
+
 }  // namespace
 
 struct cfrb_handle {
@@ -55,10 +66,12 @@ struct cfrb_handle {
   std::vector<cfrb::TreeTemplate> tmpl;   // index = root_bid + 1
   int Nmax = 0, Lmax = 0, Tmax = 0;
   int Qpad = 0, Hout = 0;
+  bool f64 = true;
   int group = 32;          // threads per subgame group (32 = warp, 256 = CTA with global scratch)
   int groups_per_cta = 8;
-  int smem_per_group = 0;  // floats
+  int scratch_per_group = 0;  // reals
   int table_stride = 0;
+  int num_sms = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   bool profiling = false;
@@ -66,33 +79,227 @@ struct cfrb_handle {
   int net_ev_used = 0;
   // device: templates
   DevBuf<cfrb::TemplateDev> d_tmpl;
-  DevBuf<int> d_child_begin, d_nchild, d_last_bid, d_kind, d_slot, d_level_begin, d_pleaf_node, d_term_node;
+  DevBuf<int> d_parent, d_child_begin, d_nchild, d_last_bid, d_level_begin, d_pleaf_node, d_term_node;
   DevBuf<unsigned char> d_matches;
-  // device: wave
+  // device: wave (untyped part)
   DevBuf<int> d_wave;      // [0] = n, [1] = rows
-  DevBuf<int> d_sg_tmpl, d_sg_player, d_sg_row_off, d_sg_act;
-  DevBuf<float> d_beliefs, d_mu;
-  DevBuf<int> d_steps;
-  DevBuf<float> d_R, d_Sg, d_S, d_Snap, d_vterm, d_X, d_out, d_scaler, d_scratch;
+  DevBuf<int> d_sg_tmpl, d_sg_player, d_sg_row_off, d_sg_act, d_steps;
+  DevBuf<float> d_X, d_out, d_dbg;
+  DevBuf<__half> d_Xh;
+  WaveState<float> sf;
+  WaveState<double> sd;
   // device: weights
   DevBuf<float> d_w;
-  DevBuf<uint8_t> d_blob;      // tensor-core weight blob (leaf_mlp_tc.cuh BlobLayout)
-  DevBuf<__half> d_Xh;         // fp16 query tiles in UMMA order
-  DevBuf<float> d_dbg;         // [2][128][256] debug taps
-  int num_sms = 0;
+  DevBuf<uint8_t> d_blob;
   cfrb::NetDev net{};
   bool have_weights = false;
   uint64_t weights_version = 0;
   // host mirror of the wave
   int n = 0, rows = 0, iters_done = 0;
   std::vector<int> h_tmpl, h_player, h_row_off, h_last_bid;
-  std::vector<float> h_beliefs;
+  std::vector<double> h_beliefs;
   int64_t launches = 0;
   float last_total_ms = 0.f, last_net_ms = 0.f;
-  cfrb::CfrDev dev{};
 };
 
+template <typename real> static WaveState<real>& state_of(cfrb_handle* h);
+template <> WaveState<float>& state_of<float>(cfrb_handle* h) { return h->sf; }
+template <> WaveState<double>& state_of<double>(cfrb_handle* h) { return h->sd; }
+
+#define DISPATCH_REAL(h, fn, ...) ((h)->f64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
 using cfrb::TemplateDev;
+
+// ------------------------------------------------------------------------------------------ typed helpers
+template <typename real>
+static int alloc_state(cfrb_handle* h, int max_optin) {
+  auto& s = state_of<real>(h);
+  const auto& g = h->g;
+  const int K = h->cfg.max_subgames;
+  const size_t tab = (size_t)K * h->table_stride;
+  const size_t rows_cap = (size_t)K * std::max(h->Lmax, 1);
+  CK(s.beliefs.alloc((size_t)K * 2 * g.H)); CK(s.mu.alloc((size_t)K * 2 * g.H));
+  CK(s.R.alloc(tab)); CK(s.Sg.alloc(tab)); CK(s.S.alloc(tab)); CK(s.Snap.alloc(tab));
+  CK(s.vterm.alloc((size_t)K * std::max(h->Tmax, 1) * g.H)); CK(s.scaler.alloc(rows_cap));
+  CK(cudaMemset(s.Snap.p, 0, tab * sizeof(real)));
+  const size_t per_group_bytes = (size_t)h->scratch_per_group * sizeof(real);
+  if (per_group_bytes * 2 <= (size_t)max_optin) {
+    h->group = 32;
+    // as many warps per CTA as keep >= 2 CTAs per SM within the shared-memory budget
+    h->groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_optin / 2 / per_group_bytes));
+    const int smem_bytes = (int)(per_group_bytes * h->groups_per_cta);
+    CK(cudaFuncSetAttribute(cfrb::cfr_iter_kernel<real, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CK(cudaFuncSetAttribute(cfrb::cfr_init_kernel<real, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  } else {
+    h->group = 256;
+    h->groups_per_cta = 1;
+    CK(s.scratch.alloc((size_t)K * h->scratch_per_group));
+  }
+  cfrb::CfrDev<real>& d = s.dev;
+  d.A = g.A; d.H = g.H; d.F = g.F; d.Q = g.Q; d.Qpad = h->Qpad; d.Hout = h->Hout;
+  d.tmpl = h->d_tmpl.p; d.parent = h->d_parent.p; d.child_begin = h->d_child_begin.p; d.nchild = h->d_nchild.p;
+  d.last_bid = h->d_last_bid.p; d.level_begin = h->d_level_begin.p; d.pleaf_node = h->d_pleaf_node.p;
+  d.term_node = h->d_term_node.p; d.matches = h->d_matches.p;
+  d.wave_n = h->d_wave.p; d.sg_tmpl = h->d_sg_tmpl.p; d.sg_player = h->d_sg_player.p; d.sg_row_off = h->d_sg_row_off.p;
+  d.sg_act_iter = h->d_sg_act.p; d.beliefs = s.beliefs.p; d.mu = s.mu.p; d.steps = h->d_steps.p;
+  d.R = s.R.p; d.Sg = s.Sg.p; d.S = s.S.p; d.Snap = s.Snap.p; d.table_stride = h->table_stride;
+  d.vterm = s.vterm.p; d.vterm_stride = std::max(h->Tmax, 1) * g.H;
+  d.X = h->cfg.net_mode == CFRB_NET_FP32 ? h->d_X.p : nullptr;
+  d.Xh = h->cfg.net_mode == CFRB_NET_TC_F16 ? h->d_Xh.p : nullptr;
+  d.net_out = h->d_out.p; d.scaler = s.scaler.p;
+  d.scratch = h->group == 32 ? nullptr : s.scratch.p; d.scratch_stride = h->scratch_per_group;
+  d.linear = h->cfg.linear_update; d.dcfr = h->cfg.dcfr;
+  d.dcfr_alpha = (real)h->cfg.dcfr_alpha; d.dcfr_beta = (real)h->cfg.dcfr_beta; d.dcfr_gamma = (real)h->cfg.dcfr_gamma;
+  d.use_net = h->cfg.net_mode != CFRB_NET_ZERO;
+  return CFRB_OK;
+}
+
+template <typename real>
+static int launch_init_t(cfrb_handle* h, cudaStream_t st) {
+  auto& s = state_of<real>(h);
+  const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
+  if (h->group == 32) {
+    const size_t smem = (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta;
+    cfrb::cfr_init_kernel<real, 32><<<blocks, 32 * h->groups_per_cta, smem, st>>>(s.dev, h->scratch_per_group);
+  } else {
+    cfrb::cfr_init_kernel<real, 256><<<blocks, 256, 0, st>>>(s.dev, h->scratch_per_group);
+  }
+  ++h->launches;
+  CK(cudaGetLastError());
+  return CFRB_OK;
+}
+
+template <typename real>
+static int launch_iter_t(cfrb_handle* h, cudaStream_t st, int iter, int do_b, int do_f) {
+  auto& s = state_of<real>(h);
+  const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
+  if (h->group == 32) {
+    const size_t smem = (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta;
+    cfrb::cfr_iter_kernel<real, 32><<<blocks, 32 * h->groups_per_cta, smem, st>>>(s.dev, iter, do_b, do_f, h->scratch_per_group);
+  } else {
+    cfrb::cfr_iter_kernel<real, 256><<<blocks, 256, 0, st>>>(s.dev, iter, do_b, do_f, h->scratch_per_group);
+  }
+  ++h->launches;
+  CK(cudaGetLastError());
+  return CFRB_OK;
+}
+
+template <typename real>
+static int upload_beliefs_t(cfrb_handle* h, cudaStream_t st) {
+  auto& s = state_of<real>(h);
+  std::vector<real> tmp(h->h_beliefs.begin(), h->h_beliefs.end());
+  CK(cudaMemcpyAsync(s.beliefs.p, tmp.data(), tmp.size() * sizeof(real), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  return CFRB_OK;
+}
+
+// compact [E][H] (edge = child-1) <-> dense [Nmax][H][A]
+template <typename real>
+static void to_dense(const cfrb_handle* h, int k, const real* compact, double* dense) {
+  const auto& t = h->tmpl[h->h_tmpl[k]];
+  const int H = h->g.H, A = h->g.A;
+  std::memset(dense, 0, sizeof(double) * (size_t)h->Nmax * H * A);
+  for (int n = 0; n < t.N; ++n)
+    for (int j = 0; j < t.nchild[n]; ++j) {
+      const int c = t.child_begin[n] + j, a = t.act_lo[n] + j;
+      for (int hd = 0; hd < H; ++hd) dense[((size_t)n * H + hd) * A + a] = (double)compact[(size_t)(c - 1) * H + hd];
+    }
+}
+template <typename real>
+static void from_dense(const cfrb_handle* h, int k, const double* dense, real* compact) {
+  const auto& t = h->tmpl[h->h_tmpl[k]];
+  const int H = h->g.H, A = h->g.A;
+  for (int n = 0; n < t.N; ++n)
+    for (int j = 0; j < t.nchild[n]; ++j) {
+      const int c = t.child_begin[n] + j, a = t.act_lo[n] + j;
+      for (int hd = 0; hd < H; ++hd) compact[(size_t)(c - 1) * H + hd] = (real)dense[((size_t)n * H + hd) * A + a];
+    }
+}
+
+template <typename real>
+static int fetch_t(cfrb_handle* h, double* root_value_means, double* snapshot_strategy, double* last_strategy, double* avg_strategy,
+                   double* sum_strategy, double* regrets) {
+  auto& s = state_of<real>(h);
+  const int n = h->n, H = h->g.H, A = h->g.A;
+  if (root_value_means) {
+    std::vector<real> mu((size_t)n * 2 * H);
+    CK(cudaMemcpy(mu.data(), s.mu.p, mu.size() * sizeof(real), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < mu.size(); ++i) root_value_means[i] = (double)mu[i];
+  }
+  const size_t dense_sz = (size_t)h->Nmax * H * A;
+  std::vector<real> tmp;
+  auto pull = [&](const real* dsrc, double* out, bool normalise) -> int {
+    tmp.resize((size_t)n * h->table_stride);
+    CK(cudaMemcpy(tmp.data(), dsrc, tmp.size() * sizeof(real), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; ++k) {
+      double* dk = out + (size_t)k * dense_sz;
+      to_dense<real>(h, k, tmp.data() + (size_t)k * h->table_stride, dk);
+      if (normalise) {   // average strategy = normalised sum (subgame_solving.cc:659-660)
+        const auto& t = h->tmpl[h->h_tmpl[k]];
+        for (int nn = 0; nn < t.N; ++nn) {
+          if (!t.nchild[nn]) continue;
+          for (int hd = 0; hd < H; ++hd) {
+            double* row = dk + ((size_t)nn * H + hd) * A;
+            double sum = 0;
+            for (int a = 0; a < A; ++a) sum += row[a];
+            if (sum > 0) for (int a = 0; a < A; ++a) row[a] /= sum;
+            else for (int j = 0; j < t.nchild[nn]; ++j) row[t.act_lo[nn] + j] = 1.0 / t.nchild[nn];
+          }
+        }
+      }
+    }
+    return CFRB_OK;
+  };
+  int rc = CFRB_OK;
+  if (snapshot_strategy && (rc = pull(s.Snap.p, snapshot_strategy, false))) return rc;
+  if (last_strategy && (rc = pull(s.Sg.p, last_strategy, false))) return rc;
+  if (avg_strategy && (rc = pull(s.S.p, avg_strategy, true))) return rc;
+  if (sum_strategy && (rc = pull(s.S.p, sum_strategy, false))) return rc;
+  if (regrets && (rc = pull(s.R.p, regrets, false))) return rc;
+  return CFRB_OK;
+}
+
+template <typename real>
+static int load_state_t(cfrb_handle* h, const double* regrets, const double* last_strategy, const double* sum_strategy,
+                        const double* root_value_means) {
+  auto& s = state_of<real>(h);
+  const int n = h->n, H = h->g.H, A = h->g.A;
+  const size_t dense_sz = (size_t)h->Nmax * H * A;
+  std::vector<real> tmp((size_t)n * h->table_stride);
+  auto push = [&](const double* dense, real* ddst) -> int {
+    CK(cudaMemcpy(tmp.data(), ddst, tmp.size() * sizeof(real), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; ++k) from_dense<real>(h, k, dense + (size_t)k * dense_sz, tmp.data() + (size_t)k * h->table_stride);
+    CK(cudaMemcpy(ddst, tmp.data(), tmp.size() * sizeof(real), cudaMemcpyHostToDevice));
+    return CFRB_OK;
+  };
+  int rc;
+  if (regrets && (rc = push(regrets, s.R.p))) return rc;
+  if (last_strategy && (rc = push(last_strategy, s.Sg.p))) return rc;
+  if (sum_strategy && (rc = push(sum_strategy, s.S.p))) return rc;
+  if (root_value_means) {
+    std::vector<real> mu(root_value_means, root_value_means + (size_t)n * 2 * H);
+    CK(cudaMemcpy(s.mu.p, mu.data(), mu.size() * sizeof(real), cudaMemcpyHostToDevice));
+  }
+  return CFRB_OK;
+}
+
+template <typename real>
+static int examples_values_t(cfrb_handle* h, float* values) {
+  auto& s = state_of<real>(h);
+  std::vector<real> mu((size_t)h->n * 2 * h->g.H);
+  CK(cudaMemcpy(mu.data(), s.mu.p, mu.size() * sizeof(real), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < mu.size(); ++i) values[i] = (float)mu[i];   // std::copy_n into a float tensor, subgame_solving.cc:224
+  return CFRB_OK;
+}
+
+template <typename real>
+static int scalers_t(cfrb_handle* h, double* out, int rows) {
+  auto& s = state_of<real>(h);
+  std::vector<real> v(rows);
+  CK(cudaMemcpy(v.data(), s.scaler.p, (size_t)rows * sizeof(real), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < rows; ++i) out[i] = (double)v[i];
+  return CFRB_OK;
+}
 
 extern "C" {
 
@@ -108,13 +315,11 @@ int cfrb_destroy(cfrb_handle* h) {
   if (!h) return CFRB_OK;
   cudaSetDevice(h->cfg.device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-  h->d_tmpl.release(); h->d_child_begin.release(); h->d_nchild.release(); h->d_last_bid.release();
-  h->d_kind.release(); h->d_slot.release(); h->d_level_begin.release(); h->d_pleaf_node.release();
-  h->d_term_node.release(); h->d_matches.release(); h->d_wave.release(); h->d_sg_tmpl.release();
-  h->d_sg_player.release(); h->d_sg_row_off.release(); h->d_sg_act.release(); h->d_beliefs.release();
-  h->d_mu.release(); h->d_steps.release(); h->d_R.release(); h->d_Sg.release(); h->d_S.release();
-  h->d_Snap.release(); h->d_vterm.release(); h->d_X.release(); h->d_out.release(); h->d_scaler.release();
-  h->d_scratch.release(); h->d_w.release(); h->d_blob.release(); h->d_Xh.release(); h->d_dbg.release();
+  h->d_tmpl.release(); h->d_parent.release(); h->d_child_begin.release(); h->d_nchild.release(); h->d_last_bid.release();
+  h->d_level_begin.release(); h->d_pleaf_node.release(); h->d_term_node.release(); h->d_matches.release();
+  h->d_wave.release(); h->d_sg_tmpl.release(); h->d_sg_player.release(); h->d_sg_row_off.release(); h->d_sg_act.release();
+  h->d_steps.release(); h->d_X.release(); h->d_out.release(); h->d_dbg.release(); h->d_Xh.release();
+  h->sf.release(); h->sd.release(); h->d_w.release(); h->d_blob.release();
   for (auto e : h->net_ev) cudaEventDestroy(e);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
@@ -135,13 +340,15 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   if (cfg->num_dice < 1 || cfg->num_faces < 1 || cfg->max_depth < 1 || cfg->max_subgames < 1)
     return fail(CFRB_EINVAL, "num_dice, num_faces, max_depth, max_subgames must be >= 1");
   if (cfg->net_mode < CFRB_NET_ZERO || cfg->net_mode > CFRB_NET_TC_F16) return fail(CFRB_EINVAL, "bad net_mode");
+  if (cfg->state_dtype != CFRB_STATE_F64 && cfg->state_dtype != CFRB_STATE_F32) return fail(CFRB_EINVAL, "bad state_dtype");
   if (cfg->net_mode != CFRB_NET_ZERO && cfg->hidden != 256) return fail(CFRB_EINVAL, "only hidden == 256 is built");
+  h->f64 = cfg->state_dtype == CFRB_STATE_F64;
   h->g = cfrb::GameShape(cfg->num_dice, cfg->num_faces);
   const auto& g = h->g;
   if (g.A > 1024 || g.H > 4096) return fail(CFRB_EINVAL, "game too large");
   // ---- templates: root_bid in {-1, 0 .. A-2}
   std::vector<TemplateDev> td;
-  std::vector<int> child_begin, nchild, last_bid, kind, slot, level_begin, pleaf_node, term_node;
+  std::vector<int> parent, child_begin, nchild, last_bid, level_begin, pleaf_node, term_node;
   for (int rb = -1; rb <= g.A - 2; ++rb) {
     h->tmpl.push_back(cfrb::build_template(g, rb, cfg->max_depth));
     const auto& t = h->tmpl.back();
@@ -150,19 +357,18 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     d.pleaf_off = (int)pleaf_node.size(); d.term_off = (int)term_node.size();
     d.N = t.N; d.L = t.L; d.T = t.T; d.levels = t.levels;
     td.push_back(d);
+    parent.insert(parent.end(), t.parent.begin(), t.parent.end());
     child_begin.insert(child_begin.end(), t.child_begin.begin(), t.child_begin.end());
     nchild.insert(nchild.end(), t.nchild.begin(), t.nchild.end());
     last_bid.insert(last_bid.end(), t.last_bid.begin(), t.last_bid.end());
-    kind.insert(kind.end(), t.kind.begin(), t.kind.end());
-    slot.insert(slot.end(), t.slot.begin(), t.slot.end());
     level_begin.insert(level_begin.end(), t.level_begin.begin(), t.level_begin.end());
+    level_begin.push_back(t.N);   // sentinel: "children of the last level" is an empty range
     pleaf_node.insert(pleaf_node.end(), t.pleaf_node.begin(), t.pleaf_node.end());
     term_node.insert(term_node.end(), t.term_node.begin(), t.term_node.end());
     for (int n : t.term_node) term_node.push_back(t.last_bid[t.parent[n]]);   // challenged bid
     for (int n : t.term_node) term_node.push_back(t.depth[n]);
     h->Nmax = std::max(h->Nmax, t.N); h->Lmax = std::max(h->Lmax, t.L); h->Tmax = std::max(h->Tmax, t.T);
   }
-  if (cfg->net_mode == CFRB_NET_ZERO) { /* pseudo-leaves evaluate to 0, like create_zero_net */ }
   std::vector<unsigned char> matches((size_t)g.H * g.F);
   for (int hd = 0; hd < g.H; ++hd)
     for (int f = 0; f < g.F; ++f) matches[(size_t)hd * g.F + f] = (unsigned char)g.num_matches(hd, f);
@@ -172,39 +378,27 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     if (e != cudaSuccess) return e;
     return cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice);
   };
-  CK(up(h->d_tmpl, td)); CK(up(h->d_child_begin, child_begin)); CK(up(h->d_nchild, nchild));
-  CK(up(h->d_last_bid, last_bid)); CK(up(h->d_kind, kind)); CK(up(h->d_slot, slot));
-  CK(up(h->d_level_begin, level_begin)); CK(up(h->d_pleaf_node, pleaf_node)); CK(up(h->d_term_node, term_node));
-  CK(up(h->d_matches, matches));
+  CK(up(h->d_tmpl, td)); CK(up(h->d_parent, parent)); CK(up(h->d_child_begin, child_begin)); CK(up(h->d_nchild, nchild));
+  CK(up(h->d_last_bid, last_bid)); CK(up(h->d_level_begin, level_begin)); CK(up(h->d_pleaf_node, pleaf_node));
+  CK(up(h->d_term_node, term_node)); CK(up(h->d_matches, matches));
 
   // ---- sizes
   const int K = cfg->max_subgames;
   h->Qpad = round_up(g.Q, 16);
   h->Hout = g.H;
   h->table_stride = std::max(1, (h->Nmax - 1) * g.H);
-  h->smem_per_group = 3 * h->Nmax * g.H + 2 * std::max(h->Lmax, 1);
+  h->scratch_per_group = cfrb::cfr_scratch_reals(h->Nmax, g.H, h->Lmax);
   int max_optin = 0;
   CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-  const size_t per_group_bytes = (size_t)h->smem_per_group * sizeof(float);
-  if (per_group_bytes * 2 <= (size_t)max_optin) {
-    h->group = 32;
-    h->groups_per_cta = (int)std::min<size_t>(8, (size_t)max_optin / 2 / per_group_bytes);   // leave room for 2 CTAs/SM
-    h->groups_per_cta = std::max(h->groups_per_cta, 1);
-  } else {
-    h->group = 256;
-    h->groups_per_cta = 1;
-    CK(h->d_scratch.alloc((size_t)K * h->smem_per_group));
-  }
+  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(h->d_wave.alloc(2));
   CK(h->d_sg_tmpl.alloc(K)); CK(h->d_sg_player.alloc(K)); CK(h->d_sg_row_off.alloc(K)); CK(h->d_sg_act.alloc(K));
-  CK(h->d_beliefs.alloc((size_t)K * 2 * g.H)); CK(h->d_mu.alloc((size_t)K * 2 * g.H)); CK(h->d_steps.alloc((size_t)K * 2));
-  const size_t tab = (size_t)K * h->table_stride;
-  CK(h->d_R.alloc(tab)); CK(h->d_Sg.alloc(tab)); CK(h->d_S.alloc(tab)); CK(h->d_Snap.alloc(tab));
-  CK(h->d_vterm.alloc((size_t)K * std::max(h->Tmax, 1) * g.H));
+  CK(h->d_steps.alloc((size_t)K * 2));
   const size_t rows_cap = (size_t)K * std::max(h->Lmax, 1);
-  CK(h->d_X.alloc(cfg->net_mode == CFRB_NET_TC_F16 ? 1 : rows_cap * h->Qpad));
-  CK(h->d_out.alloc(rows_cap * h->Hout)); CK(h->d_scaler.alloc(rows_cap));
-  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  CK(h->d_X.alloc(cfg->net_mode == CFRB_NET_FP32 ? rows_cap * h->Qpad : 1));
+  CK(h->d_out.alloc(rows_cap * h->Hout));
+  CK(cudaMemset(h->d_wave.p, 0, 2 * sizeof(int)));
+  CK(cudaMemset(h->d_out.p, 0, rows_cap * h->Hout * sizeof(float)));
   if (cfg->net_mode == CFRB_NET_TC_F16) {
     if (g.H > cfrb::tc::kNout) return fail(CFRB_EINVAL, "CFRB_NET_TC_F16 supports num_hands <= 16");
     const size_t tiles = (rows_cap + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
@@ -215,36 +409,12 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     if (L.smem_bytes > max_optin) return fail(CFRB_EINVAL, "tensor-core value net does not fit shared memory for this game shape");
     CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
   }
-  CK(cudaMemset(h->d_wave.p, 0, 2 * sizeof(int)));
-  CK(cudaMemset(h->d_Snap.p, 0, tab * sizeof(float)));
-  CK(cudaMemset(h->d_out.p, 0, rows_cap * h->Hout * sizeof(float)));
-  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreate(&h->ev_a)); CK(cudaEventCreate(&h->ev_b));
-
-  // ---- kernel attributes
-  const int smem_bytes = h->group == 32 ? (int)(per_group_bytes * h->groups_per_cta) : 0;
-  if (h->group == 32) {
-    CK(cudaFuncSetAttribute(cfrb::cfr_iter_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    CK(cudaFuncSetAttribute(cfrb::cfr_init_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  }
   CK(cudaFuncSetAttribute(cfrb::leaf_mlp_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)cfrb::leaf_mlp_fp32_smem(256)));
-
-  // ---- device view
-  cfrb::CfrDev& d = h->dev;
-  d.A = g.A; d.H = g.H; d.F = g.F; d.Q = g.Q; d.Qpad = h->Qpad; d.Hout = h->Hout;
-  d.tmpl = h->d_tmpl.p; d.child_begin = h->d_child_begin.p; d.nchild = h->d_nchild.p; d.last_bid = h->d_last_bid.p;
-  d.kind = h->d_kind.p; d.slot = h->d_slot.p; d.level_begin = h->d_level_begin.p; d.pleaf_node = h->d_pleaf_node.p;
-  d.term_node = h->d_term_node.p; d.matches = h->d_matches.p;
-  d.wave_n = h->d_wave.p; d.sg_tmpl = h->d_sg_tmpl.p; d.sg_player = h->d_sg_player.p; d.sg_row_off = h->d_sg_row_off.p;
-  d.sg_act_iter = h->d_sg_act.p; d.beliefs = h->d_beliefs.p; d.mu = h->d_mu.p; d.steps = h->d_steps.p;
-  d.R = h->d_R.p; d.Sg = h->d_Sg.p; d.S = h->d_S.p; d.Snap = h->d_Snap.p; d.table_stride = h->table_stride;
-  d.vterm = h->d_vterm.p; d.vterm_stride = std::max(h->Tmax, 1) * g.H;
-  d.X = cfg->net_mode == CFRB_NET_TC_F16 ? nullptr : h->d_X.p; d.Xh = h->d_Xh.p; d.net_out = h->d_out.p; d.scaler = h->d_scaler.p;
-  d.scratch = h->group == 32 ? nullptr : h->d_scratch.p; d.scratch_stride = h->smem_per_group;
-  d.linear = cfg->linear_update; d.dcfr = cfg->dcfr;
-  d.dcfr_alpha = (float)cfg->dcfr_alpha; d.dcfr_beta = (float)cfg->dcfr_beta; d.dcfr_gamma = (float)cfg->dcfr_gamma;
-  d.use_net = cfg->net_mode != CFRB_NET_ZERO;
+  int rc = DISPATCH_REAL(h, alloc_state, h, max_optin);
+  if (rc) return rc;
+  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev_a)); CK(cudaEventCreate(&h->ev_b));
   return CFRB_OK;
 }
 
@@ -268,38 +438,33 @@ int cfrb_num_hands(const cfrb_handle* h) { return h->g.H; }
 int cfrb_query_size(const cfrb_handle* h) { return h->g.Q; }
 int cfrb_max_nodes(const cfrb_handle* h) { return h->Nmax; }
 
+static void export_tree(const cfrb::TreeTemplate& t, int player_id, cfrb_node* out, int cap) {
+  for (int n = 0; n < t.N && n < cap; ++n) {
+    out[n].last_bid = t.last_bid[n];
+    out[n].player_id = player_id ^ (t.depth[n] & 1);
+    // like the reference, a processed node with an empty bid range (terminal above the depth limit) keeps
+    // children_begin == children_end == (tree size at that moment); unprocessed nodes keep 0/0 (tree.h:59-62)
+    out[n].children_begin = t.child_begin[n];
+    out[n].children_end = t.child_begin[n] + t.nchild[n];
+    out[n].parent = t.parent[n];
+    out[n].depth = t.depth[n];
+  }
+}
+
 int cfrb_unroll_tree(int32_t num_dice, int32_t num_faces, int32_t last_bid, int32_t player_id, int32_t max_depth,
                      cfrb_node* out, int32_t cap) {
   if (num_dice < 1 || num_faces < 1 || max_depth < 0) return fail(CFRB_EINVAL, "bad game shape");
   cfrb::GameShape g(num_dice, num_faces);
   if (last_bid < -1 || last_bid >= g.A) return fail(CFRB_EINVAL, "bad root bid");
   const auto t = cfrb::build_template(g, last_bid, max_depth);
-  for (int n = 0; n < t.N && n < cap; ++n) {
-    out[n].last_bid = t.last_bid[n];
-    out[n].player_id = player_id ^ (t.depth[n] & 1);
-    // like the reference, a processed node with an empty bid range (terminal above the depth limit) keeps
-    // children_begin == children_end == (tree size at that moment); unprocessed nodes keep 0/0 (tree.h:59-62)
-    out[n].children_begin = t.child_begin[n];
-    out[n].children_end = t.child_begin[n] + t.nchild[n];
-    out[n].parent = t.parent[n];
-    out[n].depth = t.depth[n];
-  }
+  export_tree(t, player_id, out, cap);
   return t.N;
 }
 
 int cfrb_tree_template(const cfrb_handle* h, int32_t last_bid, int32_t player_id, cfrb_node* out, int32_t cap) {
   if (!h || last_bid < -1 || last_bid > h->g.A - 2) return fail(CFRB_EINVAL, "bad root bid");
   const auto& t = h->tmpl[last_bid + 1];
-  for (int n = 0; n < t.N && n < cap; ++n) {
-    out[n].last_bid = t.last_bid[n];
-    out[n].player_id = player_id ^ (t.depth[n] & 1);
-    // like the reference, a processed node with an empty bid range (terminal above the depth limit) keeps
-    // children_begin == children_end == (tree size at that moment); unprocessed nodes keep 0/0 (tree.h:59-62)
-    out[n].children_begin = t.child_begin[n];
-    out[n].children_end = t.child_begin[n] + t.nchild[n];
-    out[n].parent = t.parent[n];
-    out[n].depth = t.depth[n];
-  }
+  export_tree(t, player_id, out, cap);
   return t.N;
 }
 
@@ -309,35 +474,11 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
   const size_t expect = (size_t)hid * Q + 3 * hid + (size_t)hid * hid + 3 * hid + (size_t)H * hid + H;
   if (n != expect) return fail(CFRB_EINVAL, "weight count mismatch: expected " + std::to_string(expect) + " got " + std::to_string(n));
   CK(cudaSetDevice(h->cfg.device));
-  // repack: transposed k-major weights for the SIMT kernel
-  const size_t total = (size_t)Qp * hid + 3 * hid + (size_t)hid * hid + 3 * hid + (size_t)hid * h->Hout + h->Hout;
-  std::vector<float> pk(total, 0.f);
   const float* w1 = flat; const float* b1 = w1 + (size_t)hid * Q; const float* g1 = b1 + hid; const float* be1 = g1 + hid;
   const float* w2 = be1 + hid; const float* b2 = w2 + (size_t)hid * hid; const float* g2 = b2 + hid; const float* be2 = g2 + hid;
   const float* w3 = be2 + hid; const float* b3 = w3 + (size_t)H * hid;
-  size_t o = 0;
-  const size_t o_w1 = o; for (int k = 0; k < Q; ++k) for (int j = 0; j < hid; ++j) pk[o_w1 + (size_t)k * hid + j] = w1[(size_t)j * Q + k];
-  o += (size_t)Qp * hid;
-  const size_t o_b1 = o; std::copy(b1, b1 + hid, pk.begin() + o); o += hid;
-  const size_t o_g1 = o; std::copy(g1, g1 + hid, pk.begin() + o); o += hid;
-  const size_t o_be1 = o; std::copy(be1, be1 + hid, pk.begin() + o); o += hid;
-  const size_t o_w2 = o; for (int k = 0; k < hid; ++k) for (int j = 0; j < hid; ++j) pk[o_w2 + (size_t)k * hid + j] = w2[(size_t)j * hid + k];
-  o += (size_t)hid * hid;
-  const size_t o_b2 = o; std::copy(b2, b2 + hid, pk.begin() + o); o += hid;
-  const size_t o_g2 = o; std::copy(g2, g2 + hid, pk.begin() + o); o += hid;
-  const size_t o_be2 = o; std::copy(be2, be2 + hid, pk.begin() + o); o += hid;
-  const size_t o_w3 = o; for (int k = 0; k < hid; ++k) for (int j = 0; j < H; ++j) pk[o_w3 + (size_t)k * h->Hout + j] = w3[(size_t)j * hid + k];
-  o += (size_t)hid * h->Hout;
-  const size_t o_b3 = o; std::copy(b3, b3 + H, pk.begin() + o); o += h->Hout;
-  if (!h->d_w.p) CK(h->d_w.alloc(total));
   // ordered after work already enqueued on the handle's stream (ModelLocker::updateModel waits for in-flight forwards)
   CK(cudaStreamSynchronize(h->own_stream));
-  CK(cudaMemcpy(h->d_w.p, pk.data(), total * sizeof(float), cudaMemcpyHostToDevice));
-  cfrb::NetDev& nd = h->net;
-  nd.Qpad = Qp; nd.hidden = hid; nd.Hout = h->Hout;
-  nd.w1t = h->d_w.p + o_w1; nd.b1 = h->d_w.p + o_b1; nd.g1 = h->d_w.p + o_g1; nd.be1 = h->d_w.p + o_be1;
-  nd.w2t = h->d_w.p + o_w2; nd.b2 = h->d_w.p + o_b2; nd.g2 = h->d_w.p + o_g2; nd.be2 = h->d_w.p + o_be2;
-  nd.w3t = h->d_w.p + o_w3; nd.b3 = h->d_w.p + o_b3;
   if (h->cfg.net_mode == CFRB_NET_TC_F16) {
     // tensor-core blob: fp16 weights in UMMA K-major core-matrix order + fp32 {bias, gamma, beta} per feature
     const cfrb::tc::BlobLayout L(Qp);
@@ -357,6 +498,31 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
     std::copy(b3, b3 + H, reinterpret_cast<float*>(blob.data() + L.off_b3));
     if (!h->d_blob.p) CK(h->d_blob.alloc(L.blob_bytes));
     CK(cudaMemcpy(h->d_blob.p, blob.data(), L.blob_bytes, cudaMemcpyHostToDevice));
+  } else {
+    // transposed k-major fp32 weights for the SIMT kernel
+    const size_t total = (size_t)Qp * hid + 3 * hid + (size_t)hid * hid + 3 * hid + (size_t)hid * h->Hout + h->Hout;
+    std::vector<float> pk(total, 0.f);
+    size_t o = 0;
+    const size_t o_w1 = o; for (int k = 0; k < Q; ++k) for (int j = 0; j < hid; ++j) pk[o_w1 + (size_t)k * hid + j] = w1[(size_t)j * Q + k];
+    o += (size_t)Qp * hid;
+    const size_t o_b1 = o; std::copy(b1, b1 + hid, pk.begin() + o); o += hid;
+    const size_t o_g1 = o; std::copy(g1, g1 + hid, pk.begin() + o); o += hid;
+    const size_t o_be1 = o; std::copy(be1, be1 + hid, pk.begin() + o); o += hid;
+    const size_t o_w2 = o; for (int k = 0; k < hid; ++k) for (int j = 0; j < hid; ++j) pk[o_w2 + (size_t)k * hid + j] = w2[(size_t)j * hid + k];
+    o += (size_t)hid * hid;
+    const size_t o_b2 = o; std::copy(b2, b2 + hid, pk.begin() + o); o += hid;
+    const size_t o_g2 = o; std::copy(g2, g2 + hid, pk.begin() + o); o += hid;
+    const size_t o_be2 = o; std::copy(be2, be2 + hid, pk.begin() + o); o += hid;
+    const size_t o_w3 = o; for (int k = 0; k < hid; ++k) for (int j = 0; j < H; ++j) pk[o_w3 + (size_t)k * h->Hout + j] = w3[(size_t)j * hid + k];
+    o += (size_t)hid * h->Hout;
+    const size_t o_b3 = o; std::copy(b3, b3 + H, pk.begin() + o);
+    if (!h->d_w.p) CK(h->d_w.alloc(total));
+    CK(cudaMemcpy(h->d_w.p, pk.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    cfrb::NetDev& nd = h->net;
+    nd.Qpad = Qp; nd.hidden = hid; nd.Hout = h->Hout;
+    nd.w1t = h->d_w.p + o_w1; nd.b1 = h->d_w.p + o_b1; nd.g1 = h->d_w.p + o_g1; nd.be1 = h->d_w.p + o_be1;
+    nd.w2t = h->d_w.p + o_w2; nd.b2 = h->d_w.p + o_b2; nd.g2 = h->d_w.p + o_g2; nd.be2 = h->d_w.p + o_be2;
+    nd.w3t = h->d_w.p + o_w3; nd.b3 = h->d_w.p + o_b3;
   }
   h->have_weights = true;
   h->weights_version = version;
@@ -365,71 +531,46 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
 
 uint64_t cfrb_weights_version(const cfrb_handle* h) { return h ? h->weights_version : 0; }
 
-static int launch_init(cfrb_handle* h, cudaStream_t st) {
-  const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
-  if (h->group == 32) {
-    const size_t smem = (size_t)h->smem_per_group * sizeof(float) * h->groups_per_cta;
-    cfrb::cfr_init_kernel<32><<<blocks, 32 * h->groups_per_cta, smem, st>>>(h->dev, h->smem_per_group);
-  } else {
-    cfrb::cfr_init_kernel<256><<<blocks, 256, 0, st>>>(h->dev, h->smem_per_group);
-  }
-  ++h->launches;
-  CK(cudaGetLastError());
-  return CFRB_OK;
-}
-
-int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const int32_t* player_id, const float* beliefs,
+int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const int32_t* player_id, const double* beliefs,
                     const int32_t* act_iteration) {
-  if (!h || !last_bid || !player_id || !beliefs) return fail(CFRB_EINVAL, "null argument");
+  if (!h || (n > 0 && (!last_bid || !player_id || !beliefs))) return fail(CFRB_EINVAL, "null argument");
   if (n < 0 || n > h->cfg.max_subgames) return fail(CFRB_EINVAL, "n exceeds max_subgames");
   CK(cudaSetDevice(h->cfg.device));
   const int H = h->g.H;
-  h->n = n; h->iters_done = 0;
-  h->h_tmpl.resize(n); h->h_player.resize(n); h->h_row_off.resize(n); h->h_last_bid.assign(last_bid, last_bid + n);
-  std::vector<int> act(n, -1);
+  std::vector<int> tm(n), pl(n), ro(n), act(n, -1);
   int rows = 0;
   for (int k = 0; k < n; ++k) {
     if (last_bid[k] < -1 || last_bid[k] > h->g.A - 2) return fail(CFRB_EINVAL, "subgame root bid out of range (terminal or invalid)");
     if (player_id[k] != 0 && player_id[k] != 1) return fail(CFRB_EINVAL, "player_id must be 0 or 1");
-    h->h_tmpl[k] = last_bid[k] + 1;
-    h->h_player[k] = player_id[k];
-    h->h_row_off[k] = rows;
-    rows += h->tmpl[h->h_tmpl[k]].L;
+    tm[k] = last_bid[k] + 1;
+    pl[k] = player_id[k];
+    ro[k] = rows;
+    rows += h->tmpl[tm[k]].L;
     if (act_iteration) act[k] = act_iteration[k];
   }
-  h->rows = rows;
+  h->n = n; h->rows = rows; h->iters_done = 0;
+  h->h_tmpl = tm; h->h_player = pl; h->h_row_off = ro;
+  h->h_last_bid.assign(last_bid, last_bid + n);
   h->h_beliefs.assign(beliefs, beliefs + (size_t)n * 2 * H);
   cudaStream_t st = h->own_stream;
   CK(cudaStreamSynchronize(st));
   const int wave[2] = {n, rows};
   CK(cudaMemcpyAsync(h->d_wave.p, wave, sizeof(wave), cudaMemcpyHostToDevice, st));
   if (n) {
-    CK(cudaMemcpyAsync(h->d_sg_tmpl.p, h->h_tmpl.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_sg_player.p, h->h_player.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_sg_row_off.p, h->h_row_off.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_sg_tmpl.p, tm.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_sg_player.p, pl.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_sg_row_off.p, ro.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_sg_act.p, act.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_beliefs.p, beliefs, (size_t)n * 2 * H * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = launch_init(h, st);
+    int rc = DISPATCH_REAL(h, upload_beliefs_t, h, st);
+    if (rc) return rc;
+    rc = DISPATCH_REAL(h, launch_init_t, h, st);
     if (rc) return rc;
   }
   CK(cudaStreamSynchronize(st));   // host staging vectors above go out of scope
   return CFRB_OK;
 }
 
-static int launch_iter(cfrb_handle* h, cudaStream_t st, int iter, int do_b, int do_f) {
-  const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
-  if (h->group == 32) {
-    const size_t smem = (size_t)h->smem_per_group * sizeof(float) * h->groups_per_cta;
-    cfrb::cfr_iter_kernel<32><<<blocks, 32 * h->groups_per_cta, smem, st>>>(h->dev, iter, do_b, do_f, h->smem_per_group);
-  } else {
-    cfrb::cfr_iter_kernel<256><<<blocks, 256, 0, st>>>(h->dev, iter, do_b, do_f, h->smem_per_group);
-  }
-  ++h->launches;
-  CK(cudaGetLastError());
-  return CFRB_OK;
-}
-
-static int launch_net(cfrb_handle* h, cudaStream_t st) {
+static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2) {
   if (h->cfg.net_mode == CFRB_NET_ZERO || h->rows == 0) return CFRB_OK;
   if (h->profiling) {
     while ((int)h->net_ev.size() < h->net_ev_used + 2) {
@@ -441,7 +582,7 @@ static int launch_net(cfrb_handle* h, cudaStream_t st) {
   }
   if (h->cfg.net_mode == CFRB_NET_TC_F16) {
     const cfrb::tc::BlobLayout L(h->Qpad);
-    cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, nullptr, nullptr};
+    cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, dbg1, dbg2};
     const int tiles = (h->rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
     cfrb::tc::leaf_mlp_tc_kernel<<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
   } else {
@@ -462,7 +603,7 @@ int cfrb_reset_wave(cfrb_handle* h, void* cuda_stream) {
   CK(cudaSetDevice(h->cfg.device));
   h->iters_done = 0;
   if (h->n == 0) return CFRB_OK;
-  return launch_init(h, cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream);
+  return DISPATCH_REAL(h, launch_init_t, h, cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream);
 }
 
 int cfrb_set_profiling(cfrb_handle* h, int32_t on) {
@@ -483,9 +624,9 @@ int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream) {
   const int first = h->iters_done, last = first + iters;
   for (int i = first; i <= last; ++i) {
     const int do_b = i > first, do_f = i < last;
-    int rc = launch_iter(h, st, i, do_b, do_f);
+    int rc = DISPATCH_REAL(h, launch_iter_t, h, st, i, do_b, do_f);
     if (rc) return rc;
-    if (do_f) { rc = launch_net(h, st); if (rc) return rc; }
+    if (do_f) { rc = launch_net(h, st, nullptr, nullptr); if (rc) return rc; }
   }
   CK(cudaEventRecord(h->ev_b, st));
   h->iters_done = last;
@@ -501,66 +642,13 @@ int cfrb_sync(cfrb_handle* h) {
 
 int cfrb_iterations_done(const cfrb_handle* h) { return h ? h->iters_done : 0; }
 
-// compact [E][H] (edge = child-1) -> dense [Nmax][H][A]
-static void to_dense(const cfrb_handle* h, int k, const float* compact, float* dense) {
-  const auto& t = h->tmpl[h->h_tmpl[k]];
-  const int H = h->g.H, A = h->g.A;
-  std::memset(dense, 0, sizeof(float) * (size_t)h->Nmax * H * A);
-  for (int n = 0; n < t.N; ++n)
-    for (int j = 0; j < t.nchild[n]; ++j) {
-      const int c = t.child_begin[n] + j, a = t.act_lo[n] + j;
-      for (int hd = 0; hd < H; ++hd) dense[((size_t)n * H + hd) * A + a] = compact[(size_t)(c - 1) * H + hd];
-    }
-}
-static void from_dense(const cfrb_handle* h, int k, const float* dense, float* compact) {
-  const auto& t = h->tmpl[h->h_tmpl[k]];
-  const int H = h->g.H, A = h->g.A;
-  for (int n = 0; n < t.N; ++n)
-    for (int j = 0; j < t.nchild[n]; ++j) {
-      const int c = t.child_begin[n] + j, a = t.act_lo[n] + j;
-      for (int hd = 0; hd < H; ++hd) compact[(size_t)(c - 1) * H + hd] = dense[((size_t)n * H + hd) * A + a];
-    }
-}
-
-int cfrb_fetch(cfrb_handle* h, float* root_value_means, float* snapshot_strategy, float* last_strategy, float* avg_strategy,
-               float* sum_strategy, float* regrets) {
+int cfrb_fetch(cfrb_handle* h, double* root_value_means, double* snapshot_strategy, double* last_strategy, double* avg_strategy,
+               double* sum_strategy, double* regrets) {
   if (!h) return fail(CFRB_EINVAL, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
-  const int n = h->n, H = h->g.H, A = h->g.A;
-  if (n == 0) return CFRB_OK;
-  if (root_value_means) CK(cudaMemcpy(root_value_means, h->d_mu.p, (size_t)n * 2 * H * sizeof(float), cudaMemcpyDeviceToHost));
-  const size_t dense_sz = (size_t)h->Nmax * H * A;
-  std::vector<float> tmp;
-  auto pull = [&](const float* dsrc, float* out, bool normalise) -> int {
-    tmp.resize((size_t)n * h->table_stride);
-    CK(cudaMemcpy(tmp.data(), dsrc, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < n; ++k) {
-      float* dk = out + (size_t)k * dense_sz;
-      to_dense(h, k, tmp.data() + (size_t)k * h->table_stride, dk);
-      if (normalise) {   // average strategy = normalised sum (subgame_solving.cc:659-660)
-        const auto& t = h->tmpl[h->h_tmpl[k]];
-        for (int nn = 0; nn < t.N; ++nn) {
-          if (!t.nchild[nn]) continue;
-          for (int hd = 0; hd < H; ++hd) {
-            float* row = dk + ((size_t)nn * H + hd) * A;
-            float s = 0.f;
-            for (int a = 0; a < A; ++a) s += row[a];
-            if (s > 0.f) for (int a = 0; a < A; ++a) row[a] /= s;
-            else for (int j = 0; j < t.nchild[nn]; ++j) row[t.act_lo[nn] + j] = 1.f / t.nchild[nn];
-          }
-        }
-      }
-    }
-    return CFRB_OK;
-  };
-  int rc = CFRB_OK;
-  if (snapshot_strategy && (rc = pull(h->d_Snap.p, snapshot_strategy, false))) return rc;
-  if (last_strategy && (rc = pull(h->d_Sg.p, last_strategy, false))) return rc;
-  if (avg_strategy && (rc = pull(h->d_S.p, avg_strategy, true))) return rc;
-  if (sum_strategy && (rc = pull(h->d_S.p, sum_strategy, false))) return rc;
-  if (regrets && (rc = pull(h->d_R.p, regrets, false))) return rc;
-  return CFRB_OK;
+  if (h->n == 0) return CFRB_OK;
+  return DISPATCH_REAL(h, fetch_t, h, root_value_means, snapshot_strategy, last_strategy, avg_strategy, sum_strategy, regrets);
 }
 
 int cfrb_examples(cfrb_handle* h, float* queries, float* values) {
@@ -569,10 +657,11 @@ int cfrb_examples(cfrb_handle* h, float* queries, float* values) {
   CK(cudaDeviceSynchronize());
   const int n = h->n, H = h->g.H, A = h->g.A, Q = h->g.Q;
   if (n == 0) return CFRB_OK;
-  CK(cudaMemcpy(values, h->d_mu.p, (size_t)n * 2 * H * sizeof(float), cudaMemcpyDeviceToHost));
+  int rc = DISPATCH_REAL(h, examples_values_t, h, values);
+  if (rc) return rc;
   // query of node 0 as seen by traverser t (write_query_to, subgame_solving.cc:104-123); root reach == beliefs
   for (int k = 0; k < n; ++k) {
-    const float* b = h->h_beliefs.data() + (size_t)k * 2 * H;
+    const double* b = h->h_beliefs.data() + (size_t)k * 2 * H;
     for (int t = 0; t < 2; ++t) {
       float* q = queries + ((size_t)k * 2 + t) * Q;
       q[0] = (float)h->h_player[k];
@@ -580,39 +669,27 @@ int cfrb_examples(cfrb_handle* h, float* queries, float* values) {
       for (int a = 0; a < A; ++a) q[2 + a] = (a == h->h_last_bid[k]) ? 1.f : 0.f;
       for (int p = 0; p < 2; ++p) {
         double s = 0;
-        for (int hd = 0; hd < H; ++hd) s += (double)b[p * H + hd] + 1e-80;
-        for (int hd = 0; hd < H; ++hd) q[2 + A + p * H + hd] = (float)(((double)b[p * H + hd] + 1e-80) / s);
+        for (int hd = 0; hd < H; ++hd) s += b[p * H + hd] + 1e-80;
+        for (int hd = 0; hd < H; ++hd) q[2 + A + p * H + hd] = (float)((b[p * H + hd] + 1e-80) / s);
       }
     }
   }
   return CFRB_OK;
 }
 
-int cfrb_load_state(cfrb_handle* h, const float* regrets, const float* last_strategy, const float* sum_strategy,
-                    const float* root_value_means, const int32_t* num_steps, int32_t iterations_done) {
+int cfrb_load_state(cfrb_handle* h, const double* regrets, const double* last_strategy, const double* sum_strategy,
+                    const double* root_value_means, const int32_t* num_steps, int32_t iterations_done) {
   if (!h) return fail(CFRB_EINVAL, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
-  const int n = h->n, H = h->g.H, A = h->g.A;
-  const size_t dense_sz = (size_t)h->Nmax * H * A;
-  std::vector<float> tmp((size_t)n * h->table_stride);
-  auto push = [&](const float* dense, float* ddst) -> int {
-    CK(cudaMemcpy(tmp.data(), ddst, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < n; ++k) from_dense(h, k, dense + (size_t)k * dense_sz, tmp.data() + (size_t)k * h->table_stride);
-    CK(cudaMemcpy(ddst, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
-    return CFRB_OK;
-  };
-  int rc;
-  if (regrets && (rc = push(regrets, h->d_R.p))) return rc;
-  if (last_strategy && (rc = push(last_strategy, h->d_Sg.p))) return rc;
-  if (sum_strategy && (rc = push(sum_strategy, h->d_S.p))) return rc;
-  if (root_value_means) CK(cudaMemcpy(h->d_mu.p, root_value_means, (size_t)n * 2 * H * sizeof(float), cudaMemcpyHostToDevice));
-  if (num_steps) CK(cudaMemcpy(h->d_steps.p, num_steps, (size_t)n * 2 * sizeof(int), cudaMemcpyHostToDevice));
+  int rc = DISPATCH_REAL(h, load_state_t, h, regrets, last_strategy, sum_strategy, root_value_means);
+  if (rc) return rc;
+  if (num_steps) CK(cudaMemcpy(h->d_steps.p, num_steps, (size_t)h->n * 2 * sizeof(int), cudaMemcpyHostToDevice));
   h->iters_done = iterations_done;
   return CFRB_OK;
 }
 
-int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, float* scalers, int32_t cap_rows) {
+int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, double* scalers, int32_t cap_rows) {
   if (!h) return fail(CFRB_EINVAL, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
@@ -625,7 +702,7 @@ int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, float* sc
       for (int q = 0; q < Q; ++q)
         queries[(size_t)r * Q + q] = __half2float(x[(size_t)(r >> 7) * cfrb::tc::kTileM * h->Qpad +
                                                     cfrb::tc::umma_kmajor_offset_halves(r & 127, q, cfrb::tc::kTileM)]);
-  } else if (rows > 0 && queries) {
+  } else if (rows > 0 && queries && h->cfg.net_mode == CFRB_NET_FP32) {
     std::vector<float> x((size_t)rows * h->Qpad);
     CK(cudaMemcpy(x.data(), h->d_X.p, x.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int r = 0; r < rows; ++r) std::memcpy(queries + (size_t)r * Q, x.data() + (size_t)r * h->Qpad, Q * sizeof(float));
@@ -635,7 +712,10 @@ int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, float* sc
     CK(cudaMemcpy(o.data(), h->d_out.p, o.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int r = 0; r < rows; ++r) std::memcpy(net_out + (size_t)r * h->g.H, o.data() + (size_t)r * h->Hout, h->g.H * sizeof(float));
   }
-  if (rows > 0 && scalers) CK(cudaMemcpy(scalers, h->d_scaler.p, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost));
+  if (rows > 0 && scalers) {
+    int rc = DISPATCH_REAL(h, scalers_t, h, scalers, rows);
+    if (rc) return rc;
+  }
   return h->rows;
 }
 
@@ -644,20 +724,19 @@ int cfrb_debug_net_taps(cfrb_handle* h, float* d1, float* d2) {
   if (!h->have_weights || h->rows == 0) return fail(CFRB_ESTATE, "no weights or no leaf rows");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
-  const cfrb::tc::BlobLayout L(h->Qpad);
   const size_t n = (size_t)cfrb::tc::kTileM * cfrb::tc::kHid;
-  cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, h->d_dbg.p, h->d_dbg.p + n};
-  const int tiles = (h->rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
-  cfrb::tc::leaf_mlp_tc_kernel<<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, h->own_stream>>>(a);
-  ++h->launches;
-  CK(cudaGetLastError());
+  const bool prof = h->profiling;
+  h->profiling = false;
+  int rc = launch_net(h, h->own_stream, h->d_dbg.p, h->d_dbg.p + n);
+  h->profiling = prof;
+  if (rc) return rc;
   CK(cudaStreamSynchronize(h->own_stream));
   if (d1) CK(cudaMemcpy(d1, h->d_dbg.p, n * sizeof(float), cudaMemcpyDeviceToHost));
   if (d2) CK(cudaMemcpy(d2, h->d_dbg.p + n, n * sizeof(float), cudaMemcpyDeviceToHost));
   return CFRB_OK;
 }
 
-int cfrb_exploitability(cfrb_handle* h, const float* full_strategy, float* out2) {
+int cfrb_exploitability(cfrb_handle* h, const double* full_strategy, double* out2) {
   (void)h; (void)full_strategy; (void)out2;
   return fail(CFRB_EINVAL, "cfrb_exploitability: best-response kernel (SURVEY 8f-1) is not built yet");
 }
