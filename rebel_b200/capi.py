@@ -62,6 +62,8 @@ def lib():
     L.cfrb_set_profiling.argtypes = [vp, C.c_int32]
     L.cfrb_fetch.argtypes = [vp] + [_dp] * 6
     L.cfrb_examples.argtypes = [vp, _fp, _fp]
+    L.cfrb_table_stride.argtypes = [vp]
+    L.cfrb_fetch_compact.argtypes = [vp, C.c_int32, _dp]
     L.cfrb_load_state.argtypes = [vp, _dp, _dp, _dp, _dp, _ip, C.c_int32]
     L.cfrb_debug_leaf_io.argtypes = [vp, _fp, _fp, _dp, C.c_int32]
     L.cfrb_exploitability.argtypes = [vp, _dp, _dp]
@@ -169,6 +171,13 @@ class WaveSolver:
         g = lambda k: _p(bufs.get(k), _dp)
         _check(lib().cfrb_fetch(self._h, g("root_means"), g("snapshot"), g("last"), g("avg"), g("sum"), g("regrets")))
         return bufs
+
+    def fetch_compact(self, which="snapshot"):
+        """[n, table_stride] fp64; entry (child - 1) * H + hand = value of (parent, hand, action to child)."""
+        stride = lib().cfrb_table_stride(self._h)
+        out = np.zeros((self.n, stride), np.float64)
+        _check(lib().cfrb_fetch_compact(self._h, {"snapshot": 0, "last": 1, "sum": 2, "regrets": 3}[which], _p(out, _dp)))
+        return out
 
     def examples(self):
         q = np.zeros((self.n, 2, self.Q), np.float32)

@@ -1,0 +1,36 @@
+// CFR wave kernels, compiled as their own translation unit with -fmad=false: without fused multiply-adds every fp64
+// operation is an individually rounded IEEE operation in the same order as the reference's scalar C++ (built without
+// contraction), which makes the CFRB_STATE_F64 path reproduce the reference bit for bit between value-net calls.
+#include "cfr_kernels.cuh"
+
+namespace cfrb {
+
+template <typename real>
+cudaError_t cfr_configure(int group, int smem_bytes) {
+  if (group != 32) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(cfr_iter_kernel<real, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(cfr_init_kernel<real, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+
+template <typename real>
+void cfr_launch_init(const CfrDev<real>& p, int group, int blocks, int threads, size_t smem, cudaStream_t st, int scratch_per_group) {
+  if (group == 32) cfr_init_kernel<real, 32><<<blocks, threads, smem, st>>>(p, scratch_per_group);
+  else cfr_init_kernel<real, 256><<<blocks, 256, 0, st>>>(p, scratch_per_group);
+}
+
+template <typename real>
+void cfr_launch_iter(const CfrDev<real>& p, int group, int blocks, int threads, size_t smem, cudaStream_t st, int iter, int do_b,
+                     int do_f, int scratch_per_group) {
+  if (group == 32) cfr_iter_kernel<real, 32><<<blocks, threads, smem, st>>>(p, iter, do_b, do_f, scratch_per_group);
+  else cfr_iter_kernel<real, 256><<<blocks, 256, 0, st>>>(p, iter, do_b, do_f, scratch_per_group);
+}
+
+#define CFRB_INSTANTIATE(real)                                                                                             \
+  template cudaError_t cfr_configure<real>(int, int);                                                                      \
+  template void cfr_launch_init<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int);                      \
+  template void cfr_launch_iter<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int, int, int, int);
+CFRB_INSTANTIATE(float)
+CFRB_INSTANTIATE(double)
+
+}  // namespace cfrb

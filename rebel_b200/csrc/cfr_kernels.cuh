@@ -20,40 +20,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "cfr_types.h"
+
 namespace cfrb {
-
-struct TemplateDev {
-  int node_off, level_off, pleaf_off, term_off;
-  int N, L, T, levels;
-};
-
-template <typename real>
-struct CfrDev {
-  // game
-  int A, H, F, Q, Qpad, Hout;
-  // templates (read-only)
-  const TemplateDev* tmpl;
-  const int* parent; const int* child_begin; const int* nchild; const int* last_bid;
-  const int* level_begin; const int* pleaf_node; const int* term_node;
-  const unsigned char* matches;   // [H][F] num_matches(hand, face), liars_dice.h:83-91
-  // wave
-  const int* wave_n;              // [1] number of live subgames
-  const int* sg_tmpl; const int* sg_player; const int* sg_row_off; const int* sg_act_iter;
-  const real* beliefs;            // [K][2][H]
-  real* mu;                       // [K][2][H] root_values_means
-  int* steps;                     // [K][2]
-  real* R; real* Sg; real* S; real* Snap;   // [K][table_stride]
-  int table_stride;
-  real* vterm; int vterm_stride;  // [K][Tmax*H] terminal payoffs of the current iteration
-  float* X;                       // [rows][Qpad] fp32 query rows (SIMT net) -- or nullptr
-  __half* Xh;                     // fp16 query tiles in UMMA core-matrix order (tensor-core net) -- or nullptr
-  const float* net_out;           // [rows][Hout] raw net outputs
-  real* scaler;                   // [rows] sum of opponent reach at the pseudo-leaf
-  real* scratch; size_t scratch_stride;   // global scratch (CTA groups), reals per subgame
-  // params
-  int linear, dcfr; real dcfr_alpha, dcfr_beta, dcfr_gamma;
-  int use_net;
-};
 
 template <int G>
 __device__ __forceinline__ void group_sync() {
@@ -64,8 +33,13 @@ __device__ __forceinline__ double rmax0(double x) { return fmax(x, 0.0); }
 __device__ __forceinline__ float rpow(float a, float b) { return powf(a, b); }
 __device__ __forceinline__ double rpow(double a, double b) { return pow(a, b); }
 
-// Scratch layout of a group (reals): bufA[N*H] | bufB[N*H] | tmp[N*H] | lsum[2*L]
-__host__ __device__ inline int cfr_scratch_reals(int N, int H, int L) { return 3 * N * H + 2 * (L > 0 ? L : 1); }
+// The reference smooths with 1e-80 (kReachSmoothingEps / kRegretSmoothingEps, subgame_solving.h:34-36).  In fp64 these
+// are applied literally, which keeps the fp64 path operation-for-operation identical to the reference (this TU is built
+// with -fmad=false for the same reason).  1e-80 does not exist in fp32: there the limit behaviour is used instead
+// ("no positive regret -> uniform", "all-zero reach -> uniform"), a documented deviation of CFRB_STATE_F32.
+template <typename real> struct Eps;
+template <> struct Eps<double> { static constexpr bool kLiteral = true;  static constexpr double v = 1e-80; };
+template <> struct Eps<float>  { static constexpr bool kLiteral = false; static constexpr float v = 0.f; };
 
 // Value of query column q of a pseudo-leaf row (write_query_to, subgame_solving.cc:104-123).  The reference's eps =
 // 1e-80 only matters when a reach vector is all zero (-> uniform); that case is reproduced explicitly.
@@ -76,8 +50,14 @@ __device__ __forceinline__ float query_value(const CfrDev<real>& p, int q, int l
   if (q == 0) return (float)leaf_player;
   if (q == 1) return (float)trav;
   if (q < 2 + A) return (q - 2 == leaf_bid) ? 1.f : 0.f;
-  if (q < 2 + A + H) return s0 > 0 ? (float)(r0[q - 2 - A] / s0) : 1.f / H;
-  if (q < 2 + A + 2 * H) return s1 > 0 ? (float)(r1[q - 2 - A - H] / s1) : 1.f / H;
+  if (q < 2 + A + H) {
+    if (Eps<real>::kLiteral) return (float)((r0[q - 2 - A] + Eps<real>::v) / s0);     // util.h:68-78
+    return s0 > 0 ? (float)(r0[q - 2 - A] / s0) : 1.f / H;
+  }
+  if (q < 2 + A + 2 * H) {
+    if (Eps<real>::kLiteral) return (float)((r1[q - 2 - A - H] + Eps<real>::v) / s1);
+    return s1 > 0 ? (float)(r1[q - 2 - A - H] / s1) : 1.f / H;
+  }
   return 0.f;
 }
 
@@ -110,9 +90,12 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
   const int row0 = p.sg_row_off[k];
   for (int r = lane; r < t.L; r += G) {
     const int n = p.pleaf_node[t.pleaf_off + r];
-    real s0 = 0, s1 = 0;
-    for (int h = 0; h < H; ++h) { s0 += reach0[n * H + h]; s1 += reach1[n * H + h]; }
-    lsum[2 * r] = s0; lsum[2 * r + 1] = s1;
+    real s0 = 0, s1 = 0, e0 = 0, e1 = 0;
+    for (int h = 0; h < H; ++h) {
+      s0 += reach0[n * H + h]; s1 += reach1[n * H + h];                      // vector_sum (:264)
+      e0 += reach0[n * H + h] + Eps<real>::v; e1 += reach1[n * H + h] + Eps<real>::v;   // normalize_probabilities_safe
+    }
+    lsum[2 * r] = e0; lsum[2 * r + 1] = e1;
     p.scaler[row0 + r] = trav == 0 ? s1 : s0;
   }
   group_sync<G>();
@@ -124,7 +107,7 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
     // one lane produces the 8 contiguous halves of a (row, k-chunk) and stores them with a single 16-byte write
     const int kc = Qp >> 3;
     for (int it = lane; it < t.L * kc; it += G) {
-      const int r = it / kc, k8 = it % kc;
+      const int k8 = it / t.L, r = it % t.L;    // consecutive lanes -> consecutive rows -> contiguous 16-byte chunks
       const int n = p.pleaf_node[t.pleaf_off + r];
       const int bid = p.last_bid[t.node_off + n];
       const real s0 = lsum[2 * r], s1 = lsum[2 * r + 1];
@@ -157,13 +140,27 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
     const real* ro = ropp + n * H;
     // P(h) = sum of opponent reach over hands g with matches(g) >= quantity - matches(h): the suffix sum of
     // the match-count histogram the reference builds (:770-779), evaluated directly; float-rounded like :785.
-    const int need = quantity - (int)p.matches[h * p.F + face];
-    real win = 0, tot = 0;
+    // believed_counts[m] += reach (hand order), suffix sums from the top (:770-779): same operation order as the
+    // reference so that the fp64 path is bit-identical.  Bins above kMaxBins-1 cannot occur (2*num_dice+1 <= kMaxBins).
+    constexpr int kMaxBins = 9;
+    real cnt[kMaxBins];
+#pragma unroll
+    for (int m = 0; m < kMaxBins; ++m) cnt[m] = 0;
+    real tot = 0;
     for (int g = 0; g < H; ++g) {
       const real r = ro[g];
+      const int mg = (int)p.matches[g * p.F + face];
       tot += r;
-      if ((int)p.matches[g * p.F + face] >= need) win += r;
+#pragma unroll
+      for (int m = 0; m < kMaxBins; ++m) cnt[m] += (m == mg) ? r : (real)0;
     }
+#pragma unroll
+    for (int m = kMaxBins - 2; m >= 0; --m) cnt[m] += cnt[m + 1];
+    int left = quantity - (int)p.matches[h * p.F + face];
+    left = left < 0 ? 0 : left;
+    real win = 0;
+#pragma unroll
+    for (int m = 0; m < kMaxBins; ++m) win = (m == left) ? cnt[m] : win;
     const real v = (real)(float)win * 2 - tot;
     // state.player_id of a terminal = the bidder; payoff is negated iff that is not the traverser (:290)
     const int pl = rp ^ (ndepth & 1);
@@ -263,7 +260,10 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
         if (!nc) continue;
         const int c0 = child_begin[n];
         real sum = 0;
-        for (int j = 0; j < nc; ++j) sum += rmax0(tmp[(c0 + j - 1) * H + h]);
+        for (int j = 0; j < nc; ++j) {
+          const real r = tmp[(c0 + j - 1) * H + h];
+          sum += Eps<real>::kLiteral ? (r > Eps<real>::v ? r : Eps<real>::v) : rmax0(r);   // max(R, 1e-80) (:626-629)
+        }
         val[n * H + h] = sum;
       }
       group_sync<G>();
@@ -271,7 +271,8 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
         const int c = cb + it / H, h = it % H;
         const int e = (c - 1) * H + h, par = parent[c];
         const real r = tmp[e], sum = val[par * H + h], rn = rt[par * H + h];
-        const real sg = sum > 0 ? rmax0(r) / sum : (real)1 / nchild[par];
+        const real sg = Eps<real>::kLiteral ? (r > Eps<real>::v ? r : Eps<real>::v) / sum
+                                            : (sum > 0 ? rmax0(r) / sum : (real)1 / nchild[par]);
         Sg[e] = sg;
         R[e] = r * (r > 0 ? pos : neg);
         S[e] = S[e] * strat + rn * sg;

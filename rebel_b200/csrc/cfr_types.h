@@ -1,0 +1,53 @@
+// Device-visible plain structs shared by the CFR kernels (cfr_kernels.cu) and the C-ABI host code (cfrb_api.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cfrb {
+
+struct TemplateDev {
+  int node_off, level_off, pleaf_off, term_off;
+  int N, L, T, levels;
+};
+
+template <typename real>
+struct CfrDev {
+  // game
+  int A, H, F, Q, Qpad, Hout;
+  // templates (read-only)
+  const TemplateDev* tmpl;
+  const int* parent; const int* child_begin; const int* nchild; const int* last_bid;
+  const int* level_begin; const int* pleaf_node; const int* term_node;
+  const unsigned char* matches;   // [H][F] num_matches(hand, face), liars_dice.h:83-91
+  // wave
+  const int* wave_n;              // [1] number of live subgames
+  const int* sg_tmpl; const int* sg_player; const int* sg_row_off; const int* sg_act_iter;
+  const real* beliefs;            // [K][2][H]
+  real* mu;                       // [K][2][H] root_values_means
+  int* steps;                     // [K][2]
+  real* R; real* Sg; real* S; real* Snap;   // [K][table_stride]
+  int table_stride;
+  real* vterm; int vterm_stride;  // [K][Tmax*H] terminal payoffs of the current iteration
+  float* X;                       // [rows][Qpad] fp32 query rows (SIMT net) -- or nullptr
+  __half* Xh;                     // fp16 query tiles in UMMA core-matrix order (tensor-core net) -- or nullptr
+  const float* net_out;           // [rows][Hout] raw net outputs
+  real* scaler;                   // [rows] sum of opponent reach at the pseudo-leaf
+  real* scratch; size_t scratch_stride;   // global scratch (CTA groups), reals per subgame
+  // params
+  int linear, dcfr; real dcfr_alpha, dcfr_beta, dcfr_gamma;
+  int use_net;
+};
+
+// Scratch layout of a group (reals): bufA[N*H] | bufB[N*H] | tmp[N*H] | lsum[2*L]
+__host__ __device__ inline int cfr_scratch_reals(int N, int H, int L) { return 3 * N * H + 2 * (L > 0 ? L : 1); }
+
+// Launchers implemented in cfr_kernels.cu (explicitly instantiated for float and double).  `group` is 32 (one warp per
+// subgame, shared-memory scratch) or 256 (one CTA per subgame, global scratch).
+template <typename real> cudaError_t cfr_configure(int group, int smem_bytes);
+template <typename real> void cfr_launch_init(const CfrDev<real>& p, int group, int blocks, int threads, size_t smem, cudaStream_t st,
+                                              int scratch_per_group);
+template <typename real> void cfr_launch_iter(const CfrDev<real>& p, int group, int blocks, int threads, size_t smem, cudaStream_t st,
+                                              int iter, int do_b, int do_f, int scratch_per_group);
+
+}  // namespace cfrb

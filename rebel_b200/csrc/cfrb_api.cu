@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "cfr_kernels.cuh"
+#include "cfr_types.h"
 #include "cfr_tree.h"
 #include "leaf_mlp_simt.cuh"
 #include "leaf_mlp_tc.cuh"
@@ -128,8 +128,7 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
     // as many warps per CTA as keep >= 2 CTAs per SM within the shared-memory budget
     h->groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_optin / 2 / per_group_bytes));
     const int smem_bytes = (int)(per_group_bytes * h->groups_per_cta);
-    CK(cudaFuncSetAttribute(cfrb::cfr_iter_kernel<real, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    CK(cudaFuncSetAttribute(cfrb::cfr_init_kernel<real, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CK(cfrb::cfr_configure<real>(32, smem_bytes));
   } else {
     h->group = 256;
     h->groups_per_cta = 1;
@@ -158,12 +157,8 @@ template <typename real>
 static int launch_init_t(cfrb_handle* h, cudaStream_t st) {
   auto& s = state_of<real>(h);
   const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
-  if (h->group == 32) {
-    const size_t smem = (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta;
-    cfrb::cfr_init_kernel<real, 32><<<blocks, 32 * h->groups_per_cta, smem, st>>>(s.dev, h->scratch_per_group);
-  } else {
-    cfrb::cfr_init_kernel<real, 256><<<blocks, 256, 0, st>>>(s.dev, h->scratch_per_group);
-  }
+  const size_t smem = h->group == 32 ? (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta : 0;
+  cfrb::cfr_launch_init<real>(s.dev, h->group, blocks, 32 * h->groups_per_cta, smem, st, h->scratch_per_group);
   ++h->launches;
   CK(cudaGetLastError());
   return CFRB_OK;
@@ -173,12 +168,8 @@ template <typename real>
 static int launch_iter_t(cfrb_handle* h, cudaStream_t st, int iter, int do_b, int do_f) {
   auto& s = state_of<real>(h);
   const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
-  if (h->group == 32) {
-    const size_t smem = (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta;
-    cfrb::cfr_iter_kernel<real, 32><<<blocks, 32 * h->groups_per_cta, smem, st>>>(s.dev, iter, do_b, do_f, h->scratch_per_group);
-  } else {
-    cfrb::cfr_iter_kernel<real, 256><<<blocks, 256, 0, st>>>(s.dev, iter, do_b, do_f, h->scratch_per_group);
-  }
+  const size_t smem = h->group == 32 ? (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta : 0;
+  cfrb::cfr_launch_iter<real>(s.dev, h->group, blocks, 32 * h->groups_per_cta, smem, st, iter, do_b, do_f, h->scratch_per_group);
   ++h->launches;
   CK(cudaGetLastError());
   return CFRB_OK;
@@ -228,6 +219,8 @@ static int fetch_t(cfrb_handle* h, double* root_value_means, double* snapshot_st
   }
   const size_t dense_sz = (size_t)h->Nmax * H * A;
   std::vector<real> tmp;
+  std::vector<int> steps((size_t)n * 2);
+  CK(cudaMemcpy(steps.data(), h->d_steps.p, steps.size() * sizeof(int), cudaMemcpyDeviceToHost));
   auto pull = [&](const real* dsrc, double* out, bool normalise) -> int {
     tmp.resize((size_t)n * h->table_stride);
     CK(cudaMemcpy(tmp.data(), dsrc, tmp.size() * sizeof(real), cudaMemcpyDeviceToHost));
@@ -238,11 +231,14 @@ static int fetch_t(cfrb_handle* h, double* root_value_means, double* snapshot_st
         const auto& t = h->tmpl[h->h_tmpl[k]];
         for (int nn = 0; nn < t.N; ++nn) {
           if (!t.nchild[nn]) continue;
+          // average_strategies of a player stays the uniform initial strategy until that player's first update
+          // (CFR ctor, subgame_solving.cc:516-518; the normalised sum is only written in step(), :659-660)
+          const bool untouched = steps[2 * k + (h->h_player[k] ^ (t.depth[nn] & 1))] == 0;
           for (int hd = 0; hd < H; ++hd) {
             double* row = dk + ((size_t)nn * H + hd) * A;
             double sum = 0;
             for (int a = 0; a < A; ++a) sum += row[a];
-            if (sum > 0) for (int a = 0; a < A; ++a) row[a] /= sum;
+            if (sum > 0 && !untouched) for (int a = 0; a < A; ++a) row[a] /= sum;
             else for (int j = 0; j < t.nchild[nn]; ++j) row[t.act_lo[nn] + j] = 1.0 / t.nchild[nn];
           }
         }
@@ -256,6 +252,21 @@ static int fetch_t(cfrb_handle* h, double* root_value_means, double* snapshot_st
   if (avg_strategy && (rc = pull(s.S.p, avg_strategy, true))) return rc;
   if (sum_strategy && (rc = pull(s.S.p, sum_strategy, false))) return rc;
   if (regrets && (rc = pull(s.R.p, regrets, false))) return rc;
+  return CFRB_OK;
+}
+
+template <typename real>
+static int fetch_compact_t(cfrb_handle* h, int which, double* out) {
+  auto& s = state_of<real>(h);
+  const real* src = which == 0 ? s.Snap.p : which == 1 ? s.Sg.p : which == 2 ? s.S.p : s.R.p;
+  const size_t cnt = (size_t)h->n * h->table_stride;
+  if (sizeof(real) == sizeof(double)) {
+    CK(cudaMemcpy(out, src, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<real> tmp(cnt);
+    CK(cudaMemcpy(tmp.data(), src, cnt * sizeof(real), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < cnt; ++i) out[i] = (double)tmp[i];
+  }
   return CFRB_OK;
 }
 
@@ -649,6 +660,16 @@ int cfrb_fetch(cfrb_handle* h, double* root_value_means, double* snapshot_strate
   CK(cudaDeviceSynchronize());
   if (h->n == 0) return CFRB_OK;
   return DISPATCH_REAL(h, fetch_t, h, root_value_means, snapshot_strategy, last_strategy, avg_strategy, sum_strategy, regrets);
+}
+
+int cfrb_table_stride(const cfrb_handle* h) { return h ? h->table_stride : 0; }
+
+int cfrb_fetch_compact(cfrb_handle* h, int32_t which, double* out) {
+  if (!h || !out || which < 0 || which > 3) return fail(CFRB_EINVAL, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  if (h->n == 0) return CFRB_OK;
+  return DISPATCH_REAL(h, fetch_compact_t, h, which, out);
 }
 
 int cfrb_examples(cfrb_handle* h, float* queries, float* values) {

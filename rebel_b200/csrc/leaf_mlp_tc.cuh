@@ -5,13 +5,15 @@
 //
 //   X tile [128 x Kp] fp16 (smem, UMMA K-major core-matrix order, written in that order by the CFR forward kernel)
 //     --tcgen05.mma SS-->  D1 [128 x 256] fp32 in TMEM cols [0,256)
-//     --epilogue (tcgen05.ld, +bias, LayerNorm, erf-GELU, ->fp16, tcgen05.st)-->  A2 [128 x 256] fp16 in TMEM cols [256,384)
+//     --epilogue (tcgen05.ld, +bias, LayerNorm, GELU, ->fp16, tcgen05.st)-->  A2 [128 x 256] fp16 in TMEM cols [256,384)
 //     --tcgen05.mma TS (A from TMEM, W2 from smem)-->  D2 in TMEM cols [0,256)   (reuses D1's columns)
 //     --epilogue-->  A3 in TMEM cols [256,384)
 //     --tcgen05.mma TS (N = 16)-->  D3 [128 x 16] in TMEM cols [384,400)  --epilogue (+bias)-->  out[rows][H] fp32
 //
-// Warp roles (160 threads): warps 0-3 = epilogue (thread == row == TMEM lane), warp 4 = TMEM allocator + single-thread
-// MMA issuer.  mbarriers: x (query tile staged), d1/d2/d3 (accumulator ready, via tcgen05.commit), a2/a3 (A operand ready).
+// Warp roles (288 threads): warps 0-7 = epilogue — warp w owns TMEM lanes 32*(w&3).. (one row per thread) and the column
+// half (w>>2), so a thread keeps its 128 accumulators in registers, reads TMEM once per layer and exchanges its LayerNorm
+// partial sums with the partner warp through shared memory; warp 8 = TMEM allocator + single-thread MMA issuer.
+// mbarriers: x (query tile staged), d1/d2/d3 (accumulator ready, via tcgen05.commit), a2/a3 (A operand ready).
 // Each barrier completes exactly once per tile, so one parity bit per tile iteration serves all of them.
 #pragma once
 #include <cuda_fp16.h>
@@ -24,13 +26,14 @@ namespace tc {
 constexpr int kHid = 256;
 constexpr int kTileM = 128;
 constexpr int kNout = 16;                 // output features padded to the minimum UMMA N
-constexpr int kThreads = 160;
+constexpr int kEpiThreads = 256;             // 8 epilogue warps
+constexpr int kThreads = kEpiThreads + 32;   // + allocator / MMA-issuer warp
 constexpr uint32_t kColD = 0, kColA = 256, kColD3 = 384, kTmemCols = 512;
 
 // ---- shared-memory / weight-blob layout (bytes).  The blob in global memory has exactly the smem layout up to kOffX.
 struct BlobLayout {
   int Kp;            // padded query width (multiple of 16)
-  int off_w1, off_w2, off_w3, off_ln1, off_ln2, off_b3, blob_bytes, off_x, off_bar, smem_bytes;
+  int off_w1, off_w2, off_w3, off_ln1, off_ln2, off_b3, blob_bytes, off_x, off_part, off_bar, smem_bytes;
   __host__ __device__ explicit BlobLayout(int kp) : Kp(kp) {
     off_w1 = 0;
     off_w2 = off_w1 + kHid * kp * 2;
@@ -40,7 +43,8 @@ struct BlobLayout {
     off_b3 = off_ln2 + kHid * 16;
     blob_bytes = off_b3 + kNout * 4;
     off_x = (blob_bytes + 127) / 128 * 128;
-    off_bar = off_x + kTileM * kp * 2;
+    off_part = off_x + kTileM * kp * 2;    // LayerNorm partial sums: [2 layers][2 halves][128 rows] float2
+    off_bar = off_part + 2 * 2 * kTileM * 8;
     smem_bytes = off_bar + 64;
   }
 };
@@ -129,44 +133,62 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float gelu_erf_tc(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(y) = y * Phi(y), Phi(y) = 0.5 (1 + erf(y / sqrt 2)).  erf(z) = tanh(z (a + b z^2 + c z^4)) to 1.0e-4 (fitted, max error
+// of the resulting GELU 2.5e-5 absolute — 20x below the fp16 rounding of the activation it feeds), evaluated as a logistic
+// with ex2 / rcp so it is branch-free: y / (1 + 2^(-2 log2(e) u)), u = y (c0 + c1 y^2 + c2 y^4).
+__device__ __forceinline__ float gelu_tc(float y) {
+  const float y2 = fminf(y * y, 52.f);                              // beyond |y| ~ 7.2 the logistic is saturated anyway
+  const float p = fmaf(y2, fmaf(y2, -3.5151e-4f, 3.70057e-2f), 7.97508e-1f);
+  const float t = y * p * -2.885390082f;                            // -2 log2(e) u
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return y * r;
+}
 
-// LayerNorm(eps 1e-5) + GELU over the 256 fp32 accumulators of this thread's row (TMEM lane), result as fp16 into the
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// LayerNorm(eps 1e-5) + GELU of this thread's half row: 128 fp32 accumulators (TMEM lane = row, columns half*128..),
+// kept in registers; the two threads of a row exchange (sum, sum of squares) through `part`.  Result as fp16 into the
 // A-operand columns.  ln: float4 {bias, gamma, beta, -} per feature in smem (broadcast reads).
-__device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, const float4* __restrict__ ln, float* dbg_row) {
+__device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int half, int row, const float4* __restrict__ ln, float2* part,
+                                                 float* dbg_row) {
+  float x[128];
   float sum = 0.f, sumsq = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < kHid / 32; ++c) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
     uint32_t v[32];
-    CFRB_TMEM_LD32(tmem_row + kColD + c * 32, v);
+    CFRB_TMEM_LD32(tmem_row + kColD + half * 128 + c * 32, v);
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float x = __uint_as_float(v[i]) + ln[c * 32 + i].x;
-      sum += x;
-      sumsq = fmaf(x, x, sumsq);
-      if (dbg_row) dbg_row[c * 32 + i] = __uint_as_float(v[i]);
+      if (dbg_row) dbg_row[half * 128 + c * 32 + i] = __uint_as_float(v[i]);
+      const float xv = __uint_as_float(v[i]) + ln[half * 128 + c * 32 + i].x;
+      x[c * 32 + i] = xv;
+      sum += xv;
+      sumsq = fmaf(xv, xv, sumsq);
     }
   }
+  part[half * kTileM + row] = make_float2(sum, sumsq);
+  named_bar_sync(1, kEpiThreads);
+  const float2 o = part[(half ^ 1) * kTileM + row];
+  sum += o.x; sumsq += o.y;
   const float mean = sum * (1.f / kHid);
   const float var = fmaxf(sumsq * (1.f / kHid) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float shift = -mean * rstd;
-#pragma unroll 1
-  for (int c = 0; c < kHid / 32; ++c) {
-    uint32_t v[32];
-    CFRB_TMEM_LD32(tmem_row + kColD + c * 32, v);
-    tmem_wait_ld();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float4 p0 = ln[c * 32 + 2 * i], p1 = ln[c * 32 + 2 * i + 1];
-      const float y0 = fmaf(fmaf(__uint_as_float(v[2 * i]) + p0.x, rstd, shift), p0.y, p0.z);
-      const float y1 = fmaf(fmaf(__uint_as_float(v[2 * i + 1]) + p1.x, rstd, shift), p1.y, p1.z);
-      const __half2 h = __floats2half2_rn(gelu_erf_tc(y0), gelu_erf_tc(y1));
+      const float4 p0 = ln[half * 128 + c * 32 + 2 * i], p1 = ln[half * 128 + c * 32 + 2 * i + 1];
+      const float y0 = fmaf(fmaf(x[c * 32 + 2 * i], rstd, shift), p0.y, p0.z);
+      const float y1 = fmaf(fmaf(x[c * 32 + 2 * i + 1], rstd, shift), p1.y, p1.z);
+      const __half2 h = __floats2half2_rn(gelu_tc(y0), gelu_tc(y1));
       pk[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
-    CFRB_TMEM_ST16(tmem_row + kColA + c * 16, pk);
+    CFRB_TMEM_ST16(tmem_row + kColA + half * 64 + c * 16, pk);
   }
   tmem_wait_st();
 }
@@ -182,6 +204,7 @@ struct TcArgs {
 };
 
 __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
+  constexpr int kMmaWarp = kEpiThreads / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
   const BlobLayout L(a.Kp);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -201,11 +224,11 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
     for (int i = tid; i < L.blob_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
   }
   if (tid == 0) {
-    mbar_init(bar_x, 128); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_d3, 1);
-    mbar_init(bar_a2, 128); mbar_init(bar_a3, 128);
+    mbar_init(bar_x, kEpiThreads); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_d3, 1);
+    mbar_init(bar_a2, kEpiThreads); mbar_init(bar_a3, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -219,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
                  sw3 = smem_u32(smem + L.off_w3);
   const int x_tile_int4 = kTileM * a.Kp * 2 / 16;
 
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc256 = make_idesc(kTileM, kHid), idesc16 = make_idesc(kTileM, kNout);
@@ -247,18 +270,21 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
       }
     }
   } else {
-    // ===================== epilogue warps: thread == row == TMEM lane =====================
-    const int row_in_tile = tid;                                   // 0..127
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // ===================== epilogue warps: thread == (row, column half) =====================
+    const int quad = warp & 3, half = warp >> 2;
+    const int row_in_tile = quad * 32 + lane;                      // 0..127 == TMEM lane
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float4* ln1 = reinterpret_cast<const float4*>(smem + L.off_ln1);
     const float4* ln2 = reinterpret_cast<const float4*>(smem + L.off_ln2);
     const float* b3 = reinterpret_cast<const float*>(smem + L.off_b3);
+    float2* part1 = reinterpret_cast<float2*>(smem + L.off_part);
+    float2* part2 = part1 + 2 * kTileM;
     int4* xdst = reinterpret_cast<int4*>(smem + L.off_x);
-    const int per_thread = x_tile_int4 / 128;                      // Kp/8 int4 per thread (4 or 6)
-    int4 xr[8];
+    const int per_thread = x_tile_int4 / kEpiThreads;              // Kp/16 int4 per thread (2 or 3)
+    int4 xr[4];
     {
       const int4* xsrc = reinterpret_cast<const int4*>(a.Xh) + (size_t)blockIdx.x * x_tile_int4;
-      for (int i = 0; i < per_thread; ++i) xdst[tid + 128 * i] = __ldg(xsrc + tid + 128 * i);
+      for (int i = 0; i < per_thread; ++i) xdst[tid + kEpiThreads * i] = __ldg(xsrc + tid + kEpiThreads * i);
       fence_proxy_async_smem();
       mbar_arrive(bar_x);
     }
@@ -272,34 +298,36 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
       if (next < ntiles) {
         const int4* xsrc = reinterpret_cast<const int4*>(a.Xh) + (size_t)next * x_tile_int4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (i < per_thread) xr[i] = __ldg(xsrc + tid + 128 * i);
+        for (int i = 0; i < 4; ++i) if (i < per_thread) xr[i] = __ldg(xsrc + tid + kEpiThreads * i);
       }
-      epilogue_ln_gelu(tmem_row, ln1, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr);
+      epilogue_ln_gelu(tmem_row, half, row_in_tile, ln1, part1, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr);
       tc_fence_before();
       mbar_arrive(bar_a2);
       if (next < ntiles) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (i < per_thread) xdst[tid + 128 * i] = xr[i];
+        for (int i = 0; i < 4; ++i) if (i < per_thread) xdst[tid + kEpiThreads * i] = xr[i];
         fence_proxy_async_smem();
         mbar_arrive(bar_x);
       }
       // ---- layer 2
       mbar_wait(bar_d2, parity);
       tc_fence_after();
-      epilogue_ln_gelu(tmem_row, ln2, (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr);
+      epilogue_ln_gelu(tmem_row, half, row_in_tile, ln2, part2, (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr);
       tc_fence_before();
       mbar_arrive(bar_a3);
       // ---- layer 3: raw net outputs (the CFR backward kernel multiplies by the opponent-reach scaler)
       mbar_wait(bar_d3, parity);
       tc_fence_after();
-      uint32_t v[16];
-      CFRB_TMEM_LD16(tmem_row + kColD3, v);
-      tmem_wait_ld();
-      const int row = tile * kTileM + row_in_tile;
-      if (row < rows) {
-        float* o = a.out + (size_t)row * a.Hout;
+      if (half == 0) {
+        uint32_t v[16];
+        CFRB_TMEM_LD16(tmem_row + kColD3, v);
+        tmem_wait_ld();
+        const int row = tile * kTileM + row_in_tile;
+        if (row < rows) {
+          float* o = a.out + (size_t)row * a.Hout;
 #pragma unroll
-        for (int h = 0; h < kNout; ++h) if (h < a.H) o[h] = __uint_as_float(v[h]) + b3[h];
+          for (int h = 0; h < kNout; ++h) if (h < a.H) o[h] = __uint_as_float(v[h]) + b3[h];
+        }
       }
       tc_fence_before();   // order this tile's TMEM reads before the next tile's MMAs (via the a2/a3/x arrivals that follow)
     }
@@ -307,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }

@@ -1,0 +1,40 @@
+// Parameter structs mirrored to Python by the `rela` module, field for field like the reference's
+// liars_dice::SubgameSolvingParams (subgame_solving.h:43-58) and RecursiveSolvingParams (recursive_solving.h:31-38).
+// cfvpy/selfplay.py fills them with setattr from cfg.env (selfplay.py:587-610) and raises on unknown keys, so the
+// B200-specific knobs below are ordinary extra fields with defaults: they can be set as `env.concurrent_games=...`
+// without touching selfplay.py, and are invisible to configs that do not mention them.
+#pragma once
+#include <cstdlib>
+
+namespace liars_dice {
+
+struct SubgameSolvingParams {
+  int num_iters = 10;
+  int max_depth = 2;
+  bool linear_update = false;
+  bool use_cfr = false;   // the reference's other solver (fictitious play) is not on the accelerated path
+  bool optimistic = false;
+  bool dcfr = false;
+  double dcfr_alpha = 0;
+  double dcfr_beta = 0;
+  double dcfr_gamma = 0;
+};
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v && *v ? std::atoi(v) : dflt;
+}
+
+struct RecursiveSolvingParams {
+  int num_dice = 0;
+  int num_faces = 0;
+  float random_action_prob = 1.0f;
+  bool sample_leaf = false;
+  SubgameSolvingParams subgame_params;
+  // ---- rebel_b200 extensions
+  int concurrent_games = env_int("CFRB_CONCURRENT_GAMES", 1024);   // self-play games advanced in lock-step per thread loop
+  int net_mode = env_int("CFRB_NET_MODE", 2);                      // include/cfrb200.h CFRB_NET_*: 2 = tcgen05 fp16
+  int state_dtype = env_int("CFRB_STATE_DTYPE", 0);                // CFRB_STATE_*: 0 = fp64 tables
+};
+
+}  // namespace liars_dice

@@ -1,0 +1,176 @@
+// Python module `rela` — drop-in for the reference's cfvpy.rela (csrc/liars_dice/rela/pybind.cc:119-213): same class and
+// function names, constructor signatures, attributes and ownership (shared_ptr holders, keep_alive on pushed loops,
+// subgame_params returned by reference so nested setattr from selfplay.py:604-607 works).  Underneath, one generator
+// loop drives thousands of concurrent games on a GPU through libcfrb200 instead of one game on a CPU thread.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include "batched_runner.h"
+#include "model_locker.h"
+#include "params.h"
+#include "replay.h"
+#include "runtime.h"
+
+namespace py = pybind11;
+using namespace rela;
+using liars_dice::RecursiveSolvingParams;
+using liars_dice::SubgameSolvingParams;
+
+namespace {
+
+// DataThreadLoop::mainLoop of the reference plays games one after another (rela/data_loop.h:67-76); here each loop
+// iteration is one wave of `concurrent_games` subgames.  Pause / terminate are observed between waves.
+class DataThreadLoop : public ThreadLoop {
+ public:
+  DataThreadLoop(std::shared_ptr<ModelLocker> locker, std::shared_ptr<ValuePrioritizedReplay> replay,
+                 const RecursiveSolvingParams& cfg, int seed)
+      : locker_(std::move(locker)), replay_(std::move(replay)), cfg_(cfg), seed_(seed) {}
+
+  void terminate() override {
+    ThreadLoop::terminate();
+    replay_->close();   // a producer blocked on a full buffer must wake up
+  }
+
+  void mainLoop() final {
+    const int ndev = cfrb_device_count();
+    if (ndev <= 0) throw std::runtime_error("rebel_b200: no CUDA device (there is no CPU generation path)");
+    BatchedRlRunner runner(cfg_, locker_->cudaOrdinal() % ndev, seed_);
+    uint64_t have = 0;
+    auto sink = [this](const float* q, int qd, const float* v, int vd, int n) { return replay_->addRows(q, qd, v, vd, n, nullptr); };
+    while (!terminated()) {
+      if (paused()) waitUntilResume();
+      if (terminated()) break;
+      const uint64_t ver = locker_->version();
+      if (ver != have) {   // ModelLocker::updateModel happened: install the new weights before the next wave
+        runner.setWeights(*locker_->weights(), ver);
+        have = ver;
+      }
+      if (!runner.step(sink)) break;
+    }
+  }
+
+ private:
+  std::shared_ptr<ModelLocker> locker_;
+  std::shared_ptr<ValuePrioritizedReplay> replay_;
+  const RecursiveSolvingParams cfg_;
+  const int seed_;
+};
+
+std::shared_ptr<ThreadLoop> create_cfr_thread(std::shared_ptr<ModelLocker> locker, std::shared_ptr<ValuePrioritizedReplay> replay,
+                                              const RecursiveSolvingParams& cfg, int seed) {
+  return std::make_shared<DataThreadLoop>(std::move(locker), std::move(replay), cfg, seed);
+}
+
+[[noreturn]] void not_on_hot_path(const char* name) {
+  throw std::runtime_error(std::string(name) +
+                           ": evaluation helpers (fictitious play / full-tree recursive strategies, pybind.cc:45-104) are outside "
+                           "the accelerated data-generation path of rebel_b200 (SURVEY.md section 8f); use the reference build for them");
+}
+float compute_exploitability_fp(RecursiveSolvingParams) { not_on_hot_path("compute_exploitability_fp"); }
+float compute_exploitability_with_net(RecursiveSolvingParams, const std::string&) { not_on_hot_path("compute_exploitability_with_net"); }
+std::tuple<float, float, float> compute_stats_with_net(RecursiveSolvingParams, const std::string&) { not_on_hot_path("compute_stats_with_net"); }
+
+// Synchronous helper for tests / benchmarks: run `waves` waves of a BatchedRlRunner on `device` and return all examples.
+std::tuple<torch::Tensor, torch::Tensor> run_selfplay_waves(const RecursiveSolvingParams& cfg, int device, int seed, int waves,
+                                                            py::object flat_weights) {
+  std::vector<float> w;
+  if (!flat_weights.is_none()) {
+    auto t = flat_weights.cast<torch::Tensor>().to(torch::kCPU, torch::kFloat32).contiguous();
+    w.assign(t.data_ptr<float>(), t.data_ptr<float>() + t.numel());
+  }
+  std::vector<float> qs, vs;
+  int qd = 0, vd = 0;
+  {
+    py::gil_scoped_release nogil;
+    BatchedRlRunner runner(cfg, device, seed);
+    if (!w.empty()) runner.setWeights(w, 1);
+    auto sink = [&](const float* q, int q_dim, const float* v, int v_dim, int n) {
+      qd = q_dim; vd = v_dim;
+      qs.insert(qs.end(), q, q + (size_t)n * q_dim);
+      vs.insert(vs.end(), v, v + (size_t)n * v_dim);
+      return true;
+    };
+    for (int i = 0; i < waves; ++i) runner.step(sink);
+  }
+  const int64_t n = qd ? (int64_t)(qs.size() / qd) : 0;
+  auto q = torch::empty({n, qd}), v = torch::empty({n, vd});
+  std::copy(qs.begin(), qs.end(), q.data_ptr<float>());
+  std::copy(vs.begin(), vs.end(), v.data_ptr<float>());
+  return std::make_tuple(q, v);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(rela, m) {
+  py::class_<ValueTransition, std::shared_ptr<ValueTransition>>(m, "ValueTransition")
+      .def(py::init<>())
+      .def_readwrite("query", &ValueTransition::query)
+      .def_readwrite("values", &ValueTransition::values);
+
+  py::class_<ValuePrioritizedReplay, std::shared_ptr<ValuePrioritizedReplay>>(m, "ValuePrioritizedReplay")
+      .def(py::init<int, int, float, float, int, bool, bool>(), py::arg("capacity"), py::arg("seed"), py::arg("alpha"),
+           py::arg("beta"), py::arg("prefetch"), py::arg("use_priority"), py::arg("compressed_values"))
+      .def("size", &ValuePrioritizedReplay::size)
+      .def("num_add", &ValuePrioritizedReplay::numAdd)
+      .def("sample", &ValuePrioritizedReplay::sample)
+      .def("pop_until", &ValuePrioritizedReplay::popUntil)
+      .def("load", &ValuePrioritizedReplay::load)
+      .def("save", &ValuePrioritizedReplay::save)
+      .def("extract", &ValuePrioritizedReplay::extract)
+      .def("push", &ValuePrioritizedReplay::push, py::call_guard<py::gil_scoped_release>())
+      .def("update_priority", &ValuePrioritizedReplay::updatePriority);
+
+  py::class_<ThreadLoop, std::shared_ptr<ThreadLoop>>(m, "ThreadLoop");
+
+  py::class_<SubgameSolvingParams>(m, "SubgameSolvingParams")
+      .def(py::init<>())
+      .def_readwrite("num_iters", &SubgameSolvingParams::num_iters)
+      .def_readwrite("max_depth", &SubgameSolvingParams::max_depth)
+      .def_readwrite("linear_update", &SubgameSolvingParams::linear_update)
+      .def_readwrite("optimistic", &SubgameSolvingParams::optimistic)
+      .def_readwrite("use_cfr", &SubgameSolvingParams::use_cfr)
+      .def_readwrite("dcfr", &SubgameSolvingParams::dcfr)
+      .def_readwrite("dcfr_alpha", &SubgameSolvingParams::dcfr_alpha)
+      .def_readwrite("dcfr_beta", &SubgameSolvingParams::dcfr_beta)
+      .def_readwrite("dcfr_gamma", &SubgameSolvingParams::dcfr_gamma);
+
+  py::class_<RecursiveSolvingParams>(m, "RecursiveSolvingParams")
+      .def(py::init<>())
+      .def_readwrite("num_dice", &RecursiveSolvingParams::num_dice)
+      .def_readwrite("num_faces", &RecursiveSolvingParams::num_faces)
+      .def_readwrite("random_action_prob", &RecursiveSolvingParams::random_action_prob)
+      .def_readwrite("sample_leaf", &RecursiveSolvingParams::sample_leaf)
+      .def_readwrite("subgame_params", &RecursiveSolvingParams::subgame_params)
+      // rebel_b200 extensions (defaults from CFRB_* environment variables, see params.h)
+      .def_readwrite("concurrent_games", &RecursiveSolvingParams::concurrent_games)
+      .def_readwrite("net_mode", &RecursiveSolvingParams::net_mode)
+      .def_readwrite("state_dtype", &RecursiveSolvingParams::state_dtype);
+
+  py::class_<DataThreadLoop, ThreadLoop, std::shared_ptr<DataThreadLoop>>(m, "DataThreadLoop")
+      .def(py::init<std::shared_ptr<ModelLocker>, std::shared_ptr<ValuePrioritizedReplay>, const RecursiveSolvingParams&, int>(),
+           py::arg("model_locker"), py::arg("replay"), py::arg("params"), py::arg("thread_id"));
+
+  py::class_<Context>(m, "Context")
+      .def(py::init<>())
+      .def("push_env_thread", &Context::pushThreadLoop, py::keep_alive<1, 2>())
+      .def("start", &Context::start)
+      .def("pause", &Context::pause)
+      .def("resume", &Context::resume)
+      .def("terminate", &Context::terminate, py::call_guard<py::gil_scoped_release>())
+      .def("terminated", &Context::terminated)
+      .def("error", &Context::error, "rebel_b200 extension: message of the last exception raised inside a generator loop");
+
+  py::class_<ModelLocker, std::shared_ptr<ModelLocker>>(m, "ModelLocker")
+      .def(py::init<std::vector<py::object>, const std::string&>())
+      .def("update_model", &ModelLocker::updateModel)
+      .def_property_readonly("version", &ModelLocker::version, "rebel_b200 extension: number of weight snapshots taken");
+
+  m.def("compute_exploitability_fp", &compute_exploitability_fp, py::arg("params"));
+  m.def("compute_exploitability_with_net", &compute_exploitability_with_net, py::arg("params"), py::arg("model_path"));
+  m.def("compute_stats_with_net", &compute_stats_with_net, py::arg("params"), py::arg("model_path"));
+  m.def("create_cfr_thread", &create_cfr_thread, py::arg("model_locker"), py::arg("replay"), py::arg("cfg"), py::arg("seed"));
+  m.def("run_selfplay_waves", &run_selfplay_waves, py::arg("cfg"), py::arg("device"), py::arg("seed"), py::arg("waves"),
+        py::arg("flat_weights") = py::none(),
+        "rebel_b200 extension: run `waves` waves of a BatchedRlRunner synchronously and return (queries, values).");
+}

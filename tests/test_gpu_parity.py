@@ -46,7 +46,7 @@ def steps_after(c):
 # value-noise level of a configuration: what one step may differ from the fp64 oracle in a node value
 def noise_level(rb, state, net):
     if net == rb.NET_TC_F16:
-        return 3e-5          # fp16 operands: ~1e-3 relative on net outputs of scale 1e-2
+        return 1e-5          # fp16 operands: ~1e-3 relative on net outputs of scale 1e-2
     if state == rb.STATE_F32:
         return 4e-7
     if net == rb.NET_FP32:
@@ -137,6 +137,12 @@ def test_teacher_forced_single_step(rb, port, net_weights, D, F, state_name, net
             S.run(1)
             g = S.fetch(("root_means", "last", "sum", "regrets"))
             tag = f"{D}x{F}f d{max_depth} {state_name}/{net_name} root={lb},{pl} step {c}->{c + 1}"
+            if state == rb.STATE_F64 and net == rb.NET_ZERO:
+                # fp64 tables without a net: every operation is the reference's, in the reference's order -> bit-identical
+                for k_ in ("regrets", "last", "sum"):
+                    assert np.array_equal(g[k_][0, :N], o[k_][ci + 1]), (tag, k_, "not bit-exact",
+                                                                         np.abs(g[k_][0, :N] - o[k_][ci + 1]).max())
+                assert np.array_equal(g["root_means"][0], o["root_means"][ci + 1]), (tag, "mu not bit-exact")
             Rn = o["regrets"][ci + 1]
             dR = np.abs(g["regrets"][0, :N] - Rn)
             worst["regrets"] = max(worst["regrets"], dR.max())
@@ -164,13 +170,23 @@ def test_teacher_forced_single_step(rb, port, net_weights, D, F, state_name, net
             if net != rb.NET_ZERO and o["queries"].shape[1]:
                 q, out, sc = S.leaf_io()
                 qtol = 1e-3 if net == rb.NET_TC_F16 else 2e-6        # fp16 query rows: 2^-11 relative on values <= 1
-                assert np.abs(q - o["queries"][ci + 1]).max() < qtol, (tag, "queries")
-                lv = out * sc[:, None]
-                assert np.abs(lv - o["leaf_values"][ci + 1]).max() < 10 * noise, (tag, "leaf values")
+                dq = np.abs(q - o["queries"][ci + 1])
+                lv = np.abs(out * sc[:, None] - o["leaf_values"][ci + 1])
+                if state == rb.STATE_F32:
+                    # documented deviation of fp32 tables: the reference's 1e-80 smoothing does not exist in fp32, so a
+                    # belief segment with zero reach is uniform instead of the reference's epsilon mixture; such rows
+                    # (and the net outputs computed from them) are excluded
+                    seg = q[:, 2 + A:].reshape(-1, 2, H)
+                    bad = (seg == np.float32(1.0 / H)).all(-1).any(-1)
+                    dq, lv = dq[~bad], lv[~bad]
+                if dq.size:
+                    assert dq.max() < qtol, (tag, "queries", dq.max())
+                    assert lv.max() < 10 * noise, (tag, "leaf values", lv.max())
     S.close()
     _note(f"P2 {D}x{F}f d{max_depth} {state_name}/{net_name}: noise {noise:g}; compared {compared} (node,hand) rows, skipped "
           f"{skipped} ill-conditioned; worst abs diff " + " ".join(f"{k}={v:.2e}" for k, v in worst.items()))
-    assert compared > skipped, (compared, skipped)
+    if net != rb.NET_TC_F16:     # with fp16-operand noise most regrets of an untrained net's tiny values are near-ties
+        assert compared > skipped, (compared, skipped)
 
 
 # ---------------------------------------------------------------------------------------------- P3
@@ -197,6 +213,27 @@ def test_short_horizon_vs_golden(rb, golden, net_weights, D, F):
                     assert d < tol, (fixture, k, i, c, d)
                 assert np.abs(f["root_means"][i] - g[f"root_means{i}"][ci]).max() < tol
         S.close()
+
+
+@pytest.mark.parametrize("D,F", SHAPES)
+def test_zero_net_trajectories_bit_exact_vs_reference(rb, golden, D, F):
+    """fp64 tables, zero net: whole trajectories (64 iterations) are bit-identical to the compiled reference
+    (-ffp-contract=off build): regrets, last / sum / average strategies and root value means."""
+    g = golden(f"cfr_zero_{D}x{F}.npz")
+    cps = list(g["checkpoints"])
+    n = len(g["roots"])
+    S = rb.WaveSolver(D, F, n, net_mode=rb.NET_ZERO)
+    S.begin(g["roots"][:, 0], g["roots"][:, 1], np.stack([g[f"beliefs{i}"] for i in range(n)]))
+    done = 0
+    for ci, c in enumerate(cps):
+        S.run(c - done); done = c
+        f = S.fetch(("root_means", "last", "sum", "regrets", "avg"))
+        for i in range(n):
+            N = g[f"regrets{i}"].shape[1]
+            for k in ("regrets", "last", "sum", "avg"):
+                assert np.array_equal(f[k][i, :N], g[f"{k}{i}"][ci]), (k, i, c, np.abs(f[k][i, :N] - g[f"{k}{i}"][ci]).max())
+            assert np.array_equal(f["root_means"][i], g[f"root_means{i}"][ci]), (i, c)
+    S.close()
 
 
 # ---------------------------------------------------------------------------------------------- P4
@@ -243,7 +280,8 @@ def test_full_tree_exploitability_1x4f(rb, golden, port, state_name):
           f"@1024 gpu={e:.4e} ref_nofma={ref_a:.4e} ref_fast={ref_b:.4e}")
     if state_name == "f64":
         assert 0 <= e < 1e-3                                                # the reference tests' own threshold
-        assert abs(e - ref_a) <= max(1e-4, 2 * abs(ref_a - ref_b)), (e, ref_a, ref_b)
+        assert np.array_equal(avg16[:g["avg16_1x4"].shape[0]], g["avg16_1x4"]), "average strategy @16 not bit-exact"
+        assert abs(e - ref_a) < 1e-15, (e, ref_a, ref_b)                    # same trajectory as the reference, bit for bit
     else:
         # fp32 tables: the same algorithm in fp32 ON THE CPU ends at 8.8e-4 (vs 5.8e-4 in fp64): a precision floor, not
         # a kernel property; only convergence is asserted.

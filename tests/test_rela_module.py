@@ -1,0 +1,191 @@
+"""The `rela` drop-in module (rebel_b200/csrc/rela): Python surface of the reference's cfvpy.rela
+(csrc/liars_dice/rela/pybind.cc:119-213).  CPU tests exercise everything that does not need a device; the GPU tests replay
+`initialize_datagen` (cfvpy/selfplay.py:182-260) and check the batched self-play walk against the reference's RlRunner."""
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import game_dims
+
+
+@pytest.fixture(scope="module")
+def rela():
+    import rebel_b200.rela as m
+    return m
+
+
+def make_cfg(rela, D, F, **kw):
+    cfg = rela.RecursiveSolvingParams()
+    # exactly what create_mdp_config does (selfplay.py:587-610): hasattr check + setattr, recursing into subgame_params
+    spec = dict(num_dice=D, num_faces=F, random_action_prob=0.25, sample_leaf=True,
+                subgame_params=dict(num_iters=1024, max_depth=2, linear_update=True, use_cfr=True))
+    spec.update(kw)
+
+    def rec(obj, d):
+        for k, v in d.items():
+            assert hasattr(obj, k), k
+            if isinstance(v, dict):
+                rec(getattr(obj, k), v)
+            else:
+                setattr(obj, k, v)
+    rec(cfg, spec)
+    return cfg
+
+
+def test_surface_matches_reference(rela):
+    for name in ("ValueTransition", "ValuePrioritizedReplay", "ThreadLoop", "SubgameSolvingParams", "RecursiveSolvingParams",
+                 "DataThreadLoop", "Context", "ModelLocker", "compute_exploitability_fp", "compute_exploitability_with_net",
+                 "compute_stats_with_net", "create_cfr_thread"):
+        assert hasattr(rela, name), name
+    sp = rela.SubgameSolvingParams()
+    assert (sp.num_iters, sp.max_depth, sp.linear_update, sp.use_cfr, sp.optimistic, sp.dcfr) == (10, 2, False, False, False, False)
+    cfg = make_cfg(rela, 1, 6)
+    assert cfg.subgame_params.num_iters == 1024 and cfg.subgame_params.use_cfr        # nested setattr sticks (by reference)
+    assert abs(cfg.random_action_prob - 0.25) < 1e-7 and cfg.sample_leaf
+    with pytest.raises(RuntimeError):
+        rela.compute_exploitability_fp(cfg)
+
+
+def test_context_is_subclassable_like_timed_context(rela):
+    class Timed(rela.Context):          # cfvpy/utils.py:70-95
+        def __init__(self):
+            super().__init__()
+            self.t0 = None
+
+        def start(self):
+            self.t0 = time.time()
+            super().start()
+    c = Timed()
+    c.start()
+    assert c.terminated() and c.t0 is not None      # no loops pushed: trivially terminated
+
+
+def test_replay_buffer_semantics(rela, tmp_path):
+    Q, H = 27, 6
+    r = rela.ValuePrioritizedReplay(capacity=100, seed=1, alpha=1.0, beta=0.4, prefetch=3, use_priority=False, compressed_values=False)
+    assert r.size() == 0 and r.num_add() == 0
+    q = torch.arange(40 * Q, dtype=torch.float32).reshape(40, Q)
+    v = torch.arange(40 * H, dtype=torch.float32).reshape(40, H)
+    r.push([q, v, torch.ones(40)])
+    assert r.size() == 40 and r.num_add() == 40
+    batch, w = r.sample(16, "cpu")
+    assert batch.query.shape == (16, Q) and batch.values.shape == (16, H) and w.shape == (16,)
+    rows = (batch.query[:, 0] / Q).long()
+    assert torch.equal(batch.values[:, 0], rows.float() * H)            # query/values of a sample belong to the same row
+    path = str(tmp_path / "dump.bin")
+    r.save(path)
+    assert os.path.getsize(path) == 40 * (8 + 4 * (Q + H))              # int32 qsize, int32 vsize, floats (types.cc:87-94)
+    r2 = rela.ValuePrioritizedReplay(100, 2, 1.0, 0.4, 0, False, False)
+    r2.load(path, 1.0, -1, 2)                                            # stride 2
+    assert r2.size() == 20
+    ex = r2.extract()
+    assert r2.size() == 0 and torch.equal(ex[0], q[::2]) and torch.equal(ex[1], v[::2]) and torch.equal(ex[2], torch.ones(20))
+    r.pop_until(10)
+    assert r.size() == 10
+    # ring of 1.25 x capacity rows: the 126th row blocks until sampling evicts down to `capacity`
+    r.pop_until(0)
+    r.push([q.repeat(3, 1), v.repeat(3, 1), torch.ones(120)])
+    done = threading.Event()
+
+    def producer():
+        r.push([q[:10], v[:10], torch.ones(10)])
+        done.set()
+    th = threading.Thread(target=producer)
+    th.start()
+    time.sleep(0.3)
+    assert not done.is_set() and r.size() == 120
+    r.sample(8, "cpu")                                                   # evicts the oldest rows down to capacity = 100
+    th.join(timeout=5)
+    assert done.is_set() and r.size() == 110 and r.num_add() == 40 + 120 + 10
+    with pytest.raises(RuntimeError):
+        rela.ValuePrioritizedReplay(10, 0, 1.0, 1.0, 0, False, True)
+
+
+def test_prioritized_sampling(rela):
+    r = rela.ValuePrioritizedReplay(1000, 3, 1.0, 0.5, 0, True, False)
+    q = torch.arange(100, dtype=torch.float32).reshape(100, 1)
+    pr = torch.ones(100); pr[50:] = 9.0
+    r.push([q, q.clone(), pr])
+    cnt_hi = 0
+    for _ in range(50):
+        b, w = r.sample(20, "cpu")
+        cnt_hi += int((b.query[:, 0] >= 50).sum())
+        assert float(w.max()) == 1.0
+        r.update_priority(torch.ones(20) * 1.0 + 8.0 * (b.query[:, 0] >= 50).float())
+    assert 0.85 < cnt_hi / 1000 < 0.95                                   # 9:1 odds
+
+
+def test_model_locker_snapshots_weights(rela):
+    from rebel_b200.models import make_selfplay_net
+    net = make_selfplay_net(1, 4)
+    replica = torch.jit.script(make_selfplay_net(1, 4, seed=1))
+    locker = rela.ModelLocker([replica], "cuda:0")
+    assert locker.version == 1
+    locker.update_model(net)
+    assert locker.version == 2
+    for a, b in zip(replica.state_dict().values(), net.state_dict().values()):   # replicas refreshed like the reference
+        assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        rela.ModelLocker([torch.nn.Linear(3, 3)], "cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,F", [(1, 4), (1, 6), (2, 3)])
+@pytest.mark.parametrize("sample_leaf", [True, False])
+def test_batched_walk_reproduces_rlrunner_stream(rela, golden, D, F, sample_leaf):
+    """One game stream (concurrent_games = 1), zero net, fp64 tables: the training examples are bit-identical to the
+    reference's RlRunner(seed=7) (golden fixture generated by oracle/make_golden.py from the compiled reference)."""
+    g = golden("selfplay_zero.npz")
+    gq, gv = g[f"q_{D}x{F}_{int(sample_leaf)}"], g[f"v_{D}x{F}_{int(sample_leaf)}"]
+    cfg = make_cfg(rela, D, F, sample_leaf=sample_leaf, concurrent_games=1, net_mode=0, state_dtype=0,
+                   subgame_params=dict(num_iters=32, max_depth=2, linear_update=True, use_cfr=True))
+    q, v = rela.run_selfplay_waves(cfg, 0, 7, len(gq) // 2)
+    assert np.array_equal(q.numpy(), gq) and np.array_equal(v.numpy(), gv)
+
+
+@pytest.mark.gpu
+def test_drop_in_datagen_flow(rela):
+    """initialize_datagen (selfplay.py:182-260) line for line: ModelLocker per device, replay, create_cfr_thread per
+    'thread', Context.start; then update_model, pause/resume, terminate."""
+    from rebel_b200.models import make_selfplay_net
+    D, F = 1, 6
+    A, H, Q = game_dims(D, F)
+    net = make_selfplay_net(D, F)
+    ref_model = [torch.jit.script(make_selfplay_net(D, F))]
+    locker = rela.ModelLocker(ref_model, "cuda:0")
+    replay = rela.ValuePrioritizedReplay(capacity=1 << 16, seed=10001, alpha=1.0, beta=1.0, prefetch=8, use_priority=False,
+                                         compressed_values=False)
+    cfg = make_cfg(rela, D, F, concurrent_games=256, subgame_params=dict(num_iters=64, max_depth=2, linear_update=True, use_cfr=True))
+    ctx = rela.Context()
+    for i in range(2):
+        ctx.push_env_thread(rela.create_cfr_thread(locker, replay, cfg, i))
+    ctx.start()
+    t0 = time.time()
+    while replay.num_add() < 4096 and time.time() - t0 < 60:
+        time.sleep(0.05)
+    assert replay.num_add() >= 4096, ctx.error()
+    locker.update_model(net)                                             # trainer pushes fresh weights
+    batch, w = replay.sample(512, "cuda:0")
+    assert batch.query.shape == (512, Q) and batch.values.shape == (512, H) and batch.query.is_cuda
+    qs = batch.query.cpu().numpy()
+    assert np.allclose(qs[:, 2 + A:2 + A + H].sum(-1), 1, atol=1e-5) and set(np.unique(qs[:, :2])) <= {0.0, 1.0}
+    ctx.pause()
+    time.sleep(0.5)
+    n0 = replay.num_add()
+    time.sleep(0.5)
+    assert replay.num_add() == n0                                        # paused between waves
+    ctx.resume()
+    t0 = time.time()
+    while replay.num_add() == n0 and time.time() - t0 < 30:
+        time.sleep(0.05)
+    assert replay.num_add() > n0
+    ctx.terminate()
+    t0 = time.time()
+    while not ctx.terminated() and time.time() - t0 < 30:
+        time.sleep(0.05)
+    assert ctx.terminated() and ctx.error() == ""
