@@ -219,6 +219,7 @@ def workload_config(args, k):
 def run_b200(args):
     import torch
     import rebel_b200 as rb
+    from rebel_b200 import dist as rbdist
     from rebel_b200.models import flatten_state_dict, make_selfplay_net
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,13 +241,7 @@ def run_b200(args):
 
     # ---- value-net weights: rank 0 owns them, NCCL broadcast to the other ranks (ModelLocker::updateModel analogue)
     nflat = 256 * Q + 3 * 256 + 256 * 256 + 3 * 256 + H * 256 + H
-    if rank == 0:
-        wt = torch.from_numpy(flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict())).to(dev)
-    else:
-        wt = torch.empty(nflat, dtype=torch.float32, device=dev)
-    if dist:
-        dist.broadcast(wt, src=0)
-    w = wt.cpu().numpy()
+    w = rbdist.broadcast_weights(flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict()) if rank == 0 else None, nflat, dev)
 
     mode, mode_name = rb.NET_FP32, "fp32"
     if args.net in ("auto", "tc"):
@@ -260,7 +255,7 @@ def run_b200(args):
     S.set_weights(w, version=1)
 
     # ---- this rank's shard of the job: subgames [rank*K, (rank+1)*K); inputs staged in pinned host memory
-    beliefs64 = workload_beliefs(K, H, rank * K)
+    beliefs64 = workload_beliefs(K, H, rbdist.shard_range(rank, world, K)[0])
     pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
     t_b = pin((K, 2, H), torch.float64); t_b.numpy()[:] = beliefs64
     t_lb = pin((K,), torch.int32); t_lb.fill_(-1)
@@ -276,11 +271,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if not dist:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return rbdist.max_over_ranks(ms, dev)
 
     # ================= device-resident throughput (`value`) =================
     S.begin(t_lb.numpy(), t_pl.numpy(), t_b.numpy(), t_act.numpy())
@@ -314,12 +305,7 @@ def run_b200(args):
         S.begin(t_lb.numpy(), t_pl.numpy(), t_b.numpy(), t_act.numpy())      # H2D from pinned memory
         S.run(iters, stream)
         q, v = S.examples()                                                   # D2H: training examples of the wave
-        if dist:                                                              # gather example blocks on rank 0 (NCCL)
-            blk = torch.from_numpy(np.concatenate([q.reshape(2 * K, Q), v.reshape(2 * K, H)], 1)).to(dev)
-            out = [torch.empty_like(blk) for _ in range(world)] if rank == 0 else None
-            dist.gather(blk, out, dst=0)
-            return out
-        return q, v
+        return rbdist.gather_examples(q, v, dev)                              # NCCL gather of the example blocks on rank 0
     for _ in range(min(args.warmup, 1)):
         e2e_step()
     barrier()

@@ -5,10 +5,25 @@
 
 namespace cfrb {
 
+// Hand counts with a compile-time specialisation (1x4f, 1x5f, 1x6f, 2x3f, 2x4f); anything else takes the generic path.
+#define CFRB_DISPATCH_H(H, CALL)          \
+  switch (H) {                            \
+    case 4: { CALL(4); break; }           \
+    case 5: { CALL(5); break; }           \
+    case 6: { CALL(6); break; }           \
+    case 9: { CALL(9); break; }           \
+    case 16: { CALL(16); break; }         \
+    default: { CALL(0); break; }          \
+  }
+
 template <typename real>
 cudaError_t cfr_configure(int group, int smem_bytes) {
   if (group != 32) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(cfr_iter_kernel<real, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaError_t e = cudaSuccess;
+#define CFRB_CFG(HC)                                                                                                      \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cfr_iter_kernel<real, 32, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  CFRB_CFG(0) CFRB_CFG(4) CFRB_CFG(5) CFRB_CFG(6) CFRB_CFG(9) CFRB_CFG(16)
+#undef CFRB_CFG
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(cfr_init_kernel<real, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
@@ -22,8 +37,13 @@ void cfr_launch_init(const CfrDev<real>& p, int group, int blocks, int threads, 
 template <typename real>
 void cfr_launch_iter(const CfrDev<real>& p, int group, int blocks, int threads, size_t smem, cudaStream_t st, int iter, int do_b,
                      int do_f, int scratch_per_group) {
-  if (group == 32) cfr_iter_kernel<real, 32><<<blocks, threads, smem, st>>>(p, iter, do_b, do_f, scratch_per_group);
-  else cfr_iter_kernel<real, 256><<<blocks, 256, 0, st>>>(p, iter, do_b, do_f, scratch_per_group);
+  if (group == 32) {
+#define CFRB_CALL(HC) cfr_iter_kernel<real, 32, HC><<<blocks, threads, smem, st>>>(p, iter, do_b, do_f, scratch_per_group)
+    CFRB_DISPATCH_H(p.H, CFRB_CALL)
+#undef CFRB_CALL
+  } else {
+    cfr_iter_kernel<real, 256, 0><<<blocks, 256, 0, st>>>(p, iter, do_b, do_f, scratch_per_group);
+  }
 }
 
 #define CFRB_INSTANTIATE(real)                                                                                             \

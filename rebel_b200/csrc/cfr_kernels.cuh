@@ -51,21 +51,23 @@ __device__ __forceinline__ float query_value(const CfrDev<real>& p, int q, int l
   if (q == 1) return (float)trav;
   if (q < 2 + A) return (q - 2 == leaf_bid) ? 1.f : 0.f;
   if (q < 2 + A + H) {
-    if (Eps<real>::kLiteral) return (float)((r0[q - 2 - A] + Eps<real>::v) / s0);     // util.h:68-78
-    return s0 > 0 ? (float)(r0[q - 2 - A] / s0) : 1.f / H;
+    if (Eps<real>::kLiteral) return (float)((r0[q - 2 - A] + Eps<real>::v) * s0);     // util.h:68-78 (s = 1 / sum)
+    return isfinite(s0) ? (float)(r0[q - 2 - A] * s0) : 1.f / H;
   }
   if (q < 2 + A + 2 * H) {
-    if (Eps<real>::kLiteral) return (float)((r1[q - 2 - A - H] + Eps<real>::v) / s1);
-    return s1 > 0 ? (float)(r1[q - 2 - A - H] / s1) : 1.f / H;
+    if (Eps<real>::kLiteral) return (float)((r1[q - 2 - A - H] + Eps<real>::v) * s1);
+    return isfinite(s1) ? (float)(r1[q - 2 - A - H] * s1) : 1.f / H;
   }
-  return 0.f;
+  // padding: column Q is the constant 1 that multiplies the bias column of W1 in the tensor-core net (leaf_mlp_tc.cuh);
+  // the fp32 SIMT net has a zero weight row there
+  return q == 2 + A + 2 * H ? 1.f : 0.f;
 }
 
 // Forward half of iteration `iter`: reach, query rows + scalers for pseudo-leaves, payoffs for terminals.
-template <typename real, int G>
-__device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0, real* reach1, real* lsum, int lane) {
+template <typename real, int G, int HC>
+__device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0, real* reach1, real* lsum, real* hist, int lane) {
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
-  const int H = p.H;
+  const int H = HC > 0 ? HC : p.H;      // compile-time hand count for the common shapes: item index -> (node, hand) without a division
   const int rp = p.sg_player[k];
   const real* __restrict__ Sg = p.Sg + (size_t)k * p.table_stride;
   const real* __restrict__ b = p.beliefs + (size_t)k * 2 * H;
@@ -95,7 +97,8 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
       s0 += reach0[n * H + h]; s1 += reach1[n * H + h];                      // vector_sum (:264)
       e0 += reach0[n * H + h] + Eps<real>::v; e1 += reach1[n * H + h] + Eps<real>::v;   // normalize_probabilities_safe
     }
-    lsum[2 * r] = e0; lsum[2 * r + 1] = e1;
+    // reciprocals: the query columns are float-rounded values of (x + eps) / sum; x * (1 / sum) is within one float ulp
+    lsum[2 * r] = (real)1 / e0; lsum[2 * r + 1] = (real)1 / e1;
     p.scaler[row0 + r] = trav == 0 ? s1 : s0;
   }
   group_sync<G>();
@@ -129,20 +132,16 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
   }
   // ---- terminals (compute_expected_terminal_values, subgame_solving.cc:80-98; win probability :765-789)
   // term_node holds three lists of length T: node id, challenged bid (= parent's last_bid, :287), node depth.
+  // Pass 1 (one lane per terminal): believed_counts[m] += reach (hand order), suffix sums from the top (:770-779) and the
+  // belief sum — the reference's operation order, so the fp64 path is bit-identical.  Pass 2 (one lane per (terminal,
+  // hand)) picks cum[max(0, quantity - matches(hand))], float-rounds it like :785 and forms the payoff.
+  constexpr int kMaxBins = 9;            // 2 * num_dice + 1 <= 9
   real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
   const real* ropp = trav == 0 ? reach1 : reach0;
-  for (int it = lane; it < t.T * H; it += G) {
-    const int z = it / H, h = it % H;
+  for (int z = lane; z < t.T; z += G) {
     const int n = p.term_node[t.term_off + z];
-    const int pbid = p.term_node[t.term_off + t.T + z];
-    const int ndepth = p.term_node[t.term_off + 2 * t.T + z];
-    const int quantity = 1 + pbid / p.F, face = pbid % p.F;   // unpack_action, liars_dice.h:74-80
+    const int face = p.term_node[t.term_off + t.T + z] % p.F;
     const real* ro = ropp + n * H;
-    // P(h) = sum of opponent reach over hands g with matches(g) >= quantity - matches(h): the suffix sum of
-    // the match-count histogram the reference builds (:770-779), evaluated directly; float-rounded like :785.
-    // believed_counts[m] += reach (hand order), suffix sums from the top (:770-779): same operation order as the
-    // reference so that the fp64 path is bit-identical.  Bins above kMaxBins-1 cannot occur (2*num_dice+1 <= kMaxBins).
-    constexpr int kMaxBins = 9;
     real cnt[kMaxBins];
 #pragma unroll
     for (int m = 0; m < kMaxBins; ++m) cnt[m] = 0;
@@ -156,11 +155,19 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
     }
 #pragma unroll
     for (int m = kMaxBins - 2; m >= 0; --m) cnt[m] += cnt[m + 1];
-    int left = quantity - (int)p.matches[h * p.F + face];
-    left = left < 0 ? 0 : left;
-    real win = 0;
 #pragma unroll
-    for (int m = 0; m < kMaxBins; ++m) win = (m == left) ? cnt[m] : win;
+    for (int m = 0; m < kMaxBins; ++m) hist[z * (kMaxBins + 1) + m] = cnt[m];
+    hist[z * (kMaxBins + 1) + kMaxBins] = tot;
+  }
+  group_sync<G>();
+  for (int it = lane; it < t.T * H; it += G) {
+    const int z = it / H, h = it % H;
+    const int pbid = p.term_node[t.term_off + t.T + z];
+    const int ndepth = p.term_node[t.term_off + 2 * t.T + z];
+    const int quantity = 1 + pbid / p.F, face = pbid % p.F;   // unpack_action, liars_dice.h:74-80
+    int left = quantity - (int)p.matches[h * p.F + face];
+    left = left < 0 ? 0 : (left > kMaxBins - 1 ? kMaxBins - 1 : left);
+    const real win = hist[z * (kMaxBins + 1) + left], tot = hist[z * (kMaxBins + 1) + kMaxBins];
     const real v = (real)(float)win * 2 - tot;
     // state.player_id of a terminal = the bidder; payoff is negated iff that is not the traverser (:290)
     const int pl = rp ^ (ndepth & 1);
@@ -169,10 +176,10 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
 }
 
 // Backward half of iteration with traverser `trav` (update_regrets :538-575 and step :577-664).
-template <typename real, int G>
+template <typename real, int G, int HC>
 __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, real* rt, real* tmp, int lane) {
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
-  const int H = p.H;
+  const int H = HC > 0 ? HC : p.H;
   const int rp = p.sg_player[k];
   real* __restrict__ R = p.R + (size_t)k * p.table_stride;
   real* __restrict__ Sg = p.Sg + (size_t)k * p.table_stride;
@@ -290,7 +297,7 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
 }
 
 // iter: global iteration index of the forward half.  do_b: run backward half of iteration iter-1 first.
-template <typename real, int G>
+template <typename real, int G, int HC>
 __global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
@@ -299,11 +306,10 @@ __global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter,
   const int k = blockIdx.x * groups_per_cta + gid;
   if (k >= *p.wave_n) return;   // uniform per group (and per CTA when G == blockDim.x)
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
-  const int NH = t.N * p.H;
   real* base = (G == 32) ? smem + (size_t)gid * scratch_per_group : p.scratch + (size_t)k * p.scratch_stride;
-  real* bufA = base; real* bufB = base + NH; real* tmp = base + 2 * NH; real* lsum = base + 3 * NH;
+  real* bufA = base; real* bufB = base + p.nh_max; real* tmp = base + 2 * p.nh_max; real* lsum = tmp + p.tmp_reals;
   if (do_b) {
-    cfr_backward<real, G>(p, k, (iter - 1) & 1, bufA, bufB, tmp, lane);
+    cfr_backward<real, G, HC>(p, k, (iter - 1) & 1, bufA, bufB, tmp, lane);
     group_sync<G>();
   }
   // sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter,
     real* __restrict__ Sn = p.Snap + (size_t)k * p.table_stride;
     for (int i = lane; i < (t.N - 1) * p.H; i += G) Sn[i] = Sg[i];
   }
-  if (do_f) cfr_forward<real, G>(p, k, iter & 1, bufA, bufB, lsum, lane);
+  if (do_f) cfr_forward<real, G, HC>(p, k, iter & 1, bufA, bufB, lsum, tmp, lane);
 }
 
 // Wave initialisation == CFR constructor (subgame_solving.cc:509-524): uniform last strategy, zero regrets,
@@ -326,9 +332,9 @@ __global__ void __launch_bounds__(256) cfr_init_kernel(CfrDev<real> p, int scrat
   const int k = blockIdx.x * groups_per_cta + gid;
   if (k >= *p.wave_n) return;
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
-  const int H = p.H, NH = t.N * H;
+  const int H = p.H;
   real* base = (G == 32) ? smem + (size_t)gid * scratch_per_group : p.scratch + (size_t)k * p.scratch_stride;
-  real* reach0 = base; real* reach1 = base + NH;
+  real* reach0 = base; real* reach1 = base + p.nh_max;
   real* __restrict__ R = p.R + (size_t)k * p.table_stride;
   real* __restrict__ Sg = p.Sg + (size_t)k * p.table_stride;
   real* __restrict__ S = p.S + (size_t)k * p.table_stride;

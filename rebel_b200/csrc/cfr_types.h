@@ -34,13 +34,16 @@ struct CfrDev {
   const float* net_out;           // [rows][Hout] raw net outputs
   real* scaler;                   // [rows] sum of opponent reach at the pseudo-leaf
   real* scratch; size_t scratch_stride;   // global scratch (CTA groups), reals per subgame
+  int nh_max, tmp_reals;                  // scratch layout: bufA[nh_max] | bufB[nh_max] | tmp[tmp_reals] | lsum[2*Lmax]
   // params
   int linear, dcfr; real dcfr_alpha, dcfr_beta, dcfr_gamma;
   int use_net;
 };
 
-// Scratch layout of a group (reals): bufA[N*H] | bufB[N*H] | tmp[N*H] | lsum[2*L]
-__host__ __device__ inline int cfr_scratch_reals(int N, int H, int L) { return 3 * N * H + 2 * (L > 0 ? L : 1); }
+// Scratch of a group (reals): bufA[N*H] | bufB[N*H] | tmp[max(N*H, 10*T)] | lsum[2*L]  (tmp doubles as the per-terminal
+// match-count histogram: 9 bins + belief sum per terminal)
+__host__ __device__ inline int cfr_tmp_reals(int N, int H, int T) { return N * H > 10 * T ? N * H : 10 * T; }
+__host__ __device__ inline int cfr_scratch_reals(int N, int H, int L, int T) { return 2 * N * H + cfr_tmp_reals(N, H, T) + 2 * (L > 0 ? L : 1); }
 
 // Launchers implemented in cfr_kernels.cu (explicitly instantiated for float and double).  `group` is 32 (one warp per
 // subgame, shared-memory scratch) or 256 (one CTA per subgame, global scratch).

@@ -147,6 +147,7 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   d.Xh = h->cfg.net_mode == CFRB_NET_TC_F16 ? h->d_Xh.p : nullptr;
   d.net_out = h->d_out.p; d.scaler = s.scaler.p;
   d.scratch = h->group == 32 ? nullptr : s.scratch.p; d.scratch_stride = h->scratch_per_group;
+  d.nh_max = h->Nmax * g.H; d.tmp_reals = cfrb::cfr_tmp_reals(h->Nmax, g.H, h->Tmax);
   d.linear = h->cfg.linear_update; d.dcfr = h->cfg.dcfr;
   d.dcfr_alpha = (real)h->cfg.dcfr_alpha; d.dcfr_beta = (real)h->cfg.dcfr_beta; d.dcfr_gamma = (real)h->cfg.dcfr_gamma;
   d.use_net = h->cfg.net_mode != CFRB_NET_ZERO;
@@ -395,10 +396,10 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
 
   // ---- sizes
   const int K = cfg->max_subgames;
-  h->Qpad = round_up(g.Q, 16);
+  h->Qpad = round_up(g.Q + 1, 16);   // one spare column carries the constant 1 that feeds bias 1 through the tensor cores
   h->Hout = g.H;
   h->table_stride = std::max(1, (h->Nmax - 1) * g.H);
-  h->scratch_per_group = cfrb::cfr_scratch_reals(h->Nmax, g.H, h->Lmax);
+  h->scratch_per_group = cfrb::cfr_scratch_reals(h->Nmax, g.H, h->Lmax, h->Tmax);
   int max_optin = 0;
   CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
   CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -498,13 +499,18 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
     __half* hw2 = reinterpret_cast<__half*>(blob.data() + L.off_w2);
     __half* hw3 = reinterpret_cast<__half*>(blob.data() + L.off_w3);
     for (int j = 0; j < hid; ++j) for (int k = 0; k < Q; ++k) hw1[cfrb::tc::umma_kmajor_offset_halves(j, k, hid)] = __float2half_rn(w1[(size_t)j * Q + k]);
+    for (int j = 0; j < hid; ++j) hw1[cfrb::tc::umma_kmajor_offset_halves(j, Q, hid)] = __float2half_rn(b1[j]);   // bias 1 x constant-1 column
+    __half* hones = reinterpret_cast<__half*>(blob.data() + L.off_ones);
+    __half* hb2 = reinterpret_cast<__half*>(blob.data() + L.off_bias2);
+    for (int r = 0; r < cfrb::tc::kTileM; ++r) hones[cfrb::tc::umma_kmajor_offset_halves(r, 0, cfrb::tc::kTileM)] = __float2half_rn(1.f);
+    for (int j = 0; j < hid; ++j) hb2[cfrb::tc::umma_kmajor_offset_halves(j, 0, hid)] = __float2half_rn(b2[j]);
     for (int j = 0; j < hid; ++j) for (int k = 0; k < hid; ++k) hw2[cfrb::tc::umma_kmajor_offset_halves(j, k, hid)] = __float2half_rn(w2[(size_t)j * hid + k]);
     for (int j = 0; j < H; ++j) for (int k = 0; k < hid; ++k) hw3[cfrb::tc::umma_kmajor_offset_halves(j, k, cfrb::tc::kNout)] = __float2half_rn(w3[(size_t)j * hid + k]);
     float* ln1 = reinterpret_cast<float*>(blob.data() + L.off_ln1);
     float* ln2 = reinterpret_cast<float*>(blob.data() + L.off_ln2);
     for (int j = 0; j < hid; ++j) {
-      ln1[4 * j] = b1[j]; ln1[4 * j + 1] = g1[j]; ln1[4 * j + 2] = be1[j];
-      ln2[4 * j] = b2[j]; ln2[4 * j + 1] = g2[j]; ln2[4 * j + 2] = be2[j];
+      ln1[2 * j] = g1[j]; ln1[2 * j + 1] = be1[j];
+      ln2[2 * j] = g2[j]; ln2[2 * j + 1] = be2[j];
     }
     std::copy(b3, b3 + H, reinterpret_cast<float*>(blob.data() + L.off_b3));
     if (!h->d_blob.p) CK(h->d_blob.alloc(L.blob_bytes));

@@ -10,9 +10,11 @@
 //     --epilogue-->  A3 in TMEM cols [256,384)
 //     --tcgen05.mma TS (N = 16)-->  D3 [128 x 16] in TMEM cols [384,400)  --epilogue (+bias)-->  out[rows][H] fp32
 //
-// Warp roles (288 threads): warps 0-7 = epilogue — warp w owns TMEM lanes 32*(w&3).. (one row per thread) and the column
-// half (w>>2), so a thread keeps its 128 accumulators in registers, reads TMEM once per layer and exchanges its LayerNorm
-// partial sums with the partner warp through shared memory; warp 8 = TMEM allocator + single-thread MMA issuer.
+// Warp roles (544 threads): warps 0-15 = epilogue — warp w owns TMEM lanes 32*(w&3).. (one row per thread) and the column
+// quarter (w>>2), so a thread keeps its 64 accumulators in registers, reads TMEM once per layer and exchanges its LayerNorm
+// partial sums with the three partner warps through shared memory; warp 16 = TMEM allocator + single-thread MMA issuer.
+// The biases ride on the tensor cores: layer 1 through a constant-1 query column (written by the CFR kernel) against a bias
+// column in W1, layer 2 through one extra K=16 MMA of a constant "ones" tile against a bias tile.
 // mbarriers: x (query tile staged), d1/d2/d3 (accumulator ready, via tcgen05.commit), a2/a3 (A operand ready).
 // Each barrier completes exactly once per tile, so one parity bit per tile iteration serves all of them.
 #pragma once
@@ -26,25 +28,29 @@ namespace tc {
 constexpr int kHid = 256;
 constexpr int kTileM = 128;
 constexpr int kNout = 16;                 // output features padded to the minimum UMMA N
-constexpr int kEpiThreads = 256;             // 8 epilogue warps
+constexpr int kParts = 4;                    // column quarters per row
+constexpr int kColsPerThread = kHid / kParts;   // 64
+constexpr int kEpiThreads = 128 * kParts;    // 16 epilogue warps
 constexpr int kThreads = kEpiThreads + 32;   // + allocator / MMA-issuer warp
 constexpr uint32_t kColD = 0, kColA = 256, kColD3 = 384, kTmemCols = 512;
 
 // ---- shared-memory / weight-blob layout (bytes).  The blob in global memory has exactly the smem layout up to kOffX.
 struct BlobLayout {
-  int Kp;            // padded query width (multiple of 16)
-  int off_w1, off_w2, off_w3, off_ln1, off_ln2, off_b3, blob_bytes, off_x, off_part, off_bar, smem_bytes;
+  int Kp;            // padded query width (multiple of 16, with at least one spare column for the constant 1)
+  int off_w1, off_w2, off_w3, off_ones, off_bias2, off_ln1, off_ln2, off_b3, blob_bytes, off_x, off_part, off_bar, smem_bytes;
   __host__ __device__ explicit BlobLayout(int kp) : Kp(kp) {
-    off_w1 = 0;
-    off_w2 = off_w1 + kHid * kp * 2;
-    off_w3 = off_w2 + kHid * kHid * 2;
-    off_ln1 = off_w3 + kNout * kHid * 2;
-    off_ln2 = off_ln1 + kHid * 16;          // float4 {bias, gamma, beta, 0} per feature
-    off_b3 = off_ln2 + kHid * 16;
+    off_w1 = 0;                               // [256 x Kp]  fp16, column Q holds bias 1
+    off_w2 = off_w1 + kHid * kp * 2;          // [256 x 256] fp16
+    off_w3 = off_w2 + kHid * kHid * 2;        // [16 x 256]  fp16
+    off_ones = off_w3 + kNout * kHid * 2;     // [128 x 16]  fp16, column 0 = 1
+    off_bias2 = off_ones + kTileM * 16 * 2;   // [256 x 16]  fp16, column 0 = bias 2
+    off_ln1 = off_bias2 + kHid * 16 * 2;      // float2 {gamma, beta} per feature
+    off_ln2 = off_ln1 + kHid * 8;
+    off_b3 = off_ln2 + kHid * 8;
     blob_bytes = off_b3 + kNout * 4;
     off_x = (blob_bytes + 127) / 128 * 128;
-    off_part = off_x + kTileM * kp * 2;    // LayerNorm partial sums: [2 layers][2 halves][128 rows] float2
-    off_bar = off_part + 2 * 2 * kTileM * 8;
+    off_part = off_x + kTileM * kp * 2;       // LayerNorm partial sums: [2 layers][kParts][128 rows] float2
+    off_bar = off_part + 2 * kParts * kTileM * 8;
     smem_bytes = off_bar + 64;
   }
 };
@@ -148,47 +154,51 @@ __device__ __forceinline__ float gelu_tc(float y) {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// LayerNorm(eps 1e-5) + GELU of this thread's half row: 128 fp32 accumulators (TMEM lane = row, columns half*128..),
-// kept in registers; the two threads of a row exchange (sum, sum of squares) through `part`.  Result as fp16 into the
-// A-operand columns.  ln: float4 {bias, gamma, beta, -} per feature in smem (broadcast reads).
-__device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int half, int row, const float4* __restrict__ ln, float2* part,
+// LayerNorm(eps 1e-5) + GELU of this thread's quarter row: 64 fp32 accumulators (TMEM lane = row, columns part*64..),
+// bias already added by the tensor cores, kept in registers; the four threads of a row exchange (sum, sum of squares)
+// through `part`.  Result as fp16 into the A-operand columns.  ln: float2 {gamma, beta} per feature in smem (broadcast reads).
+__device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id, int row, const float2* __restrict__ ln, float2* part,
                                                  float* dbg_row) {
-  float x[128];
+  uint32_t xr[kColsPerThread];
+  {
+    uint32_t* lo = xr; uint32_t* hi = xr + 32;
+    CFRB_TMEM_LD32(tmem_row + kColD + part_id * kColsPerThread, lo);
+    CFRB_TMEM_LD32(tmem_row + kColD + part_id * kColsPerThread + 32, hi);
+    tmem_wait_ld();
+  }
   float sum = 0.f, sumsq = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    CFRB_TMEM_LD32(tmem_row + kColD + half * 128 + c * 32, v);
-    tmem_wait_ld();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (dbg_row) dbg_row[half * 128 + c * 32 + i] = __uint_as_float(v[i]);
-      const float xv = __uint_as_float(v[i]) + ln[half * 128 + c * 32 + i].x;
-      x[c * 32 + i] = xv;
-      sum += xv;
-      sumsq = fmaf(xv, xv, sumsq);
-    }
+  for (int i = 0; i < kColsPerThread; ++i) {
+    const float xv = __uint_as_float(xr[i]);
+    if (dbg_row) dbg_row[part_id * kColsPerThread + i] = xv;
+    sum += xv;
+    sumsq = fmaf(xv, xv, sumsq);
   }
-  part[half * kTileM + row] = make_float2(sum, sumsq);
+  part[part_id * kTileM + row] = make_float2(sum, sumsq);
   named_bar_sync(1, kEpiThreads);
-  const float2 o = part[(half ^ 1) * kTileM + row];
-  sum += o.x; sumsq += o.y;
+  sum = 0.f; sumsq = 0.f;
+#pragma unroll
+  for (int p = 0; p < kParts; ++p) {          // fixed order: all four threads of a row get bit-identical statistics
+    const float2 o = part[p * kTileM + row];
+    sum += o.x; sumsq += o.y;
+  }
   const float mean = sum * (1.f / kHid);
   const float var = fmaxf(sumsq * (1.f / kHid) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float shift = -mean * rstd;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < kColsPerThread / 32; ++c) {
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float4 p0 = ln[half * 128 + c * 32 + 2 * i], p1 = ln[half * 128 + c * 32 + 2 * i + 1];
-      const float y0 = fmaf(fmaf(x[c * 32 + 2 * i], rstd, shift), p0.y, p0.z);
-      const float y1 = fmaf(fmaf(x[c * 32 + 2 * i + 1], rstd, shift), p1.y, p1.z);
+      const int j = c * 32 + 2 * i;
+      const float2 p0 = ln[part_id * kColsPerThread + j], p1 = ln[part_id * kColsPerThread + j + 1];
+      const float y0 = fmaf(fmaf(__uint_as_float(xr[j]), rstd, shift), p0.x, p0.y);
+      const float y1 = fmaf(fmaf(__uint_as_float(xr[j + 1]), rstd, shift), p1.x, p1.y);
       const __half2 h = __floats2half2_rn(gelu_tc(y0), gelu_tc(y1));
       pk[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
-    CFRB_TMEM_ST16(tmem_row + kColA + half * 64 + c * 16, pk);
+    CFRB_TMEM_ST16(tmem_row + kColA + part_id * (kColsPerThread / 2) + c * 16, pk);
   }
   tmem_wait_st();
 }
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   const uint32_t sx = smem_u32(smem + L.off_x), sw1 = smem_u32(smem + L.off_w1), sw2 = smem_u32(smem + L.off_w2),
-                 sw3 = smem_u32(smem + L.off_w3);
+                 sw3 = smem_u32(smem + L.off_w3), sones = smem_u32(smem + L.off_ones), sbias2 = smem_u32(smem + L.off_bias2);
   const int x_tile_int4 = kTileM * a.Kp * 2 / 16;
 
   if (warp == kMmaWarp) {
@@ -255,11 +265,12 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
         for (int k = 0; k < a.Kp / 16; ++k)
           mma_ss(tmem_base + kColD, make_desc(sx + k * 2 * lbo_x, lbo_x, 128), make_desc(sw1 + k * 2 * lbo_w, lbo_w, 128), idesc256, k > 0);
         tc_commit(bar_d1);
-        // layer 2: D2 = A2 * W2^T  (A from TMEM: 16 fp16 = 8 columns per K step)
+        // layer 2: D2 = ones * bias2^T + A2 * W2^T  (A from TMEM: 16 fp16 = 8 columns per K step)
         mbar_wait(bar_a2, parity);
         tc_fence_after();
+        mma_ss(tmem_base + kColD, make_desc(sones, lbo_x, 128), make_desc(sbias2, lbo_w, 128), idesc256, 0);
         for (int k = 0; k < kHid / 16; ++k)
-          mma_ts(tmem_base + kColD, tmem_base + kColA + k * 8, make_desc(sw2 + k * 2 * lbo_w, lbo_w, 128), idesc256, k > 0);
+          mma_ts(tmem_base + kColD, tmem_base + kColA + k * 8, make_desc(sw2 + k * 2 * lbo_w, lbo_w, 128), idesc256, 1);
         tc_commit(bar_d2);
         // layer 3: D3 = A3 * W3^T  (N = 16)
         mbar_wait(bar_a3, parity);
@@ -270,21 +281,21 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
       }
     }
   } else {
-    // ===================== epilogue warps: thread == (row, column half) =====================
-    const int quad = warp & 3, half = warp >> 2;
+    // ===================== epilogue warps: thread == (row, column quarter) =====================
+    const int quad = warp & 3, part_id = warp >> 2;
     const int row_in_tile = quad * 32 + lane;                      // 0..127 == TMEM lane
     const uint32_t tmem_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const float4* ln1 = reinterpret_cast<const float4*>(smem + L.off_ln1);
-    const float4* ln2 = reinterpret_cast<const float4*>(smem + L.off_ln2);
+    const float2* ln1 = reinterpret_cast<const float2*>(smem + L.off_ln1);
+    const float2* ln2 = reinterpret_cast<const float2*>(smem + L.off_ln2);
     const float* b3 = reinterpret_cast<const float*>(smem + L.off_b3);
     float2* part1 = reinterpret_cast<float2*>(smem + L.off_part);
-    float2* part2 = part1 + 2 * kTileM;
+    float2* part2 = part1 + kParts * kTileM;
     int4* xdst = reinterpret_cast<int4*>(smem + L.off_x);
-    const int per_thread = x_tile_int4 / kEpiThreads;              // Kp/16 int4 per thread (2 or 3)
-    int4 xr[4];
+    const int x_items = x_tile_int4;                               // 512 or 768 int4 per tile: <= 2 per thread
+    int4 xr0, xr1;
     {
       const int4* xsrc = reinterpret_cast<const int4*>(a.Xh) + (size_t)blockIdx.x * x_tile_int4;
-      for (int i = 0; i < per_thread; ++i) xdst[tid + kEpiThreads * i] = __ldg(xsrc + tid + kEpiThreads * i);
+      for (int i = tid; i < x_items; i += kEpiThreads) xdst[i] = __ldg(xsrc + i);
       fence_proxy_async_smem();
       mbar_arrive(bar_x);
     }
@@ -297,28 +308,28 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
       tc_fence_after();
       if (next < ntiles) {
         const int4* xsrc = reinterpret_cast<const int4*>(a.Xh) + (size_t)next * x_tile_int4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < per_thread) xr[i] = __ldg(xsrc + tid + kEpiThreads * i);
+        xr0 = __ldg(xsrc + tid);
+        if (tid + kEpiThreads < x_items) xr1 = __ldg(xsrc + tid + kEpiThreads);
       }
-      epilogue_ln_gelu(tmem_row, half, row_in_tile, ln1, part1, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr);
+      epilogue_ln_gelu(tmem_row, part_id, row_in_tile, ln1, part1, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr);
       tc_fence_before();
       mbar_arrive(bar_a2);
       if (next < ntiles) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < per_thread) xdst[tid + kEpiThreads * i] = xr[i];
+        xdst[tid] = xr0;
+        if (tid + kEpiThreads < x_items) xdst[tid + kEpiThreads] = xr1;
         fence_proxy_async_smem();
         mbar_arrive(bar_x);
       }
       // ---- layer 2
       mbar_wait(bar_d2, parity);
       tc_fence_after();
-      epilogue_ln_gelu(tmem_row, half, row_in_tile, ln2, part2, (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr);
+      epilogue_ln_gelu(tmem_row, part_id, row_in_tile, ln2, part2, (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr);
       tc_fence_before();
       mbar_arrive(bar_a3);
       // ---- layer 3: raw net outputs (the CFR backward kernel multiplies by the opponent-reach scaler)
       mbar_wait(bar_d3, parity);
       tc_fence_after();
-      if (half == 0) {
+      if (part_id == 0) {
         uint32_t v[16];
         CFRB_TMEM_LD16(tmem_row + kColD3, v);
         tmem_wait_ld();

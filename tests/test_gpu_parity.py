@@ -113,6 +113,11 @@ def test_teacher_forced_single_step(rb, port, net_weights, D, F, state_name, net
     state = {"f64": rb.STATE_F64, "f32": rb.STATE_F32}[state_name]
     net = {"zero": rb.NET_ZERO, "fp32": rb.NET_FP32, "tc": rb.NET_TC_F16}[net_name]
     noise = noise_level(rb, state, net)
+    # fp32 tables + value net: the reference's 1e-80 smoothing cannot be represented, so the query of a leaf reached with zero
+    # probability carries uniform beliefs instead of the reference's epsilon mixture and the net output there differs at
+    # the 1e-3 level (documented deviation of CFRB_STATE_F32); CFRB_STATE_F64 (the default) has no such term
+    if state == rb.STATE_F32 and net != rb.NET_ZERO:
+        noise = 2e-4
     w = net_weights(D, F) if net != rb.NET_ZERO else None
     cps = [0, 1, 2, 3, 4, 5, 16, 17, 18, 101, 102, 103]
     roots = [(-1, 0), (-1, 1), (1, 1), (A - 4, 0)]
