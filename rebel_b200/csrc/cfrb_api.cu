@@ -419,7 +419,8 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     CK(h->d_dbg.alloc(2 * cfrb::tc::kTileM * cfrb::tc::kHid));
     const cfrb::tc::BlobLayout L(h->Qpad);
     if (L.smem_bytes > max_optin) return fail(CFRB_EINVAL, "tensor-core value net does not fit shared memory for this game shape");
-    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
   }
   CK(cudaFuncSetAttribute(cfrb::leaf_mlp_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)cfrb::leaf_mlp_fp32_smem(256)));
@@ -601,7 +602,8 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
     const cfrb::tc::BlobLayout L(h->Qpad);
     cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, dbg1, dbg2};
     const int tiles = (h->rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
-    cfrb::tc::leaf_mlp_tc_kernel<<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+    if (dbg1 || dbg2) cfrb::tc::leaf_mlp_tc_kernel<true><<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+    else cfrb::tc::leaf_mlp_tc_kernel<false><<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
   } else {
     const int blocks = (h->rows + cfrb::kMlpRows - 1) / cfrb::kMlpRows;
     cfrb::leaf_mlp_fp32_kernel<256><<<blocks, 256, cfrb::leaf_mlp_fp32_smem(256), st>>>(h->net, h->d_X.p, h->d_wave.p + 1, h->d_out.p);

@@ -144,8 +144,9 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // with ex2 / rcp so it is branch-free: y / (1 + 2^(-2 log2(e) u)), u = y (c0 + c1 y^2 + c2 y^4).
 __device__ __forceinline__ float gelu_tc(float y) {
   const float y2 = fminf(y * y, 52.f);                              // beyond |y| ~ 7.2 the logistic is saturated anyway
-  const float p = fmaf(y2, fmaf(y2, -3.5151e-4f, 3.70057e-2f), 7.97508e-1f);
-  const float t = y * p * -2.885390082f;                            // -2 log2(e) u
+  // -2 log2(e) * (c0 + c1 y^2 + c2 y^4)
+  const float p = fmaf(y2, fmaf(y2, 1.014244e-3f, -1.0677588e-1f), -2.3011216f);
+  const float t = y * p;
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
@@ -157,6 +158,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 // LayerNorm(eps 1e-5) + GELU of this thread's quarter row: 64 fp32 accumulators (TMEM lane = row, columns part*64..),
 // bias already added by the tensor cores, kept in registers; the four threads of a row exchange (sum, sum of squares)
 // through `part`.  Result as fp16 into the A-operand columns.  ln: float2 {gamma, beta} per feature in smem (broadcast reads).
+template <bool kDebug>
 __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id, int row, const float2* __restrict__ ln, float2* part,
                                                  float* dbg_row) {
   uint32_t xr[kColsPerThread];
@@ -170,7 +172,7 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
 #pragma unroll
   for (int i = 0; i < kColsPerThread; ++i) {
     const float xv = __uint_as_float(xr[i]);
-    if (dbg_row) dbg_row[part_id * kColsPerThread + i] = xv;
+    if (kDebug && dbg_row) dbg_row[part_id * kColsPerThread + i] = xv;
     sum += xv;
     sumsq = fmaf(xv, xv, sumsq);
   }
@@ -192,9 +194,9 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int j = c * 32 + 2 * i;
-      const float2 p0 = ln[part_id * kColsPerThread + j], p1 = ln[part_id * kColsPerThread + j + 1];
-      const float y0 = fmaf(fmaf(__uint_as_float(xr[j]), rstd, shift), p0.x, p0.y);
-      const float y1 = fmaf(fmaf(__uint_as_float(xr[j + 1]), rstd, shift), p1.x, p1.y);
+      const float4 pp = *reinterpret_cast<const float4*>(ln + part_id * kColsPerThread + j);   // {gamma_j, beta_j, gamma_j+1, beta_j+1}
+      const float y0 = fmaf(fmaf(__uint_as_float(xr[j]), rstd, shift), pp.x, pp.y);
+      const float y1 = fmaf(fmaf(__uint_as_float(xr[j + 1]), rstd, shift), pp.z, pp.w);
       const __half2 h = __floats2half2_rn(gelu_tc(y0), gelu_tc(y1));
       pk[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
@@ -213,6 +215,7 @@ struct TcArgs {
   float* dbg_d2;            // optional [128][256] raw layer-2 accumulators of tile 0
 };
 
+template <bool kDebug>
 __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
   constexpr int kMmaWarp = kEpiThreads / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
         xr0 = __ldg(xsrc + tid);
         if (tid + kEpiThreads < x_items) xr1 = __ldg(xsrc + tid + kEpiThreads);
       }
-      epilogue_ln_gelu(tmem_row, part_id, row_in_tile, ln1, part1, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr);
+      epilogue_ln_gelu<kDebug>(tmem_row, part_id, row_in_tile, ln1, part1, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr);
       tc_fence_before();
       mbar_arrive(bar_a2);
       if (next < ntiles) {
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
       // ---- layer 2
       mbar_wait(bar_d2, parity);
       tc_fence_after();
-      epilogue_ln_gelu(tmem_row, part_id, row_in_tile, ln2, part2, (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr);
+      epilogue_ln_gelu<kDebug>(tmem_row, part_id, row_in_tile, ln2, part2, (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr);
       tc_fence_before();
       mbar_arrive(bar_a3);
       // ---- layer 3: raw net outputs (the CFR backward kernel multiplies by the opponent-reach scaler)

@@ -40,13 +40,13 @@ def main():
         d1, d2 = S.net_taps()
         n = min(128, q.shape[0])
         W1, W2, W3 = h16(sd["body.0.weight"]), h16(sd["body.4.weight"]), h16(sd["output.weight"])
-        e1 = q[:n] @ W1.T
+        e1 = q[:n] @ W1.T + h16(sd["body.0.bias"])          # bias 1 rides on the tensor cores (constant-1 query column)
         print(f"== {D}x{F}f rows={q.shape[0]} Q={Q}")
         print("  layer1 acc: max|d1-exp| =", np.abs(d1[:n] - e1).max(), " scale", np.abs(e1).max())
-        a2 = h16(gelu(ln(d1[:n] + sd["body.0.bias"], sd["body.1.weight"], sd["body.1.bias"])))
-        e2 = a2 @ W2.T
+        a2 = h16(gelu(ln(d1[:n], sd["body.1.weight"], sd["body.1.bias"])))
+        e2 = a2 @ W2.T + h16(sd["body.4.bias"])
         print("  layer2 acc (teacher-forced from gpu d1): max|d2-exp| =", np.abs(d2[:n] - e2).max(), " scale", np.abs(e2).max())
-        a3 = h16(gelu(ln(d2[:n] + sd["body.4.bias"], sd["body.5.weight"], sd["body.5.bias"])))
+        a3 = h16(gelu(ln(d2[:n], sd["body.5.weight"], sd["body.5.bias"])))
         e3 = a3 @ W3.T + sd["output.bias"]
         print("  layer3 out (teacher-forced from gpu d2): max|out-exp| =", np.abs(o[:n] - e3).max(), " scale", np.abs(e3).max())
         with torch.no_grad():

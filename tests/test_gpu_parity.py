@@ -190,7 +190,7 @@ def test_teacher_forced_single_step(rb, port, net_weights, D, F, state_name, net
     S.close()
     _note(f"P2 {D}x{F}f d{max_depth} {state_name}/{net_name}: noise {noise:g}; compared {compared} (node,hand) rows, skipped "
           f"{skipped} ill-conditioned; worst abs diff " + " ".join(f"{k}={v:.2e}" for k, v in worst.items()))
-    if net != rb.NET_TC_F16:     # with fp16-operand noise most regrets of an untrained net's tiny values are near-ties
+    if noise < 1e-5:     # at fp16-operand / epsilon-deviation noise most regrets of an untrained net's tiny values are near-ties
         assert compared > skipped, (compared, skipped)
 
 
