@@ -65,26 +65,41 @@ __device__ __forceinline__ float query_value(const CfrDev<real>& p, int q, int l
 
 // Forward half of iteration `iter`: reach, query rows + scalers for pseudo-leaves, payoffs for terminals.
 template <typename real, int G, int HC>
-__device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0, real* reach1, real* lsum, real* hist, int lane) {
+__device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0, real* reach1, int have, real* lsum, real* hist, int lane) {
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int H = HC > 0 ? HC : p.H;      // compile-time hand count for the common shapes: item index -> (node, hand) without a division
   const int rp = p.sg_player[k];
   const real* __restrict__ Sg = p.Sg + (size_t)k * p.table_stride;
   const real* __restrict__ b = p.beliefs + (size_t)k * 2 * H;
   const int* __restrict__ parent = p.parent + t.node_off;
-  // ---- top-down reach of both players under Sg (compute_reach_probabilities, subgame_solving.cc:54-78)
-  for (int h = lane; h < H; h += G) { reach0[h] = b[h]; reach1[h] = b[H + h]; }
+  // ---- top-down reach under Sg (compute_reach_probabilities, subgame_solving.cc:54-78).  `have` = player whose reach is
+  // already in its buffer: the backward half that just ran left the traverser's reach under the new strategy there
+  // (same products, same order), so only the other player's table is rebuilt; -1 = build both.
+  for (int h = lane; h < H; h += G) {
+    if (have != 0) reach0[h] = b[h];
+    if (have != 1) reach1[h] = b[H + h];
+  }
   group_sync<G>();
   for (int d = 1; d < t.levels; ++d) {
     const int nb = p.level_begin[t.level_off + d], ne = p.level_begin[t.level_off + d + 1];
     const int actor = rp ^ ((d - 1) & 1);              // who moved into level d
-    for (int it = lane; it < (ne - nb) * H; it += G) {
-      const int c = nb + it / H, h = it % H;
-      const int par = parent[c];
-      const real s = Sg[(c - 1) * H + h];
-      const real a0 = reach0[par * H + h], a1 = reach1[par * H + h];
-      reach0[c * H + h] = actor == 0 ? a0 * s : a0;
-      reach1[c * H + h] = actor == 1 ? a1 * s : a1;
+    if (have < 0) {
+      for (int it = lane; it < (ne - nb) * H; it += G) {
+        const int c = nb + it / H, h = it % H;
+        const int par = parent[c];
+        const real s = Sg[(c - 1) * H + h];
+        const real a0 = reach0[par * H + h], a1 = reach1[par * H + h];
+        reach0[c * H + h] = actor == 0 ? a0 * s : a0;
+        reach1[c * H + h] = actor == 1 ? a1 * s : a1;
+      }
+    } else {
+      real* ro = have == 0 ? reach1 : reach0;          // the table to rebuild belongs to player 1 - have
+      const bool acts = actor != have;
+      for (int it = lane; it < (ne - nb) * H; it += G) {
+        const int c = nb + it / H, h = it % H;
+        const real a = ro[parent[c] * H + h];
+        ro[c * H + h] = acts ? a * Sg[(c - 1) * H + h] : a;
+      }
     }
     group_sync<G>();
   }
@@ -106,21 +121,40 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
   const int leaf_player = rp ^ ((t.levels - 1) & 1);
   const int Qp = p.Qpad;
   if (p.Xh != nullptr) {
-    // fp16 tile in UMMA K-major core-matrix order (leaf_mlp_tc.cuh umma_kmajor_offset_halves, R = 128):
-    // one lane produces the 8 contiguous halves of a (row, k-chunk) and stores them with a single 16-byte write
-    const int kc = Qp >> 3;
-    for (int it = lane; it < t.L * kc; it += G) {
-      const int k8 = it / t.L, r = it % t.L;    // consecutive lanes -> consecutive rows -> contiguous 16-byte chunks
+    // fp16 tile in UMMA K-major core-matrix order (leaf_mlp_tc.cuh umma_kmajor_offset_halves, R = 128).
+    // Stage 1: the 2H normalised beliefs of every pseudo-leaf as fp16 in scratch.  Stage 2: one lane per (row, 8-column
+    // chunk) takes the chunk of the template's constant row (one-hot last bid, the constant 1 of the bias column, zero
+    // padding), patches player / traverser and the belief columns in, and stores it with a single 16-byte write;
+    // consecutive lanes -> consecutive rows -> contiguous chunks.
+    __half* qb = reinterpret_cast<__half*>(hist + 10 * t.T);
+    const int H2 = 2 * H;
+    for (int it = lane; it < t.L * H2; it += G) {
+      const int r = it / H2, j = it % H2;
       const int n = p.pleaf_node[t.pleaf_off + r];
-      const int bid = p.last_bid[t.node_off + n];
-      const real s0 = lsum[2 * r], s1 = lsum[2 * r + 1];
-      __align__(16) __half hv[8];
+      const real x = j < H ? reach0[n * H + j] : reach1[n * H + j - H];
+      const real inv = lsum[2 * r + (j >= H)];
+      const float v = Eps<real>::kLiteral ? (float)((x + Eps<real>::v) * inv) : (isfinite(inv) ? (float)(x * inv) : 1.f / H);
+      qb[it] = __float2half_rn(v);
+    }
+    group_sync<G>();
+    const __half* __restrict__ qc = p.qconst + t.qconst_off;
+    const int kc = Qp >> 3, b_lo = 2 + p.A, b_hi = 2 + p.A + H2;
+    const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+    for (int it = lane; it < t.L * kc; it += G) {
+      const int k8 = it / t.L, r = it % t.L;
+      union { int4 v; __half h[8]; } c;
+      c.v = __ldg(reinterpret_cast<const int4*>(qc + (size_t)r * Qp + k8 * 8));
+      if (k8 == 0) { c.h[0] = leaf_player ? one : zero; c.h[1] = trav ? one : zero; }
+      const int q0 = k8 * 8;
+      if (q0 + 8 > b_lo && q0 < b_hi) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        hv[j] = __float2half_rn(query_value(p, k8 * 8 + j, leaf_player, trav, bid, reach0 + n * H, reach1 + n * H, s0, s1));
+        for (int j = 0; j < 8; ++j) {
+          const int q = q0 + j;
+          if (q >= b_lo && q < b_hi) c.h[j] = qb[r * H2 + q - b_lo];
+        }
+      }
       const int Rr = row0 + r, rr = Rr & 127;
-      *reinterpret_cast<int4*>(p.Xh + (size_t)(Rr >> 7) * 128 * Qp + k8 * 1024 + (rr >> 3) * 64 + (rr & 7) * 8) =
-          *reinterpret_cast<const int4*>(hv);
+      *reinterpret_cast<int4*>(p.Xh + (size_t)(Rr >> 7) * 128 * Qp + k8 * 1024 + (rr >> 3) * 64 + (rr & 7) * 8) = c.v;
     }
   } else if (p.X != nullptr) {
     for (int it = lane; it < t.L * Qp; it += G) {
@@ -308,8 +342,9 @@ __global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter,
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   real* base = (G == 32) ? smem + (size_t)gid * scratch_per_group : p.scratch + (size_t)k * p.scratch_stride;
   real* bufA = base; real* bufB = base + p.nh_max; real* tmp = base + 2 * p.nh_max; real* lsum = tmp + p.tmp_reals;
+  const int tb = (iter - 1) & 1;
   if (do_b) {
-    cfr_backward<real, G, HC>(p, k, (iter - 1) & 1, bufA, bufB, tmp, lane);
+    cfr_backward<real, G, HC>(p, k, tb, bufA, bufB, tmp, lane);   // leaves the reach of player tb (new strategy) in bufB
     group_sync<G>();
   }
   // sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
@@ -318,7 +353,10 @@ __global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter,
     real* __restrict__ Sn = p.Snap + (size_t)k * p.table_stride;
     for (int i = lane; i < (t.N - 1) * p.H; i += G) Sn[i] = Sg[i];
   }
-  if (do_f) cfr_forward<real, G, HC>(p, k, iter & 1, bufA, bufB, lsum, tmp, lane);
+  if (do_f) {
+    if (do_b) cfr_forward<real, G, HC>(p, k, iter & 1, tb == 0 ? bufB : bufA, tb == 0 ? bufA : bufB, tb, lsum, tmp, lane);
+    else      cfr_forward<real, G, HC>(p, k, iter & 1, bufA, bufB, -1, lsum, tmp, lane);
+  }
 }
 
 // Wave initialisation == CFR constructor (subgame_solving.cc:509-524): uniform last strategy, zero regrets,

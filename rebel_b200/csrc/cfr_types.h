@@ -9,6 +9,7 @@ namespace cfrb {
 struct TemplateDev {
   int node_off, level_off, pleaf_off, term_off;
   int N, L, T, levels;
+  int qconst_off, pad_[3];
 };
 
 template <typename real>
@@ -20,6 +21,7 @@ struct CfrDev {
   const int* parent; const int* child_begin; const int* nchild; const int* last_bid;
   const int* level_begin; const int* pleaf_node; const int* term_node;
   const unsigned char* matches;   // [H][F] num_matches(hand, face), liars_dice.h:83-91
+  const __half* qconst;           // per template [L][Qpad] fp16: constant part of the query rows (one-hot last bid, 1 at column Q)
   // wave
   const int* wave_n;              // [1] number of live subgames
   const int* sg_tmpl; const int* sg_player; const int* sg_row_off; const int* sg_act_iter;
@@ -42,8 +44,9 @@ struct CfrDev {
 
 // Scratch of a group (reals): bufA[N*H] | bufB[N*H] | tmp[max(N*H, 10*T)] | lsum[2*L]  (tmp doubles as the per-terminal
 // match-count histogram: 9 bins + belief sum per terminal)
-__host__ __device__ inline int cfr_tmp_reals(int N, int H, int T) { return N * H > 10 * T ? N * H : 10 * T; }
-__host__ __device__ inline int cfr_scratch_reals(int N, int H, int L, int T) { return 2 * N * H + cfr_tmp_reals(N, H, T) + 2 * (L > 0 ? L : 1); }
+// and as the fp16 staging of the normalised leaf beliefs (L * 2H halves <= L * H reals)
+__host__ __device__ inline int cfr_tmp_reals(int N, int H, int L, int T) { const int a = N * H, b = 10 * T + L * H; return a > b ? a : b; }
+__host__ __device__ inline int cfr_scratch_reals(int N, int H, int L, int T) { return 2 * N * H + cfr_tmp_reals(N, H, L, T) + 2 * (L > 0 ? L : 1); }
 
 // Launchers implemented in cfr_kernels.cu (explicitly instantiated for float and double).  `group` is 32 (one warp per
 // subgame, shared-memory scratch) or 256 (one CTA per subgame, global scratch).

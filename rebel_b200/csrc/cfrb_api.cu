@@ -81,6 +81,7 @@ struct cfrb_handle {
   DevBuf<cfrb::TemplateDev> d_tmpl;
   DevBuf<int> d_parent, d_child_begin, d_nchild, d_last_bid, d_level_begin, d_pleaf_node, d_term_node;
   DevBuf<unsigned char> d_matches;
+  DevBuf<__half> d_qconst;
   // device: wave (untyped part)
   DevBuf<int> d_wave;      // [0] = n, [1] = rows
   DevBuf<int> d_sg_tmpl, d_sg_player, d_sg_row_off, d_sg_act, d_steps;
@@ -138,7 +139,7 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   d.A = g.A; d.H = g.H; d.F = g.F; d.Q = g.Q; d.Qpad = h->Qpad; d.Hout = h->Hout;
   d.tmpl = h->d_tmpl.p; d.parent = h->d_parent.p; d.child_begin = h->d_child_begin.p; d.nchild = h->d_nchild.p;
   d.last_bid = h->d_last_bid.p; d.level_begin = h->d_level_begin.p; d.pleaf_node = h->d_pleaf_node.p;
-  d.term_node = h->d_term_node.p; d.matches = h->d_matches.p;
+  d.term_node = h->d_term_node.p; d.matches = h->d_matches.p; d.qconst = h->d_qconst.p;
   d.wave_n = h->d_wave.p; d.sg_tmpl = h->d_sg_tmpl.p; d.sg_player = h->d_sg_player.p; d.sg_row_off = h->d_sg_row_off.p;
   d.sg_act_iter = h->d_sg_act.p; d.beliefs = s.beliefs.p; d.mu = s.mu.p; d.steps = h->d_steps.p;
   d.R = s.R.p; d.Sg = s.Sg.p; d.S = s.S.p; d.Snap = s.Snap.p; d.table_stride = h->table_stride;
@@ -147,7 +148,7 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   d.Xh = h->cfg.net_mode == CFRB_NET_TC_F16 ? h->d_Xh.p : nullptr;
   d.net_out = h->d_out.p; d.scaler = s.scaler.p;
   d.scratch = h->group == 32 ? nullptr : s.scratch.p; d.scratch_stride = h->scratch_per_group;
-  d.nh_max = h->Nmax * g.H; d.tmp_reals = cfrb::cfr_tmp_reals(h->Nmax, g.H, h->Tmax);
+  d.nh_max = h->Nmax * g.H; d.tmp_reals = cfrb::cfr_tmp_reals(h->Nmax, g.H, h->Lmax, h->Tmax);
   d.linear = h->cfg.linear_update; d.dcfr = h->cfg.dcfr;
   d.dcfr_alpha = (real)h->cfg.dcfr_alpha; d.dcfr_beta = (real)h->cfg.dcfr_beta; d.dcfr_gamma = (real)h->cfg.dcfr_gamma;
   d.use_net = h->cfg.net_mode != CFRB_NET_ZERO;
@@ -328,7 +329,7 @@ int cfrb_destroy(cfrb_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   h->d_tmpl.release(); h->d_parent.release(); h->d_child_begin.release(); h->d_nchild.release(); h->d_last_bid.release();
-  h->d_level_begin.release(); h->d_pleaf_node.release(); h->d_term_node.release(); h->d_matches.release();
+  h->d_level_begin.release(); h->d_pleaf_node.release(); h->d_term_node.release(); h->d_matches.release(); h->d_qconst.release();
   h->d_wave.release(); h->d_sg_tmpl.release(); h->d_sg_player.release(); h->d_sg_row_off.release(); h->d_sg_act.release();
   h->d_steps.release(); h->d_X.release(); h->d_out.release(); h->d_dbg.release(); h->d_Xh.release();
   h->sf.release(); h->sd.release(); h->d_w.release(); h->d_blob.release();
@@ -361,6 +362,8 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   // ---- templates: root_bid in {-1, 0 .. A-2}
   std::vector<TemplateDev> td;
   std::vector<int> parent, child_begin, nchild, last_bid, level_begin, pleaf_node, term_node;
+  std::vector<__half> qconst;
+  const int Qpad = round_up(g.Q + 1, 16);
   for (int rb = -1; rb <= g.A - 2; ++rb) {
     h->tmpl.push_back(cfrb::build_template(g, rb, cfg->max_depth));
     const auto& t = h->tmpl.back();
@@ -368,6 +371,10 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     d.node_off = (int)child_begin.size(); d.level_off = (int)level_begin.size();
     d.pleaf_off = (int)pleaf_node.size(); d.term_off = (int)term_node.size();
     d.N = t.N; d.L = t.L; d.T = t.T; d.levels = t.levels;
+    d.qconst_off = (int)qconst.size();
+    for (int n : t.pleaf_node)
+      for (int q = 0; q < Qpad; ++q)   // one-hot of the leaf's last bid (subgame_solving.cc:111-113) and the constant 1 at column Q
+        qconst.push_back(__float2half_rn((q >= 2 && q < 2 + g.A && q - 2 == t.last_bid[n]) || q == g.Q ? 1.f : 0.f));
     td.push_back(d);
     parent.insert(parent.end(), t.parent.begin(), t.parent.end());
     child_begin.insert(child_begin.end(), t.child_begin.begin(), t.child_begin.end());
@@ -392,7 +399,7 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   };
   CK(up(h->d_tmpl, td)); CK(up(h->d_parent, parent)); CK(up(h->d_child_begin, child_begin)); CK(up(h->d_nchild, nchild));
   CK(up(h->d_last_bid, last_bid)); CK(up(h->d_level_begin, level_begin)); CK(up(h->d_pleaf_node, pleaf_node));
-  CK(up(h->d_term_node, term_node)); CK(up(h->d_matches, matches));
+  CK(up(h->d_term_node, term_node)); CK(up(h->d_matches, matches)); CK(up(h->d_qconst, qconst));
 
   // ---- sizes
   const int K = cfg->max_subgames;
