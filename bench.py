@@ -277,7 +277,7 @@ def run_b200(args):
     S.begin(t_lb.numpy(), t_pl.numpy(), t_b.numpy(), t_act.numpy())
     for _ in range(args.warmup):
         S.reset(stream); S.run(iters, stream)
-    S.set_profiling(True)
+    S.set_profiling(16)                     # CUDA-event pairs around every 16th value-net launch of the timed steps
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -334,7 +334,8 @@ def run_b200(args):
     achieved = flops_launch / (avg_net_ms * 1e-3) / 1e12 if avg_net_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "leaf value net (Net2 forward over all pseudo-leaf rows of the wave)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["src"], "avg_launch_ms": avg_net_ms, "rows_per_launch": rows,
+                "traffic": None, "peak_source": peaks["src"], "avg_launch_ms": avg_net_ms, "launch_timing": "CUDA events around every 16th launch inside the timed steps",
+                "rows_per_launch": rows,
                 "flops_per_launch": flops_launch, "share_of_step": net_ms / ms if ms > 0 else None,
                 "cfr_tables_algorithmic_GBps": (4 * H * (90 + 6 * 45) + 4 * 66 * (Q + H) + 8 * H) * K * iters * args.steps / max(ms - net_ms, 1e-9) / 1e6
                 if (D, F) == (1, 6) else None}

@@ -132,8 +132,9 @@ int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const in
  * host->device traffic): what constructing fresh CFR solvers for the same subgames would do. */
 int cfrb_reset_wave(cfrb_handle* h, void* cuda_stream);
 
-/* Profiling switch: when on, cfrb_run brackets every value-net launch with CUDA events on the launching stream
- * so that cfrb_last_run_ms can report the summed device time of the value-net kernels of the last run. */
+/* Profiling switch: 0 = off; n > 0 = cfrb_run brackets every n-th value-net launch with a pair of CUDA events on the
+ * launching stream, and cfrb_last_run_ms reports the value-net kernel time of the last run estimated from those samples
+ * (mean sampled duration x number of launches).  Sampling keeps the event traffic out of the way of the measurement. */
 int cfrb_set_profiling(cfrb_handle* h, int32_t on);
 
 /* Advance every subgame of the wave by `iters` CFR iterations (iteration i has traverser i % 2,

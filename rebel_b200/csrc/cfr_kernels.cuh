@@ -121,38 +121,19 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
   const int leaf_player = rp ^ ((t.levels - 1) & 1);
   const int Qp = p.Qpad;
   if (p.Xh != nullptr) {
-    // fp16 tile in UMMA K-major core-matrix order (leaf_mlp_tc.cuh umma_kmajor_offset_halves, R = 128).
-    // Stage 1: the 2H normalised beliefs of every pseudo-leaf as fp16 in scratch.  Stage 2: one lane per (row, 8-column
-    // chunk) takes the chunk of the template's constant row (one-hot last bid, the constant 1 of the bias column, zero
-    // padding), patches player / traverser and the belief columns in, and stores it with a single 16-byte write;
-    // consecutive lanes -> consecutive rows -> contiguous chunks.
-    __half* qb = reinterpret_cast<__half*>(hist + 10 * t.T);
-    const int H2 = 2 * H;
-    for (int it = lane; it < t.L * H2; it += G) {
-      const int r = it / H2, j = it % H2;
-      const int n = p.pleaf_node[t.pleaf_off + r];
-      const real x = j < H ? reach0[n * H + j] : reach1[n * H + j - H];
-      const real inv = lsum[2 * r + (j >= H)];
-      const float v = Eps<real>::kLiteral ? (float)((x + Eps<real>::v) * inv) : (isfinite(inv) ? (float)(x * inv) : 1.f / H);
-      qb[it] = __float2half_rn(v);
-    }
-    group_sync<G>();
-    const __half* __restrict__ qc = p.qconst + t.qconst_off;
-    const int kc = Qp >> 3, b_lo = 2 + p.A, b_hi = 2 + p.A + H2;
-    const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+    // fp16 tile in UMMA K-major core-matrix order (leaf_mlp_tc.cuh umma_kmajor_offset_halves, R = 128): one lane produces
+    // the 8 contiguous halves of a (row, k-chunk) and stores them with a single 16-byte write; consecutive lanes ->
+    // consecutive rows -> contiguous chunks
+    const int kc = Qp >> 3;
     for (int it = lane; it < t.L * kc; it += G) {
       const int k8 = it / t.L, r = it % t.L;
+      const int n = p.pleaf_node[t.pleaf_off + r];
+      const int bid = p.last_bid[t.node_off + n];
+      const real s0 = lsum[2 * r], s1 = lsum[2 * r + 1];
       union { int4 v; __half h[8]; } c;
-      c.v = __ldg(reinterpret_cast<const int4*>(qc + (size_t)r * Qp + k8 * 8));
-      if (k8 == 0) { c.h[0] = leaf_player ? one : zero; c.h[1] = trav ? one : zero; }
-      const int q0 = k8 * 8;
-      if (q0 + 8 > b_lo && q0 < b_hi) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int q = q0 + j;
-          if (q >= b_lo && q < b_hi) c.h[j] = qb[r * H2 + q - b_lo];
-        }
-      }
+      for (int j = 0; j < 8; ++j)
+        c.h[j] = __float2half_rn(query_value(p, k8 * 8 + j, leaf_player, trav, bid, reach0 + n * H, reach1 + n * H, s0, s1));
       const int Rr = row0 + r, rr = Rr & 127;
       *reinterpret_cast<int4*>(p.Xh + (size_t)(Rr >> 7) * 128 * Qp + k8 * 1024 + (rr >> 3) * 64 + (rr & 7) * 8) = c.v;
     }
@@ -211,7 +192,11 @@ __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0
 
 // Backward half of iteration with traverser `trav` (update_regrets :538-575 and step :577-664).
 template <typename real, int G, int HC>
-__device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, real* rt, real* tmp, int lane) {
+__device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, real* rt, int lane) {
+  // Scratch discipline (all indexed [node * H + hand]): `val` holds node values; once a traverser level is processed its
+  // children's slots are dead and take the new regrets R(parent, hand, action->child); later the slots of the traverser
+  // nodes themselves take the positive-regret sums.  `rt` is free during the bottom-up sweep and carries the value*sigma
+  // products there; in the top-down sweep it becomes the traverser's reach under the new strategy.
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int H = HC > 0 ? HC : p.H;
   const int rp = p.sg_player[k];
@@ -242,7 +227,7 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
     if (mine) {   // per-edge products value * sigma
       for (int it = lane; it < (ce - cb) * H; it += G) {
         const int c = cb + it / H, h = it % H;
-        tmp[(c - 1) * H + h] = val[c * H + h] * Sg[(c - 1) * H + h];
+        rt[c * H + h] = val[c * H + h] * Sg[(c - 1) * H + h];
       }
       group_sync<G>();
     }
@@ -252,16 +237,15 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
       if (!nc) continue;
       const int c0 = child_begin[n];
       real v = 0;
-      if (mine) { for (int j = 0; j < nc; ++j) v += tmp[(c0 + j - 1) * H + h]; }
+      if (mine) { for (int j = 0; j < nc; ++j) v += rt[(c0 + j) * H + h]; }
       else      { for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h]; }
       val[n * H + h] = v;
     }
     group_sync<G>();
-    if (mine) {   // regrets += action value - node value (kept in tmp; written back once, discounted, below)
+    if (mine) {   // regrets += action value - node value (kept in the child's slot; written back once, discounted, below)
       for (int it = lane; it < (ce - cb) * H; it += G) {
         const int c = cb + it / H, h = it % H;
-        const int e = (c - 1) * H + h;
-        tmp[e] = (R[e] + val[c * H + h]) - val[parent[c] * H + h];
+        val[c * H + h] = (R[(c - 1) * H + h] + val[c * H + h]) - val[parent[c] * H + h];
       }
       group_sync<G>();
     }
@@ -302,7 +286,7 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
         const int c0 = child_begin[n];
         real sum = 0;
         for (int j = 0; j < nc; ++j) {
-          const real r = tmp[(c0 + j - 1) * H + h];
+          const real r = val[(c0 + j) * H + h];
           sum += Eps<real>::kLiteral ? (r > Eps<real>::v ? r : Eps<real>::v) : rmax0(r);   // max(R, 1e-80) (:626-629)
         }
         val[n * H + h] = sum;
@@ -311,7 +295,7 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
       for (int it = lane; it < (ce - cb) * H; it += G) {
         const int c = cb + it / H, h = it % H;
         const int e = (c - 1) * H + h, par = parent[c];
-        const real r = tmp[e], sum = val[par * H + h], rn = rt[par * H + h];
+        const real r = val[c * H + h], sum = val[par * H + h], rn = rt[par * H + h];
         const real sg = Eps<real>::kLiteral ? (r > Eps<real>::v ? r : Eps<real>::v) / sum
                                             : (sum > 0 ? rmax0(r) / sum : (real)1 / nchild[par]);
         Sg[e] = sg;
@@ -332,7 +316,7 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
 
 // iter: global iteration index of the forward half.  do_b: run backward half of iteration iter-1 first.
 template <typename real, int G, int HC>
-__global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
+__global__ void __launch_bounds__(512) cfr_iter_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   const int groups_per_cta = blockDim.x / G;
@@ -344,7 +328,7 @@ __global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter,
   real* bufA = base; real* bufB = base + p.nh_max; real* tmp = base + 2 * p.nh_max; real* lsum = tmp + p.tmp_reals;
   const int tb = (iter - 1) & 1;
   if (do_b) {
-    cfr_backward<real, G, HC>(p, k, tb, bufA, bufB, tmp, lane);   // leaves the reach of player tb (new strategy) in bufB
+    cfr_backward<real, G, HC>(p, k, tb, bufA, bufB, lane);   // leaves the reach of player tb (new strategy) in bufB
     group_sync<G>();
   }
   // sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
@@ -362,7 +346,7 @@ __global__ void __launch_bounds__(256) cfr_iter_kernel(CfrDev<real> p, int iter,
 // Wave initialisation == CFR constructor (subgame_solving.cc:509-524): uniform last strategy, zero regrets,
 // sum = uniform * reach-under-uniform of the acting player (get_uniform_reach_weigted_strategy :125-149).
 template <typename real, int G>
-__global__ void __launch_bounds__(256) cfr_init_kernel(CfrDev<real> p, int scratch_per_group) {
+__global__ void __launch_bounds__(512) cfr_init_kernel(CfrDev<real> p, int scratch_per_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   const int groups_per_cta = blockDim.x / G;

@@ -42,10 +42,9 @@ struct CfrDev {
   int use_net;
 };
 
-// Scratch of a group (reals): bufA[N*H] | bufB[N*H] | tmp[max(N*H, 10*T)] | lsum[2*L]  (tmp doubles as the per-terminal
-// match-count histogram: 9 bins + belief sum per terminal)
-// and as the fp16 staging of the normalised leaf beliefs (L * 2H halves <= L * H reals)
-__host__ __device__ inline int cfr_tmp_reals(int N, int H, int L, int T) { const int a = N * H, b = 10 * T + L * H; return a > b ? a : b; }
+// Scratch of a group (reals): bufA[N*H] | bufB[N*H] | hist[10*T] | lsum[2*L]  (hist: per-terminal match-count histogram,
+// 9 bins + belief sum)
+__host__ __device__ inline int cfr_tmp_reals(int N, int H, int L, int T) { (void)N; (void)H; (void)L; return 10 * (T > 0 ? T : 1); }
 __host__ __device__ inline int cfr_scratch_reals(int N, int H, int L, int T) { return 2 * N * H + cfr_tmp_reals(N, H, L, T) + 2 * (L > 0 ? L : 1); }
 
 // Launchers implemented in cfr_kernels.cu (explicitly instantiated for float and double).  `group` is 32 (one warp per

@@ -74,7 +74,8 @@ struct cfrb_handle {
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-  bool profiling = false;
+  int profiling = 0;          // 0 off, n: bracket every n-th value-net launch with CUDA events
+  int net_launch_idx = 0, net_launches_run = 0;
   std::vector<cudaEvent_t> net_ev;   // pairs around value-net launches (profiling mode)
   int net_ev_used = 0;
   // device: templates
@@ -126,8 +127,10 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   const size_t per_group_bytes = (size_t)h->scratch_per_group * sizeof(real);
   if (per_group_bytes * 2 <= (size_t)max_optin) {
     h->group = 32;
-    // as many warps per CTA as keep >= 2 CTAs per SM within the shared-memory budget
-    h->groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_optin / 2 / per_group_bytes));
+    // 2 CTAs per SM, as many warps per CTA as fit in ~85 % of the shared memory (the rest stays L1 for the read-only
+    // template arrays), capped by the register file (64 registers x 32 warps) and the 512-thread block
+    const size_t budget = (size_t)max_optin * 85 / 100 / 2;
+    h->groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(16, budget / per_group_bytes));
     const int smem_bytes = (int)(per_group_bytes * h->groups_per_cta);
     CK(cfrb::cfr_configure<real>(32, smem_bytes));
   } else {
@@ -597,7 +600,9 @@ int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const in
 
 static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2) {
   if (h->cfg.net_mode == CFRB_NET_ZERO || h->rows == 0) return CFRB_OK;
-  if (h->profiling) {
+  const bool sample = h->profiling > 0 && (h->net_launch_idx % h->profiling) == 0;
+  ++h->net_launch_idx;
+  if (sample) {
     while ((int)h->net_ev.size() < h->net_ev_used + 2) {
       cudaEvent_t e;
       CK(cudaEventCreate(&e));
@@ -617,7 +622,7 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
   }
   ++h->launches;
   CK(cudaGetLastError());
-  if (h->profiling) {
+  if (sample) {
     CK(cudaEventRecord(h->net_ev[h->net_ev_used + 1], st));
     h->net_ev_used += 2;
   }
@@ -634,7 +639,7 @@ int cfrb_reset_wave(cfrb_handle* h, void* cuda_stream) {
 
 int cfrb_set_profiling(cfrb_handle* h, int32_t on) {
   if (!h) return fail(CFRB_EINVAL, "null handle");
-  h->profiling = on != 0;
+  h->profiling = on < 0 ? 0 : on;
   return CFRB_OK;
 }
 
@@ -647,6 +652,7 @@ int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream) {
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
   CK(cudaEventRecord(h->ev_a, st));
   h->net_ev_used = 0;
+  h->net_launch_idx = 0;
   const int first = h->iters_done, last = first + iters;
   for (int i = first; i <= last; ++i) {
     const int do_b = i > first, do_f = i < last;
@@ -655,6 +661,7 @@ int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream) {
     if (do_f) { rc = launch_net(h, st, nullptr, nullptr); if (rc) return rc; }
   }
   CK(cudaEventRecord(h->ev_b, st));
+  h->net_launches_run = h->net_launch_idx;
   h->iters_done = last;
   return CFRB_OK;
 }
@@ -761,8 +768,8 @@ int cfrb_debug_net_taps(cfrb_handle* h, float* d1, float* d2) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
   const size_t n = (size_t)cfrb::tc::kTileM * cfrb::tc::kHid;
-  const bool prof = h->profiling;
-  h->profiling = false;
+  const int prof = h->profiling;
+  h->profiling = 0;
   int rc = launch_net(h, h->own_stream, h->d_dbg.p, h->d_dbg.p + n);
   h->profiling = prof;
   if (rc) return rc;
@@ -793,6 +800,8 @@ int cfrb_last_run_ms(cfrb_handle* h, float* total_ms, float* net_ms) {
     CK(cudaEventElapsedTime(&t, h->net_ev[i], h->net_ev[i + 1]));
     net += t;
   }
+  // sampled launches -> estimate for all value-net launches of the run
+  if (h->net_ev_used > 0) net = net / (h->net_ev_used / 2) * h->net_launches_run;
   h->last_net_ms = net;
   if (total_ms) *total_ms = ms;
   if (net_ms) *net_ms = net;
