@@ -334,10 +334,17 @@ def run_b200(args):
     n_net = args.steps * iters
     flops_launch = 2.0 * rows * (256 * Q + 256 * 256 + 256 * H)
     avg_net_ms = net_ms / max(n_net, 1)
+    traffic = None   # DRAM bytes per launch of the value-net kernel from the committed ncu --set full capture (same workload only)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if mode == rb.NET_TC_F16 and (D, F, K) == (1, 6, 8192):
+            traffic = [v["dram_bytes_per_launch"] for k, v in tj.items() if "leaf_mlp_tc_kernel" in k][0]
+    except Exception:
+        traffic = None
     achieved = flops_launch / (avg_net_ms * 1e-3) / 1e12 if avg_net_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "leaf value net (Net2 forward over all pseudo-leaf rows of the wave)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["src"], "avg_launch_ms": avg_net_ms, "launch_timing": "CUDA events around every 16th launch inside the timed steps",
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "peak_source": peaks["src"], "avg_launch_ms": avg_net_ms, "launch_timing": "CUDA events around every 16th launch inside the timed steps",
                 "rows_per_launch": rows,
                 "flops_per_launch": flops_launch, "share_of_step": net_ms / ms if ms > 0 else None,
                 "cfr_tables_algorithmic_GBps": (4 * H * (90 + 6 * 45) + 4 * 66 * (Q + H) + 8 * H) * K * iters * args.steps / max(ms - net_ms, 1e-9) / 1e6

@@ -51,6 +51,14 @@ if os.path.exists(rep):
             if m in hdr:
                 i = hdr.index(m)
                 w.writerow([m, units[i]] + [r[i] for r in rows[2:]])
+    traffic = {}
+    for r in rows[2:]:
+        rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+        traffic["cfr_iter_kernel" if "cfr_iter_kernel" in r[hdr.index("Kernel Name")] else "leaf_mlp_tc_kernel" if "leaf_mlp_tc" in r[hdr.index("Kernel Name")] else r[hdr.index("Kernel Name")][:40]] = {
+            "dram_bytes_per_launch": float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]],
+            "workload": "1x6f K=8192 root subgames", "source": f"profiles/{tag}_ncu_full_extract.csv (ncu --set full, one launch)"}
+    json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     for r in rows[2:]:
         out.append(f"### `{r[hdr.index('Kernel Name')][:90]}`\n")
         out.append("| metric | value |\n|---|---|")
