@@ -24,6 +24,33 @@ def weights(D, F):
     return flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict())
 
 
+def recursive_eval_reference(lib, D, F, num_iters, num_repeats, net_w=None, keep=2):
+    """The accumulation loop of the reference's recursive_eval main (recursive_eval.cc:343-369) around its own
+    compute_sampled_strategy_recursive_to_leaf and compute_stategy_stats, float32 tensors emulated with numpy."""
+    tree = lib.unroll_tree(D, F)
+    player = tree[:, 1]   # columns: last_bid, player_id, children_begin, children_end, parent, depth
+    ss = sr = None
+    expl, cps, first = [], [], []
+    for sid in range(num_repeats):
+        s = lib.sampled_strategy(D, F, seed=sid, num_iters=num_iters, net_w=net_w)
+        reach = lib.strategy_reach(D, F, s)
+        w = reach[player, np.arange(len(player))].astype(np.float32)[:, :, None]
+        st = s.astype(np.float32)
+        if sid < keep:
+            first.append(s)
+        if sid == 0:
+            ss, sr = st * w, w.copy()
+        else:
+            ss += st * w
+            sr += w
+        if ((sid + 1) & sid) == 0 or sid + 1 == num_repeats:
+            final = ss / (sr + np.float32(1e-6))
+            cps.append(sid + 1)
+            expl.append(lib.exploitability(D, F, final.astype(np.float64)))
+    return {"summed_strategy": ss, "summed_reach": sr, "final_strategy": ss / (sr + np.float32(1e-6)),
+            "checkpoints": np.array(cps), "exploitability": np.stack(expl), "first_strategies": np.stack(first)}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = Oracle("ref_nofma")
@@ -93,6 +120,17 @@ def main():
             out[f"q_{D}x{F}_{sl}"] = q
             out[f"v_{D}x{F}_{sl}"] = v
     np.savez_compressed(os.path.join(OUT, "selfplay_zero.npz"), **out)
+
+    # ---- recursive evaluation (recursive_eval.cc:117-191,343-369) with the zero net: sampled recursive strategies of
+    # seeds 0..R-1, their float32 reach-weighted sums in strategy_id order, and the exploitability at powers of two
+    out = {}
+    for (D, F, iters, reps) in [(1, 4, 64, 8), (1, 6, 32, 4), (2, 3, 32, 2)]:
+        r = recursive_eval_reference(R, D, F, iters, reps)
+        for k, v in r.items():
+            if k in ("summed_strategy", "summed_reach", "checkpoints", "exploitability") or (k == "first_strategies" and (D, F) == (1, 4)):
+                out[f"{k}_{D}x{F}"] = v
+        out[f"cfg_{D}x{F}"] = np.array([iters, reps])
+    np.savez_compressed(os.path.join(OUT, "recursive_eval_zero.npz"), **out)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -155,6 +155,30 @@ class Oracle:
         assert 0 <= n <= cap, n
         return q[:n].copy(), v[:n].copy()
 
+    def sampled_strategy(self, D, F, seed, num_iters=1024, max_depth=2, linear_update=True, net_w=None, hidden=256):
+        """compute_sampled_strategy_recursive_to_leaf (reference builds only): dense [N_full, H, A]."""
+        assert self.kind != "port"
+        A, H, Q = game_dims(D, F)
+        N = len(self.unroll_tree(D, F))
+        out = np.zeros((N, H, A), np.float64)
+        w = None if net_w is None else np.ascontiguousarray(net_w, np.float32)
+        f = self._f("sampled_strategy")
+        f.argtypes = [C.c_int] * 6 + [_fp, C.c_int, _dp]
+        n = f(D, F, num_iters, max_depth, int(linear_update), seed, _ptr(w, _fp), hidden, _ptr(out, _dp))
+        if n < 0:
+            raise RuntimeError(self._f("last_error")().decode())
+        assert n == N
+        return out
+
+    def strategy_reach(self, D, F, strategy):
+        assert self.kind != "port"
+        A, H, Q = game_dims(D, F)
+        s = np.ascontiguousarray(strategy, np.float64)
+        out = np.zeros((2, s.shape[0], H), np.float64)
+        n = self._f("strategy_reach")(int(D), int(F), _ptr(s, _dp), _ptr(out, _dp))
+        assert n == s.shape[0]
+        return out
+
     def net2_forward(self, w, Q, hidden, H, queries):
         assert self.kind == "port"
         w = np.ascontiguousarray(w, np.float32)

@@ -333,6 +333,54 @@ int ref_rl_runner(int D, int F, int num_iters, int max_depth, int linear_update,
   }
 }
 
+// One sampled recursive strategy (BASELINE config 5 unit): compute_sampled_strategy_recursive_to_leaf
+// (recursive_solving.cc:301-327).  net_w == nullptr -> zero net.  strategy_out: dense [N_full][H][A] doubles.
+// Also returns, per full-tree node that roots a subgame, the sampled act_iteration (-1 elsewhere) by re-running the
+// same mt19937 stream in the same recursion order (stats for the GPU driver's tests).
+int ref_sampled_strategy(int D, int F, int num_iters, int max_depth, int linear_update, int seed, const float* net_w,
+                         int hidden, double* strategy_out) {
+  try {
+    Game game(D, F);
+    const int H = game.num_hands(), A = game.num_actions();
+    auto params = make_params(num_iters, max_depth, linear_update, 0, 0, 0, 0);
+    std::shared_ptr<IValueNet> net;
+    if (net_w) net = std::make_shared<FlatNet2>(net_w, 2 + A + 2 * H, hidden, H);
+    else net = create_zero_net(H, false);
+    auto strategy = compute_sampled_strategy_recursive_to_leaf(game, params, net, seed);
+    size_t k = 0;
+    for (auto& n : strategy) {
+      if (n.empty()) { k += (size_t)H * A; continue; }   // terminal nodes keep an empty entry
+      for (auto& h : n)
+        for (double v : h) strategy_out[k++] = v;
+    }
+    return (int)strategy.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// compute_stategy_stats reach weights (subgame_solving.cc:823-899): reach_probabilities[p][node][hand], dense [2][N][H].
+int ref_strategy_reach(int D, int F, const double* strategy, double* reach_out) {
+  try {
+    Game game(D, F);
+    auto tree = unroll_tree(game);
+    TreeStrategy s;
+    init_nd(tree.size(), game.num_hands(), game.num_actions(), 0.0, &s);
+    size_t k = 0;
+    for (auto& n : s) for (auto& h : n) for (double& v : h) v = strategy[k++];
+    auto stats = compute_stategy_stats(game, s);
+    k = 0;
+    for (int p = 0; p < 2; ++p)
+      for (auto& n : stats.reach_probabilities[p])
+        for (double v : n) reach_out[k++] = v;
+    return (int)tree.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // Synthetic bench/parity inputs, shared definition with rebel_b200:
 // beliefs b_p[h] = u/sum(u), u ~ U(0,1) drawn from mt19937(seed) via
 // uniform_real_distribution<double>, player 0 first.

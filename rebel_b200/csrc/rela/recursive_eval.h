@@ -1,0 +1,297 @@
+// RecursiveEvaluator — BASELINE config 5: the reference's `recursive_eval --cfr --num_repeats R` (recursive_eval.cc:117-191,
+// 331-363), i.e. R sampled recursive strategies (compute_sampled_strategy_recursive_to_leaf, recursive_solving.cc:301-327 with
+// compute_strategy_recursive_to_leaf :76-134), their reach-weighted float32 average, and its exploitability
+// (compute_exploitability2, subgame_solving.cc:802-816).
+//
+// The reference solves the 2^(A-2) subgames of ONE repeat depth-first on one CPU thread.  Here the subgames of MANY repeats
+// are solved level by level (a subgame's root beliefs only depend on its ancestors' sampled strategies), thousands per wave
+// through the C ABI.  Everything that fixes the numbers is kept: the per-repeat mt19937(seed = strategy_id) stream is consumed
+// in the reference's recursion order (which depends only on the tree), a subgame solved for `act_iteration` iterations is the
+// snapshot of the lock-step wave at that iteration, beliefs are propagated unnormalised inside a subgame and eps-normalised at
+// its leaves, and the accumulation `sum += float(strategy) * float(reach)` runs in strategy_id order per node.
+#pragma once
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <deque>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../../include/cfrb200.h"
+#include "params.h"
+
+namespace rela {
+
+// Best response of both players against `strategy` (dense [N][H][A], fp64) on the full tree from uniform beliefs:
+// BRSolver::compute_br + compute_exploitability2 (subgame_solving.cc:316-358, 802-816).
+inline std::array<double, 2> best_response_values(int D, int F, const std::vector<cfrb_node>& tree, const std::vector<double>& strategy) {
+  const int A = 1 + 2 * D * F;
+  int H = 1;
+  for (int i = 0; i < D; ++i) H *= F;
+  const int N = (int)tree.size();
+  auto matches = [&](int hand, int face) { int m = 0; for (int i = 0; i < D; ++i) { int d = hand % F; m += (d == face || d == F - 1); hand /= F; } return m; };
+  std::array<double, 2> out{};
+  std::vector<double> reach((size_t)2 * N * H), val((size_t)N * H);
+  for (int p = 0; p < 2; ++p)   // compute_reach_probabilities (:54-78) from uniform beliefs
+    for (int n = 0; n < N; ++n)
+      for (int h = 0; h < H; ++h) {
+        double& r = reach[((size_t)p * N + n) * H + h];
+        if (n == 0) { r = 1.0 / H; continue; }
+        const int par = tree[n].parent;
+        const double rp = reach[((size_t)p * N + par) * H + h];
+        r = tree[par].player_id == p ? rp * strategy[((size_t)par * H + h) * A + tree[n].last_bid] : rp;
+      }
+  for (int trav = 0; trav < 2; ++trav) {
+    for (int n = N; n-- > 0;) {
+      const int nc = tree[n].children_end - tree[n].children_begin;
+      double* v = &val[(size_t)n * H];
+      if (tree[n].last_bid == A - 1) {   // terminal: compute_expected_terminal_values (:80-98, :765-789)
+        const int bid = tree[tree[n].parent].last_bid, quantity = 1 + bid / F, face = bid % F;
+        const double* ro = &reach[((size_t)(1 - trav) * N + n) * H];
+        std::vector<double> cnt(2 * D + 1, 0.0);
+        double tot = 0;
+        for (int g = 0; g < H; ++g) { cnt[matches(g, face)] += ro[g]; }
+        for (int i = (int)cnt.size() - 1; i-- > 0;) cnt[i] += cnt[i + 1];
+        for (int g = 0; g < H; ++g) tot += ro[g];
+        for (int h = 0; h < H; ++h) {
+          const int left = std::max(0, quantity - matches(h, face));
+          const float pw = (float)cnt[left];
+          double x = (double)pw * 2 - tot;
+          v[h] = tree[n].player_id != trav ? -x : x;
+        }
+        continue;
+      }
+      if (!nc) continue;
+      for (int h = 0; h < H; ++h) v[h] = 0.0;
+      if (tree[n].player_id == trav) {
+        for (int c = tree[n].children_begin; c < tree[n].children_end; ++c)
+          for (int h = 0; h < H; ++h) {
+            const double nv = val[(size_t)c * H + h];
+            if (c == tree[n].children_begin || nv > v[h]) v[h] = nv;   // first child wins ties (:336-337)
+          }
+      } else {
+        for (int c = tree[n].children_begin; c < tree[n].children_end; ++c)
+          for (int h = 0; h < H; ++h) v[h] += val[(size_t)c * H + h];
+      }
+    }
+    double s = 0;
+    for (int h = 0; h < H; ++h) s += val[h];
+    out[trav] = s / H;
+  }
+  return out;
+}
+
+struct RecursiveEvalResult {
+  std::vector<float> summed_strategy;   // [N][H][A]
+  std::vector<float> summed_reach;      // [N][H]
+  std::vector<float> final_strategy;    // summed_strategy / (summed_reach + 1e-6)   (recursive_eval.cc:362-363)
+  std::vector<int> checkpoints;         // number of repeats at which exploitability was evaluated (powers of two + last)
+  std::vector<std::array<double, 2>> exploitability;
+  int num_nodes = 0;
+  int64_t subgames_solved = 0;
+  double gpu_seconds = 0;   // host wall time spent inside cfrb_begin_wave / cfrb_run / cfrb_fetch_compact
+};
+
+class RecursiveEvaluator {
+ public:
+  RecursiveEvaluator(const liars_dice::RecursiveSolvingParams& cfg, int device, int wave_capacity)
+      : cfg_(cfg), K_(std::max(1, wave_capacity)) {
+    const auto& sp = cfg.subgame_params;
+    if (!sp.use_cfr) throw std::runtime_error("RecursiveEvaluator: set subgame_params.use_cfr=true");
+    cfrb_config c{};
+    c.num_dice = cfg.num_dice; c.num_faces = cfg.num_faces; c.max_depth = sp.max_depth; c.num_iters = sp.num_iters;
+    c.linear_update = sp.linear_update; c.dcfr = sp.dcfr; c.dcfr_alpha = sp.dcfr_alpha; c.dcfr_beta = sp.dcfr_beta;
+    c.dcfr_gamma = sp.dcfr_gamma; c.max_subgames = K_; c.device = device; c.net_mode = cfg.net_mode; c.hidden = 256;
+    c.state_dtype = cfg.state_dtype;
+    if (cfrb_create(&c, &h_) < 0) throw std::runtime_error(std::string("cfrb_create: ") + cfrb_last_error());
+    A_ = cfrb_num_actions(h_); H_ = cfrb_num_hands(h_); stride_ = cfrb_table_stride(h_);
+    // full tree + the order in which the reference's recursion creates subgame solvers (= order of its RNG draws)
+    full_.resize(1 << 20);
+    int n = cfrb_unroll_tree(cfg.num_dice, cfg.num_faces, -1, 0, 1 << 30, full_.data(), (int)full_.size());
+    if (n < 0 || n > (int)full_.size()) throw std::runtime_error("full tree too large");
+    full_.resize(n);
+    visit(0);
+    level_of_.assign(n, -1);
+    int max_level = 0;
+    for (int r : order_) { level_of_[r] = full_[r].depth / sp.max_depth; max_level = std::max(max_level, level_of_[r]); }
+    by_level_.resize(max_level + 1);
+    for (int r : order_) by_level_[level_of_[r]].push_back(r);
+    trees_.resize(A_);
+  }
+  ~RecursiveEvaluator() { if (h_) cfrb_destroy(h_); }
+  RecursiveEvaluator(const RecursiveEvaluator&) = delete;
+  RecursiveEvaluator& operator=(const RecursiveEvaluator&) = delete;
+
+  int numActions() const { return A_; }
+  int numHands() const { return H_; }
+  void setWeights(const std::vector<float>& flat) {
+    if (cfrb_set_weights(h_, flat.data(), flat.size(), 1) < 0) throw std::runtime_error(cfrb_last_error());
+  }
+
+  RecursiveEvalResult run(int num_repeats, int seed0, int batch_repeats) {
+    const int N = (int)full_.size();
+    RecursiveEvalResult res;
+    res.num_nodes = N;
+    res.summed_strategy.assign((size_t)N * H_ * A_, 0.f);
+    res.summed_reach.assign((size_t)N * H_, 0.f);
+    int done = 0;
+    while (done < num_repeats) {
+      // batches end at powers of two so that the exploitability curve of the reference (:364-369) can be reported
+      int next_cp = 1;
+      while (next_cp <= done) next_cp <<= 1;
+      const int hi = std::min({num_repeats, done + std::max(1, batch_repeats), next_cp});
+      runBatch(seed0 + done, hi - done, res);
+      done = hi;
+      if ((done & (done - 1)) == 0 || done == num_repeats) {
+        finalize(res);
+        std::vector<double> s(res.final_strategy.begin(), res.final_strategy.end());
+        res.checkpoints.push_back(done);
+        res.exploitability.push_back(best_response_values(cfg_.num_dice, cfg_.num_faces, full_, s));
+      }
+    }
+    return res;
+  }
+
+ private:
+  struct Pending { int repeat, root; std::vector<double> beliefs, reach; };   // [2][H] each
+
+  void visit(int root) {   // compute_strategy_recursive_to_leaf's control flow (recursive_solving.cc:76-134), structure only
+    if (full_[root].last_bid == A_ - 1) return;
+    order_.push_back(root);
+    std::deque<std::pair<int, int>> q;
+    q.emplace_back(root, 0);
+    const int md = cfg_.subgame_params.max_depth;
+    while (!q.empty()) {
+      auto [fn, d] = q.front();
+      q.pop_front();
+      const int nc = full_[fn].children_end - full_[fn].children_begin;
+      if (d < md) {
+        for (int c = full_[fn].children_begin; c < full_[fn].children_end; ++c) q.emplace_back(c, d + 1);
+      } else if (nc != 0) {
+        visit(fn);
+      }
+    }
+  }
+  const std::vector<cfrb_node>& tmpl(int root_bid) {
+    auto& t = trees_[root_bid + 1];
+    if (t.empty()) {
+      t.resize(cfrb_max_nodes(h_));
+      int n = cfrb_tree_template(h_, root_bid, 0, t.data(), (int)t.size());
+      if (n < 0) throw std::runtime_error(cfrb_last_error());
+      t.resize(n);
+    }
+    return t;
+  }
+  void normalize(double* b) const {   // normalize_beliefs_inplace (recursive_solving.cc:41-44)
+    double s = 0;
+    for (int h = 0; h < H_; ++h) s += b[h] + 1e-80;
+    for (int h = 0; h < H_; ++h) b[h] = (b[h] + 1e-80) / s;
+  }
+
+  void runBatch(int seed_first, int count, RecursiveEvalResult& res) {
+    const auto& sp = cfg_.subgame_params;
+    const int N = (int)full_.size();
+    // act_iteration per (repeat, subgame root): discrete distribution with weight i/2+1 on even i (:304-309,315-319)
+    std::vector<double> weights;
+    for (int i = 0; i < sp.num_iters; ++i) weights.push_back(i % 2 ? 0.0 : (i / 2. + 1));
+    std::vector<std::vector<int>> act(count, std::vector<int>(N, -1));
+    for (int r = 0; r < count; ++r) {
+      std::mt19937 gen(seed_first + r);
+      for (int root : order_) {
+        std::discrete_distribution<int> dist(weights.begin(), weights.end());
+        act[r][root] = dist(gen);
+      }
+    }
+    // level 0: the game root with uniform beliefs
+    std::vector<Pending> cur, next;
+    for (int r = 0; r < count; ++r) cur.push_back(Pending{r, 0, std::vector<double>((size_t)2 * H_, 1.0 / H_), std::vector<double>((size_t)2 * H_, 1.0 / H_)});
+    std::vector<int32_t> lb, pl, ai;
+    std::vector<double> bel, snap;
+    while (!cur.empty()) {
+      next.clear();
+      for (size_t off = 0; off < cur.size(); off += K_) {
+        const int n = (int)std::min<size_t>(K_, cur.size() - off);
+        lb.resize(n); pl.resize(n); ai.resize(n); bel.resize((size_t)n * 2 * H_); snap.resize((size_t)n * stride_);
+        int max_act = 0;
+        for (int i = 0; i < n; ++i) {
+          const Pending& P = cur[off + i];
+          lb[i] = full_[P.root].last_bid; pl[i] = full_[P.root].player_id; ai[i] = act[P.repeat][P.root];
+          max_act = std::max(max_act, ai[i]);
+          std::copy(P.beliefs.begin(), P.beliefs.end(), bel.begin() + (size_t)i * 2 * H_);
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        if (cfrb_begin_wave(h_, n, lb.data(), pl.data(), bel.data(), ai.data()) < 0) throw std::runtime_error(cfrb_last_error());
+        if (cfrb_run(h_, max_act, nullptr) < 0) throw std::runtime_error(cfrb_last_error());
+        if (cfrb_fetch_compact(h_, 0, snap.data()) < 0) throw std::runtime_error(cfrb_last_error());
+        res.gpu_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        res.subgames_solved += n;
+        for (int i = 0; i < n; ++i) expand(cur[off + i], snap.data() + (size_t)i * stride_, res, next);
+      }
+      cur.swap(next);
+    }
+  }
+
+  // BFS over one solved subgame (recursive_solving.cc:97-133): accumulate strategy x reach of its inner nodes, propagate
+  // beliefs / reach to its pseudo-leaves and queue the next-level subgames.
+  void expand(const Pending& P, const double* sigma, RecursiveEvalResult& res, std::vector<Pending>& next) {
+    const auto& t = tmpl(full_[P.root].last_bid);
+    const int rp = full_[P.root].player_id;
+    struct Item { int full, part; std::vector<double> beliefs, reach; };
+    std::deque<Item> q;
+    q.push_back(Item{P.root, 0, P.beliefs, P.reach});
+    while (!q.empty()) {
+      Item it = std::move(q.front());
+      q.pop_front();
+      const int pnc = t[it.part].children_end - t[it.part].children_begin;
+      const int fnc = full_[it.full].children_end - full_[it.full].children_begin;
+      const int pid = full_[it.full].player_id;
+      if (pnc == 0 && fnc != 0) {   // non-terminal leaf of the subgame: root of a subgame on the next level (:127-132)
+        Pending C{P.repeat, it.full, std::move(it.beliefs), std::move(it.reach)};
+        normalize(C.beliefs.data());
+        normalize(C.beliefs.data() + H_);
+        next.push_back(std::move(C));
+        continue;
+      }
+      // weight of infoset (node, hand) = reach_probabilities[player(node)][node][hand] under the sampled strategy
+      // (recursive_eval.cc:143-148; compute_stategy_stats, subgame_solving.cc:839-842), accumulated in float32
+      for (int h = 0; h < H_; ++h) res.summed_reach[(size_t)it.full * H_ + h] += (float)it.reach[(size_t)pid * H_ + h];
+      if (pnc == 0) continue;   // terminal node
+      const int lo = t[it.part].last_bid < 0 ? 0 : t[it.part].last_bid + 1;
+      for (int j = 0; j < pnc; ++j) {
+        const int pc = t[it.part].children_begin + j, action = lo + j;
+        Item ch{full_[it.full].children_begin + j, pc, it.beliefs, it.reach};
+        for (int h = 0; h < H_; ++h) {
+          const double s = sigma[(size_t)(pc - 1) * H_ + h];
+          res.summed_strategy[((size_t)it.full * H_ + h) * A_ + action] += (float)s * (float)it.reach[(size_t)pid * H_ + h];
+          ch.beliefs[(size_t)pid * H_ + h] *= s;
+          ch.reach[(size_t)pid * H_ + h] *= s;
+        }
+        q.push_back(std::move(ch));
+      }
+    }
+  }
+
+  void finalize(RecursiveEvalResult& res) const {
+    const size_t NH = res.summed_reach.size();
+    res.final_strategy.resize(res.summed_strategy.size());
+    for (size_t i = 0; i < NH; ++i) {
+      const float den = res.summed_reach[i] + 1e-6f;
+      for (int a = 0; a < A_; ++a) res.final_strategy[i * A_ + a] = res.summed_strategy[i * A_ + a] / den;
+    }
+  }
+
+  const liars_dice::RecursiveSolvingParams cfg_;
+  const int K_;
+  cfrb_handle* h_ = nullptr;
+  int A_ = 0, H_ = 0, stride_ = 0;
+  std::vector<cfrb_node> full_;
+  std::vector<int> order_, level_of_;
+  std::vector<std::vector<int>> by_level_;
+  std::vector<std::vector<cfrb_node>> trees_;
+};
+
+}  // namespace rela

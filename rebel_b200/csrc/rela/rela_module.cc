@@ -9,6 +9,7 @@
 #include "batched_runner.h"
 #include "model_locker.h"
 #include "params.h"
+#include "recursive_eval.h"
 #include "replay.h"
 #include "runtime.h"
 
@@ -100,6 +101,53 @@ std::tuple<torch::Tensor, torch::Tensor> run_selfplay_waves(const RecursiveSolvi
   return std::make_tuple(q, v);
 }
 
+// BASELINE config 5 (`recursive_eval --cfr --num_repeats R`, recursive_eval.cc:331-369): R sampled recursive strategies,
+// float32 reach-weighted average, exploitability of the average.  Returns a dict of tensors.
+py::dict recursive_eval_sampled(const RecursiveSolvingParams& cfg, int device, int num_repeats, int seed0, int batch_repeats,
+                                int wave_capacity, py::object flat_weights) {
+  std::vector<float> w;
+  if (!flat_weights.is_none()) {
+    auto t = flat_weights.cast<torch::Tensor>().to(torch::kCPU, torch::kFloat32).contiguous();
+    w.assign(t.data_ptr<float>(), t.data_ptr<float>() + t.numel());
+  }
+  RecursiveEvalResult r;
+  int A = 0, H = 0;
+  {
+    py::gil_scoped_release nogil;
+    RecursiveEvaluator ev(cfg, device, wave_capacity);
+    if (!w.empty()) ev.setWeights(w);
+    r = ev.run(num_repeats, seed0, batch_repeats);
+    A = ev.numActions(); H = ev.numHands();
+  }
+  const int64_t N = r.num_nodes;
+  auto ss = torch::empty({N, H, A}), sr = torch::empty({N, H, 1}), fs = torch::empty({N, H, A});
+  std::copy(r.summed_strategy.begin(), r.summed_strategy.end(), ss.data_ptr<float>());
+  std::copy(r.summed_reach.begin(), r.summed_reach.end(), sr.data_ptr<float>());
+  std::copy(r.final_strategy.begin(), r.final_strategy.end(), fs.data_ptr<float>());
+  auto ex = torch::empty({(int64_t)r.exploitability.size(), 2}, torch::kFloat64);
+  for (size_t i = 0; i < r.exploitability.size(); ++i) {
+    ex[i][0] = r.exploitability[i][0];
+    ex[i][1] = r.exploitability[i][1];
+  }
+  py::dict d;
+  d["summed_strategy"] = ss; d["summed_reach"] = sr; d["final_strategy"] = fs;
+  d["checkpoints"] = r.checkpoints; d["exploitability"] = ex; d["subgames_solved"] = r.subgames_solved;
+  d["gpu_seconds"] = r.gpu_seconds;
+  return d;
+}
+
+// compute_exploitability2 (subgame_solving.cc:802-816) of a dense full-tree strategy [N][H][A]; host code, no GPU needed.
+std::tuple<double, double> exploitability_of_strategy(int num_dice, int num_faces, torch::Tensor strategy) {
+  auto s = strategy.to(torch::kCPU, torch::kFloat64).contiguous();
+  std::vector<cfrb_node> tree(1 << 20);
+  const int n = cfrb_unroll_tree(num_dice, num_faces, -1, 0, 1 << 30, tree.data(), (int)tree.size());
+  if (n <= 0 || n > (int)tree.size() || s.dim() != 3 || s.size(0) != n) throw std::runtime_error("exploitability_of_strategy: strategy must be [num_full_tree_nodes, H, A]");
+  tree.resize(n);
+  std::vector<double> v(s.data_ptr<double>(), s.data_ptr<double>() + s.numel());
+  auto e = best_response_values(num_dice, num_faces, tree, v);
+  return std::make_tuple(e[0], e[1]);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(rela, m) {
@@ -173,4 +221,10 @@ PYBIND11_MODULE(rela, m) {
   m.def("run_selfplay_waves", &run_selfplay_waves, py::arg("cfg"), py::arg("device"), py::arg("seed"), py::arg("waves"),
         py::arg("flat_weights") = py::none(),
         "rebel_b200 extension: run `waves` waves of a BatchedRlRunner synchronously and return (queries, values).");
+  m.def("exploitability_of_strategy", &exploitability_of_strategy, py::arg("num_dice"), py::arg("num_faces"), py::arg("strategy"),
+        "rebel_b200 extension: compute_exploitability2 of a dense full-tree strategy (host best response).");
+  m.def("recursive_eval_sampled", &recursive_eval_sampled, py::arg("cfg"), py::arg("device"), py::arg("num_repeats"), py::arg("seed") = 0,
+        py::arg("batch_repeats") = 64, py::arg("wave_capacity") = 8192, py::arg("flat_weights") = py::none(),
+        "rebel_b200 extension: the reference's `recursive_eval --cfr --num_repeats R` (sampled recursive strategies, float32 "
+        "reach-weighted average, exploitability at powers of two) with the subgame solves batched on the GPU.");
 }

@@ -27,6 +27,13 @@ def _worker(rank, world, port, K, Q, H, out_dir):
     q = np.repeat(ids[:, None], Q, 1)
     v = np.repeat(-ids[:, None], H, 1)
     res = D.gather_examples(q, v, "cpu")
+    # recursive evaluation: contiguous strategy-id blocks per rank, float32 partial sums reduced to rank 0
+    from rebel_b200.recursive_eval import reduce_sums, strategy_ids
+    blocks = [strategy_ids(r, world, 4097) for r in range(world)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == 4097 and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+    ss, sr = reduce_sums(torch.full((5, 3, 4), float(rank + 1)), torch.full((5, 3, 1), 0.5), "cpu")
+    if rank == 0:
+        assert torch.all(ss == sum(range(1, world + 1))) and torch.all(sr == 0.5 * world)
     m = D.max_over_ranks(10.0 + rank, "cpu")
     assert m == 10.0 + world - 1
     if rank == 0:

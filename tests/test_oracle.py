@@ -183,3 +183,22 @@ def test_port_vs_compiled_reference_live():
         qa, va = P.rl_runner(D, F, seed=3, n_games=2, num_iters=24)
         qb, vb = R.rl_runner(D, F, seed=3, n_games=2, num_iters=24)
         assert np.array_equal(qa, qb) and np.array_equal(va, vb)
+
+
+@pytest.mark.skipif(not available("ref_nofma"), reason="oracle/_ref not built (needs /root/reference)")
+def test_recursive_eval_golden_reproducible_live(golden):
+    """The recursive-evaluation fixture (BASELINE config 5 path) is what the compiled reference produces here: its own
+    compute_sampled_strategy_recursive_to_leaf + compute_stategy_stats + compute_exploitability2 under the accumulation loop
+    of recursive_eval.cc:343-369."""
+    from oracle.make_golden import recursive_eval_reference
+    g = golden("recursive_eval_zero.npz")
+    D, F = 1, 4
+    iters, reps = (int(x) for x in g[f"cfg_{D}x{F}"])
+    r = recursive_eval_reference(Oracle("ref_nofma"), D, F, iters, reps)
+    for k in ("summed_strategy", "summed_reach", "checkpoints", "exploitability", "first_strategies"):
+        assert np.array_equal(r[k], g[f"{k}_{D}x{F}"]), k
+    # the sampled strategies are proper strategies on every non-terminal node of the full tree
+    s = r["first_strategies"][0]
+    tree = Oracle("ref_nofma").unroll_tree(D, F)
+    inner = tree[:, 2] != tree[:, 3]
+    assert np.allclose(s[inner].sum(-1), 1.0, atol=1e-12) and np.all(s[~inner] == 0)

@@ -133,7 +133,45 @@ def test_model_locker_snapshots_weights(rela):
         rela.ModelLocker([torch.nn.Linear(3, 3)], "cuda:0")
 
 
+@pytest.mark.parametrize("D,F", [(1, 2), (1, 3), (1, 4)])
+def test_host_best_response_bit_exact(rela, golden, D, F):
+    """exploitability_of_strategy = compute_exploitability2 / BRSolver::compute_br (subgame_solving.cc:316-358,802-816):
+    bit-identical to the compiled reference on the golden 16-iteration full-tree strategies."""
+    g = golden("fulltree.npz")
+    e = rela.exploitability_of_strategy(D, F, torch.from_numpy(g[f"avg16_{D}x{F}"]))
+    assert np.array_equal(np.array(e), g[f"expl_{D}x{F}_nofma"][0])
+
+
+@pytest.mark.parametrize("D,F", [(1, 4), (1, 6), (2, 3)])
+def test_host_best_response_on_recursive_eval_golden(rela, golden, D, F):
+    g = golden("recursive_eval_zero.npz")
+    ss, sr = g[f"summed_strategy_{D}x{F}"], g[f"summed_reach_{D}x{F}"]
+    e = rela.exploitability_of_strategy(D, F, torch.from_numpy(ss / (sr + np.float32(1e-6))))
+    assert np.array_equal(np.array(e), g[f"exploitability_{D}x{F}"][-1])
+    with pytest.raises(RuntimeError):
+        rela.exploitability_of_strategy(D, F, torch.zeros(3, 2, 2))
+
+
 # ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,F", [(1, 4), (1, 6), (2, 3)])
+@pytest.mark.parametrize("batch_repeats,wave_capacity", [(64, 4096), (1, 37)])
+def test_recursive_eval_bit_exact_vs_reference(rela, golden, D, F, batch_repeats, wave_capacity):
+    """BASELINE config 5 path (recursive_eval.cc:117-191,343-369): sampled recursive strategies of seeds 0..R-1 solved as
+    level-batched GPU waves, float32 reach-weighted sums in strategy_id order, exploitability at powers of two.  Zero net,
+    fp64 tables: every number is bit-identical to the compiled reference (fixture from oracle/make_golden.py), however the
+    repeats are batched and whatever the wave capacity."""
+    g = golden("recursive_eval_zero.npz")
+    iters, reps = (int(x) for x in g[f"cfg_{D}x{F}"])
+    cfg = make_cfg(rela, D, F, net_mode=0, state_dtype=0, subgame_params=dict(num_iters=iters, max_depth=2, linear_update=True, use_cfr=True))
+    r = rela.recursive_eval_sampled(cfg, 0, reps, seed=0, batch_repeats=batch_repeats, wave_capacity=wave_capacity)
+    assert list(r["checkpoints"]) == list(g[f"checkpoints_{D}x{F}"])
+    assert np.array_equal(r["summed_reach"].numpy(), g[f"summed_reach_{D}x{F}"])
+    assert np.array_equal(r["summed_strategy"].numpy(), g[f"summed_strategy_{D}x{F}"])
+    assert np.array_equal(r["exploitability"].numpy(), g[f"exploitability_{D}x{F}"])
+    assert r["subgames_solved"] > 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("D,F", [(1, 4), (1, 6), (2, 3)])
 @pytest.mark.parametrize("sample_leaf", [True, False])
