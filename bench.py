@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--iters", type=int, default=1024)
     ap.add_argument("--dice", type=int, default=1)
     ap.add_argument("--faces", type=int, default=6)
-    ap.add_argument("--net", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--net", default="auto", choices=["auto", "fp32", "tc", "tcx2"],
+                    help="value-net kernel: tcx2 (default) = tcgen05 fp16 with packed-half GELU, tc = tcgen05 fp16 with fp32 GELU, fp32 = SIMT parity net")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="subgames in the CPU-baseline sample (0 = auto)")
     return ap.parse_args()
@@ -246,14 +247,9 @@ def run_b200(args):
     nflat = 256 * Q + 3 * 256 + 256 * 256 + 3 * 256 + H * 256 + H
     w = rbdist.broadcast_weights(flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict()) if rank == 0 else None, nflat, dev)
 
-    mode, mode_name = rb.NET_FP32, "fp32"
-    if args.net in ("auto", "tc"):
-        try:
-            rb.WaveSolver(D, F, 1, net_mode=rb.NET_TC_F16, device=local).close()
-            mode, mode_name = rb.NET_TC_F16, "tc_f16"
-        except rb.CfrbError:
-            if args.net == "tc":
-                raise
+    mode, mode_name = {"auto": (rb.NET_TC_F16X2, "tc_f16x2"), "tcx2": (rb.NET_TC_F16X2, "tc_f16x2"), "tc": (rb.NET_TC_F16, "tc_f16"),
+                       "fp32": (rb.NET_FP32, "fp32")}[args.net]
+    is_tc = mode in (rb.NET_TC_F16, rb.NET_TC_F16X2)
     S = rb.WaveSolver(D, F, K, num_iters=iters, net_mode=mode, device=local)
     S.set_weights(w, version=1)
 
@@ -337,7 +333,7 @@ def run_b200(args):
     traffic = None   # DRAM bytes per launch of the value-net kernel from the committed ncu --set full capture (same workload only)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if mode == rb.NET_TC_F16 and (D, F, K) == (1, 6, 8192):
+        if is_tc and (D, F, K) == (1, 6, 8192):
             traffic = [v["dram_bytes_per_launch"] for k, v in tj.items() if "leaf_mlp_tc_kernel" in k][0]
     except Exception:
         traffic = None
@@ -352,7 +348,7 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 (CFR tables) / " + ("f16 operands, f32 accumulate (value net, tcgen05)" if mode == rb.NET_TC_F16 else "f32 (value net)"),
+        "dtype": "f64 (CFR tables) / " + ("f16 operands, f32 accumulate + LayerNorm, " + ("f16x2" if mode == rb.NET_TC_F16X2 else "f32") + " GELU (value net, tcgen05)" if is_tc else "f32 (value net)"),
         "data": "synthetic", "config": dict(workload_config(args, K), value_net_kernel=mode_name, parallelism=f"dp{world}",
                                            l2="256 MiB memset between steps, inside the timed region"),
         "clocks": clocks,

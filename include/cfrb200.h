@@ -61,8 +61,10 @@ enum {
 enum {
   CFRB_NET_ZERO = 0,      /* leaf values are 0 (reference: create_zero_net, real_net.cc:30-55) */
   CFRB_NET_FP32 = 1,      /* fp32 SIMT kernel: parity path, matches libtorch fp32 to ~1e-6 */
-  CFRB_NET_TC_F16 = 2     /* tcgen05 tensor-core kernel: fp16 operands, fp32 accumulate/LayerNorm/GELU
+  CFRB_NET_TC_F16 = 2,    /* tcgen05 tensor-core kernel: fp16 operands, fp32 accumulate/LayerNorm/GELU
                              (the reference's own `half_inference` option, selfplay.py:42-43,211) */
+  CFRB_NET_TC_F16X2 = 3   /* same kernel, GELU evaluated on packed fp16 pairs (HFMA2 + tanh.approx.f16x2) after the
+                             fp32 LayerNorm: ~40 % fewer epilogue instructions, ~1.6x the activation rounding noise */
 };
 
 /* Arithmetic type of the per-infoset CFR tables (regrets, strategies, reach, values). */
@@ -175,6 +177,9 @@ int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, double* s
 /* Debug taps of the tensor-core value net (CFRB_NET_TC_F16 only): re-runs it on the current query tiles and returns
  * the raw fp32 accumulators of layer 1 and layer 2 for the first 128 rows, each [128][256]. */
 int cfrb_debug_net_taps(cfrb_handle* h, float* d1, float* d2);
+/* Development aid: re-runs the tensor-core value net once with clock64() stamps of CTA 0 (out[2048]: epilogue thread 0 at
+ * [iter*16 + e], MMA-issuing thread at [1024 + iter*8 + m]; see leaf_mlp_tc.cuh). */
+int cfrb_debug_net_trace(cfrb_handle* h, long long* out, int n);
 
 /* Exploitability (best-response values of both players, compute_exploitability2) of a full-tree strategy
  * given as dense [N_full][H][A] fp64, evaluated on the GPU. out2 = {br0, br1}. */

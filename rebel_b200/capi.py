@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfrb200.so")
 
-NET_ZERO, NET_FP32, NET_TC_F16 = 0, 1, 2
+NET_ZERO, NET_FP32, NET_TC_F16, NET_TC_F16X2 = 0, 1, 2, 3
 STATE_F64, STATE_F32 = 0, 1
 
 
@@ -68,6 +68,7 @@ def lib():
     L.cfrb_debug_leaf_io.argtypes = [vp, _fp, _fp, _dp, C.c_int32]
     L.cfrb_exploitability.argtypes = [vp, _dp, _dp]
     L.cfrb_debug_net_taps.argtypes = [vp, _fp, _fp]
+    L.cfrb_debug_net_trace.argtypes = [vp, C.POINTER(C.c_longlong), C.c_int]
     L.cfrb_kernel_launches.argtypes = [vp]
     L.cfrb_kernel_launches.restype = C.c_int64
     L.cfrb_wave_leaf_rows.argtypes = [vp]
@@ -204,6 +205,11 @@ class WaveSolver:
         d2 = np.zeros((128, 256), np.float32)
         _check(lib().cfrb_debug_net_taps(self._h, _p(d1, _fp), _p(d2, _fp)))
         return d1, d2
+
+    def net_trace(self):
+        t = np.zeros(2048, np.int64)
+        _check(lib().cfrb_debug_net_trace(self._h, t.ctypes.data_as(C.POINTER(C.c_longlong)), 2048))
+        return t
 
     def exploitability(self, full_strategy):
         s = np.ascontiguousarray(full_strategy, np.float64)

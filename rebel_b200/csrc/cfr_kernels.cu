@@ -46,10 +46,30 @@ void cfr_launch_iter(const CfrDev<real>& p, int group, int blocks, int threads, 
   }
 }
 
+template <typename real>
+cudaError_t cfr_configure_d2(int smem_bytes) {
+  cudaError_t e = cudaSuccess;
+#define CFRB_CFG(HC)                                                                                                      \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cfr_iter_d2_kernel<real, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  CFRB_CFG(0) CFRB_CFG(4) CFRB_CFG(5) CFRB_CFG(6) CFRB_CFG(9) CFRB_CFG(16)
+#undef CFRB_CFG
+  return e;
+}
+
+template <typename real>
+void cfr_launch_iter_d2(const CfrDev<real>& p, int blocks, int threads, size_t smem, cudaStream_t st, int iter, int do_b, int do_f,
+                        int scratch_per_group) {
+#define CFRB_CALL(HC) cfr_iter_d2_kernel<real, HC><<<blocks, threads, smem, st>>>(p, iter, do_b, do_f, scratch_per_group)
+  CFRB_DISPATCH_H(p.H, CFRB_CALL)
+#undef CFRB_CALL
+}
+
 #define CFRB_INSTANTIATE(real)                                                                                             \
   template cudaError_t cfr_configure<real>(int, int);                                                                      \
   template void cfr_launch_init<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int);                      \
-  template void cfr_launch_iter<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int, int, int, int);
+  template void cfr_launch_iter<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int, int, int, int);             \
+  template cudaError_t cfr_configure_d2<real>(int);                                                                        \
+  template void cfr_launch_iter_d2<real>(const CfrDev<real>&, int, int, size_t, cudaStream_t, int, int, int, int);
 CFRB_INSTANTIATE(float)
 CFRB_INSTANTIATE(double)
 

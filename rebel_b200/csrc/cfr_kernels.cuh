@@ -343,6 +343,284 @@ __global__ void __launch_bounds__(512) cfr_iter_kernel(CfrDev<real> p, int iter,
   }
 }
 
+// ======================================================================================================================
+// Depth <= 2 specialisation (templates with at most three levels: root, level 1, level 2 — every subgame of a max_depth <= 2
+// solver, i.e. the self-play configuration).  Each player acts on exactly one level there (the root player P0 = rp at the
+// root, P1 at level 1), which removes most of the generic kernel's scratch:
+//   * the traverser's reach at the nodes where it acts is just its root belief;
+//   * reach_P0 is constant below level 1 and reach_P1 is the root belief down to level 1, so ONE [N*H] buffer holds
+//     everything the forward half needs: slot[n] = reach_P0[n] for level-1 nodes, slot[c] = reach_P1[c] for level-2 nodes;
+//   * the backward half uses the same buffer for node values / new regrets and leaves the traverser's new reach
+//     (belief * new strategy) in the slots of the level where it acts, exactly the products the forward half would form.
+// Scratch per subgame: slot[N*H] | bel[2*H] | hist[10*T] | lsum[2*L] — half of the generic layout, so twice as many
+// subgames are resident per SM.  All arithmetic is the generic kernel's, operation for operation (bit-identical results).
+struct D2Levels {
+  int n1b, n1e, n2e;   // level 1 = [n1b, n1e), level 2 = [n1e, n2e) (empty when the template has two levels)
+};
+__device__ __forceinline__ D2Levels d2_levels(const int* __restrict__ level_begin, const TemplateDev& t) {
+  D2Levels L;
+  L.n1b = level_begin[t.level_off + 1];
+  L.n1e = t.levels >= 2 ? level_begin[t.level_off + 2] : L.n1b;
+  L.n2e = t.levels >= 3 ? level_begin[t.level_off + 3] : L.n1e;
+  return L;
+}
+// Row [H] of reach probabilities of `player` at node n (level 1 or 2) in the d2 scratch.
+template <typename real>
+__device__ __forceinline__ const real* d2_reach_row(const real* slot, const real* bel, const int* __restrict__ parent, int n, int n1e,
+                                                    int player, int rp, int H) {
+  if (n < n1e) return player == rp ? slot + n * H : bel + player * H;           // level 1
+  return player == rp ? slot + parent[n] * H : slot + n * H;                    // level 2
+}
+
+template <typename real, int HC>
+__device__ void cfr_backward_d2(const CfrDev<real>& p, int k, int trav, real* val, const real* bel, int lane) {
+  constexpr int G = 32;
+  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
+  const int H = HC > 0 ? HC : p.H;
+  const int rp = p.sg_player[k];
+  real* R = p.R + (size_t)k * p.table_stride;
+  real* Sg = p.Sg + (size_t)k * p.table_stride;
+  real* S = p.S + (size_t)k * p.table_stride;
+  const int* __restrict__ parent = p.parent + t.node_off;
+  const int* __restrict__ nchild = p.nchild + t.node_off;
+  const int* __restrict__ child_begin = p.child_begin + t.node_off;
+  const int row0 = p.sg_row_off[k];
+  const D2Levels lv = d2_levels(p.level_begin, t);
+  const bool mine0 = rp == trav;          // traverser acts at the root (else at level 1)
+  // leaf values = (float)(net(query) * scaler) (subgame_solving.cc:266-282); terminals from the forward half
+  for (int it = lane; it < t.L * H; it += G) {
+    const int r = it / H, h = it % H;
+    const int n = p.pleaf_node[t.pleaf_off + r];
+    val[n * H + h] = p.use_net ? (real)(float)((real)p.net_out[(size_t)(row0 + r) * p.Hout + h] * p.scaler[row0 + r]) : (real)0;
+  }
+  const real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
+  for (int it = lane; it < t.T * H; it += G) {
+    const int z = it / H, h = it % H;
+    val[p.term_node[t.term_off + z] * H + h] = vt[z * H + h];
+  }
+  __syncwarp();
+  // ---- bottom-up (update_regrets :538-575): level-1 node values, then the root
+  if (lv.n2e > lv.n1e) {
+    for (int it = lane; it < (lv.n1e - lv.n1b) * H; it += G) {
+      const int n = lv.n1b + it / H, h = it % H;
+      const int nc = nchild[n];
+      if (!nc) continue;
+      const int c0 = child_begin[n];
+      real v = 0;
+      if (!mine0) { for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h] * Sg[(c0 + j - 1) * H + h]; }
+      else        { for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h]; }
+      val[n * H + h] = v;
+    }
+    __syncwarp();
+    if (!mine0) {   // new regrets of the level-1 actions, kept in the child's slot
+      for (int it = lane; it < (lv.n2e - lv.n1e) * H; it += G) {
+        const int c = lv.n1e + it / H, h = it % H;
+        val[c * H + h] = (R[(c - 1) * H + h] + val[c * H + h]) - val[parent[c] * H + h];
+      }
+    }
+  }
+  for (int h = lane; h < H; h += G) {
+    real v = 0;
+    if (mine0) { for (int n = lv.n1b; n < lv.n1e; ++n) v += val[n * H + h] * Sg[(n - 1) * H + h]; }
+    else       { for (int n = lv.n1b; n < lv.n1e; ++n) v += val[n * H + h]; }
+    val[h] = v;
+  }
+  __syncwarp();
+  if (mine0) {
+    for (int it = lane; it < (lv.n1e - lv.n1b) * H; it += G) {
+      const int n = lv.n1b + it / H, h = it % H;
+      val[n * H + h] = (R[(n - 1) * H + h] + val[n * H + h]) - val[h];
+    }
+  }
+  // ---- root value running mean (:579-590) and discounts (:592-617)
+  const int s = p.steps[2 * k + trav];
+  {
+    const real alpha = p.linear ? (real)2 / (s + 2) : (real)1 / (s + 1);
+    real* mu = p.mu + ((size_t)k * 2 + trav) * H;
+    for (int h = lane; h < H; h += G) mu[h] += (val[h] - mu[h]) * alpha;
+  }
+  real pos = 1, neg = 1, strat = 1;
+  {
+    const real ns = (real)(s + 1);
+    if (p.linear) {
+      pos = neg = strat = ns / (ns + 1);
+    } else if (p.dcfr) {
+      pos = p.dcfr_alpha >= 5 ? (real)1 : rpow(ns, p.dcfr_alpha) / (rpow(ns, p.dcfr_alpha) + 1);
+      neg = p.dcfr_beta <= -5 ? (real)0 : rpow(ns, p.dcfr_beta) / (rpow(ns, p.dcfr_beta) + 1);
+      strat = rpow(ns / (ns + 1), p.dcfr_gamma);
+    }
+  }
+  __syncwarp();
+  // ---- regret matching (:619-634), regret discount and sum-strategy update (:639-661) on the traverser's level.  The
+  // traverser has not acted above that level, so its reach there is its root belief; the child's slot receives
+  // belief * new strategy = the traverser's reach under the new strategy (:636-638), which the forward half reuses.
+  const real* bt = bel + trav * H;
+  const int pb = mine0 ? 0 : lv.n1b, pe = mine0 ? 1 : lv.n1e;            // acting nodes
+  const int cb = mine0 ? lv.n1b : lv.n1e, ce = mine0 ? lv.n1e : lv.n2e;  // their children
+  for (int it = lane; it < (pe - pb) * H; it += G) {
+    const int n = pb + it / H, h = it % H;
+    const int nc = nchild[n];
+    if (!nc) continue;
+    const int c0 = child_begin[n];
+    real sum = 0;
+    for (int j = 0; j < nc; ++j) {
+      const real r = val[(c0 + j) * H + h];
+      sum += Eps<real>::kLiteral ? (r > Eps<real>::v ? r : Eps<real>::v) : rmax0(r);   // max(R, 1e-80) (:626-629)
+    }
+    val[n * H + h] = sum;
+  }
+  __syncwarp();
+  for (int it = lane; it < (ce - cb) * H; it += G) {
+    const int c = cb + it / H, h = it % H;
+    const int e = (c - 1) * H + h, par = parent[c];
+    const real r = val[c * H + h], sum = val[par * H + h], rn = bt[h];
+    const real sg = Eps<real>::kLiteral ? (r > Eps<real>::v ? r : Eps<real>::v) / sum
+                                        : (sum > 0 ? rmax0(r) / sum : (real)1 / nchild[par]);
+    Sg[e] = sg;
+    R[e] = r * (r > 0 ? pos : neg);
+    S[e] = S[e] * strat + rn * sg;
+    val[c * H + h] = rn * sg;
+  }
+  if (lane == 0) p.steps[2 * k + trav] = s + 1;
+  __syncwarp();
+}
+
+// have: level whose slots already hold the reach of the player acting above it (0: level-1 slots = reach_P0 valid,
+// 1: level-2 slots = reach_P1 valid, -1: neither).
+template <typename real, int HC>
+__device__ void cfr_forward_d2(const CfrDev<real>& p, int k, int trav, real* slot, const real* bel, int have, real* lsum, real* hist,
+                               int lane) {
+  constexpr int G = 32;
+  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
+  const int H = HC > 0 ? HC : p.H;
+  const int rp = p.sg_player[k];
+  const real* Sg = p.Sg + (size_t)k * p.table_stride;     // not __restrict__/const-cached: written earlier in this launch
+  const int* __restrict__ parent = p.parent + t.node_off;
+  const D2Levels lv = d2_levels(p.level_begin, t);
+  // ---- reach under Sg (compute_reach_probabilities, subgame_solving.cc:54-78): belief * strategy of the acting level
+  if (have != 0) {
+    const real* b0 = bel + rp * H;
+    for (int it = lane; it < (lv.n1e - lv.n1b) * H; it += G) {
+      const int n = lv.n1b + it / H, h = it % H;
+      slot[n * H + h] = b0[h] * Sg[(n - 1) * H + h];
+    }
+  }
+  if (have != 1) {
+    const real* b1 = bel + (1 - rp) * H;
+    for (int it = lane; it < (lv.n2e - lv.n1e) * H; it += G) {
+      const int c = lv.n1e + it / H, h = it % H;
+      slot[c * H + h] = b1[h] * Sg[(c - 1) * H + h];
+    }
+  }
+  __syncwarp();
+  // ---- pseudo-leaves: normalisation sums + scaler (subgame_solving.cc:257-265)
+  const int row0 = p.sg_row_off[k];
+  for (int r = lane; r < t.L; r += G) {
+    const int n = p.pleaf_node[t.pleaf_off + r];
+    const real* r0 = d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H);
+    const real* r1 = d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H);
+    real s0 = 0, s1 = 0, e0 = 0, e1 = 0;
+    for (int h = 0; h < H; ++h) {
+      s0 += r0[h]; s1 += r1[h];                                              // vector_sum (:264)
+      e0 += r0[h] + Eps<real>::v; e1 += r1[h] + Eps<real>::v;               // normalize_probabilities_safe
+    }
+    lsum[2 * r] = (real)1 / e0; lsum[2 * r + 1] = (real)1 / e1;
+    p.scaler[row0 + r] = trav == 0 ? s1 : s0;
+  }
+  __syncwarp();
+  // ---- query rows (write_query_to :104-123); all pseudo-leaves sit on the last level
+  const int leaf_player = rp ^ ((t.levels - 1) & 1);
+  const int Qp = p.Qpad;
+  if (p.Xh != nullptr) {
+    const int kc = Qp >> 3;
+    for (int it = lane; it < t.L * kc; it += G) {
+      const int k8 = it / t.L, r = it % t.L;
+      const int n = p.pleaf_node[t.pleaf_off + r];
+      const int bid = p.last_bid[t.node_off + n];
+      const real* r0 = d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H);
+      const real* r1 = d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H);
+      const real s0 = lsum[2 * r], s1 = lsum[2 * r + 1];
+      union { int4 v; __half h[8]; } c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c.h[j] = __float2half_rn(query_value(p, k8 * 8 + j, leaf_player, trav, bid, r0, r1, s0, s1));
+      const int Rr = row0 + r, rr = Rr & 127;
+      *reinterpret_cast<int4*>(p.Xh + (size_t)(Rr >> 7) * 128 * Qp + k8 * 1024 + (rr >> 3) * 64 + (rr & 7) * 8) = c.v;
+    }
+  } else if (p.X != nullptr) {
+    for (int it = lane; it < t.L * Qp; it += G) {
+      const int r = it / Qp, q = it % Qp;
+      const int n = p.pleaf_node[t.pleaf_off + r];
+      p.X[(size_t)(row0 + r) * Qp + q] =
+          query_value(p, q, leaf_player, trav, p.last_bid[t.node_off + n], d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H),
+                      d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H), lsum[2 * r], lsum[2 * r + 1]);
+    }
+  }
+  // ---- terminals (compute_expected_terminal_values :80-98; win probability :765-789), as in cfr_forward
+  constexpr int kMaxBins = 9;
+  real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
+  for (int z = lane; z < t.T; z += G) {
+    const int n = p.term_node[t.term_off + z];
+    const int face = p.term_node[t.term_off + t.T + z] % p.F;
+    const real* ro = d2_reach_row(slot, bel, parent, n, lv.n1e, 1 - trav, rp, H);
+    real cnt[kMaxBins];
+#pragma unroll
+    for (int m = 0; m < kMaxBins; ++m) cnt[m] = 0;
+    real tot = 0;
+    for (int g = 0; g < H; ++g) {
+      const real r = ro[g];
+      const int mg = (int)p.matches[g * p.F + face];
+      tot += r;
+#pragma unroll
+      for (int m = 0; m < kMaxBins; ++m) cnt[m] += (m == mg) ? r : (real)0;
+    }
+#pragma unroll
+    for (int m = kMaxBins - 2; m >= 0; --m) cnt[m] += cnt[m + 1];
+#pragma unroll
+    for (int m = 0; m < kMaxBins; ++m) hist[z * (kMaxBins + 1) + m] = cnt[m];
+    hist[z * (kMaxBins + 1) + kMaxBins] = tot;
+  }
+  __syncwarp();
+  for (int it = lane; it < t.T * H; it += G) {
+    const int z = it / H, h = it % H;
+    const int pbid = p.term_node[t.term_off + t.T + z];
+    const int ndepth = p.term_node[t.term_off + 2 * t.T + z];
+    const int quantity = 1 + pbid / p.F, face = pbid % p.F;
+    int left = quantity - (int)p.matches[h * p.F + face];
+    left = left < 0 ? 0 : (left > kMaxBins - 1 ? kMaxBins - 1 : left);
+    const real win = hist[z * (kMaxBins + 1) + left], tot = hist[z * (kMaxBins + 1) + kMaxBins];
+    const real v = (real)(float)win * 2 - tot;
+    const int pl = rp ^ (ndepth & 1);
+    vt[z * H + h] = (pl != trav) ? -v : v;
+  }
+}
+
+// Scratch of a d2 group (reals): slot[nh_max] | bel[2*H] | hist[tmp_reals] | lsum[2*Lmax]
+template <typename real, int HC>
+__global__ void __launch_bounds__(256, 4) cfr_iter_d2_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* smem = reinterpret_cast<real*>(smem_raw);
+  const int groups_per_cta = blockDim.x / 32;
+  const int gid = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int k = blockIdx.x * groups_per_cta + gid;
+  if (k >= *p.wave_n) return;
+  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
+  const int H = HC > 0 ? HC : p.H;
+  real* slot = smem + (size_t)gid * scratch_per_group;
+  real* bel = slot + p.nh_max; real* hist = bel + 2 * H; real* lsum = hist + p.tmp_reals;
+  for (int i = lane; i < 2 * H; i += 32) bel[i] = p.beliefs[(size_t)k * 2 * H + i];
+  __syncwarp();
+  const int tb = (iter - 1) & 1;
+  const int rp = p.sg_player[k];
+  if (do_b) cfr_backward_d2<real, HC>(p, k, tb, slot, bel, lane);
+  // sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
+  if (p.sg_act_iter[k] == iter) {
+    const real* Sg = p.Sg + (size_t)k * p.table_stride;
+    real* __restrict__ Sn = p.Snap + (size_t)k * p.table_stride;
+    for (int i = lane; i < (t.N - 1) * H; i += 32) Sn[i] = Sg[i];
+  }
+  if (do_f) cfr_forward_d2<real, HC>(p, k, iter & 1, slot, bel, do_b ? (tb == rp ? 0 : 1) : -1, lsum, hist, lane);
+}
+
 // Wave initialisation == CFR constructor (subgame_solving.cc:509-524): uniform last strategy, zero regrets,
 // sum = uniform * reach-under-uniform of the acting player (get_uniform_reach_weigted_strategy :125-149).
 template <typename real, int G>

@@ -47,6 +47,9 @@ struct CfrDev {
 __host__ __device__ inline int cfr_tmp_reals(int N, int H, int L, int T) { (void)N; (void)H; (void)L; return 10 * (T > 0 ? T : 1); }
 __host__ __device__ inline int cfr_scratch_reals(int N, int H, int L, int T) { return 2 * N * H + cfr_tmp_reals(N, H, L, T) + 2 * (L > 0 ? L : 1); }
 
+// Depth <= 2 kernel (cfr_iter_d2_kernel): slot[N*H] | bel[2*H] | hist[10*T] | lsum[2*L]
+__host__ __device__ inline int cfr_scratch_reals_d2(int N, int H, int L, int T) { return N * H + 2 * H + cfr_tmp_reals(N, H, L, T) + 2 * (L > 0 ? L : 1); }
+
 // Launchers implemented in cfr_kernels.cu (explicitly instantiated for float and double).  `group` is 32 (one warp per
 // subgame, shared-memory scratch) or 256 (one CTA per subgame, global scratch).
 template <typename real> cudaError_t cfr_configure(int group, int smem_bytes);
@@ -54,5 +57,9 @@ template <typename real> void cfr_launch_init(const CfrDev<real>& p, int group, 
                                               int scratch_per_group);
 template <typename real> void cfr_launch_iter(const CfrDev<real>& p, int group, int blocks, int threads, size_t smem, cudaStream_t st,
                                               int iter, int do_b, int do_f, int scratch_per_group);
+// Depth <= 2 specialisation (warp per subgame, half the scratch); threads must be a multiple of 32 and <= 256.
+template <typename real> cudaError_t cfr_configure_d2(int smem_bytes);
+template <typename real> void cfr_launch_iter_d2(const CfrDev<real>& p, int blocks, int threads, size_t smem, cudaStream_t st, int iter,
+                                                 int do_b, int do_f, int scratch_per_group);
 
 }  // namespace cfrb

@@ -18,6 +18,7 @@
 #include "leaf_mlp_tc.cuh"
 
 namespace {
+inline bool is_tc(int net_mode) { return net_mode == CFRB_NET_TC_F16 || net_mode == CFRB_NET_TC_F16X2; }
 
 thread_local std::string g_err;
 
@@ -70,6 +71,11 @@ struct cfrb_handle {
   int group = 32;          // threads per subgame group (32 = warp, 256 = CTA with global scratch)
   int groups_per_cta = 8;
   int scratch_per_group = 0;  // reals
+  // depth <= 2 kernel (all templates have at most three levels): own scratch layout and CTA shape
+  bool d2 = false;
+  int max_levels = 0;
+  int d2_groups_per_cta = 8;
+  int d2_scratch_per_group = 0;
   int table_stride = 0;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
@@ -87,6 +93,7 @@ struct cfrb_handle {
   DevBuf<int> d_wave;      // [0] = n, [1] = rows
   DevBuf<int> d_sg_tmpl, d_sg_player, d_sg_row_off, d_sg_act, d_steps;
   DevBuf<float> d_X, d_out, d_dbg;
+  long long* dbg_trace = nullptr;   // set only inside cfrb_debug_net_trace
   DevBuf<__half> d_Xh;
   WaveState<float> sf;
   WaveState<double> sd;
@@ -133,6 +140,16 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
     h->groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(16, budget / per_group_bytes));
     const int smem_bytes = (int)(per_group_bytes * h->groups_per_cta);
     CK(cfrb::cfr_configure<real>(32, smem_bytes));
+    const char* no_d2 = std::getenv("CFRB_NO_D2");
+    if (h->max_levels <= 3 && !(no_d2 && *no_d2 == '1')) {
+      // 4 CTAs of up to 8 warps per SM (register file: 64 registers x 32 warps), each with 1 KB reserved by the runtime
+      h->d2 = true;
+      h->d2_scratch_per_group = cfrb::cfr_scratch_reals_d2(h->Nmax, h->g.H, h->Lmax, h->Tmax);
+      const size_t d2_bytes = (size_t)h->d2_scratch_per_group * sizeof(real);
+      const size_t cta_budget = ((size_t)228 * 1024 - 4 * 1024) / 4;
+      h->d2_groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(8, cta_budget / d2_bytes));
+      CK(cfrb::cfr_configure_d2<real>((int)(d2_bytes * h->d2_groups_per_cta)));
+    }
   } else {
     h->group = 256;
     h->groups_per_cta = 1;
@@ -148,7 +165,7 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   d.R = s.R.p; d.Sg = s.Sg.p; d.S = s.S.p; d.Snap = s.Snap.p; d.table_stride = h->table_stride;
   d.vterm = s.vterm.p; d.vterm_stride = std::max(h->Tmax, 1) * g.H;
   d.X = h->cfg.net_mode == CFRB_NET_FP32 ? h->d_X.p : nullptr;
-  d.Xh = h->cfg.net_mode == CFRB_NET_TC_F16 ? h->d_Xh.p : nullptr;
+  d.Xh = is_tc(h->cfg.net_mode) ? h->d_Xh.p : nullptr;
   d.net_out = h->d_out.p; d.scaler = s.scaler.p;
   d.scratch = h->group == 32 ? nullptr : s.scratch.p; d.scratch_stride = h->scratch_per_group;
   d.nh_max = h->Nmax * g.H; d.tmp_reals = cfrb::cfr_tmp_reals(h->Nmax, g.H, h->Lmax, h->Tmax);
@@ -172,9 +189,15 @@ static int launch_init_t(cfrb_handle* h, cudaStream_t st) {
 template <typename real>
 static int launch_iter_t(cfrb_handle* h, cudaStream_t st, int iter, int do_b, int do_f) {
   auto& s = state_of<real>(h);
-  const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
-  const size_t smem = h->group == 32 ? (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta : 0;
-  cfrb::cfr_launch_iter<real>(s.dev, h->group, blocks, 32 * h->groups_per_cta, smem, st, iter, do_b, do_f, h->scratch_per_group);
+  if (h->d2) {
+    const int blocks = (h->n + h->d2_groups_per_cta - 1) / h->d2_groups_per_cta;
+    const size_t smem = (size_t)h->d2_scratch_per_group * sizeof(real) * h->d2_groups_per_cta;
+    cfrb::cfr_launch_iter_d2<real>(s.dev, blocks, 32 * h->d2_groups_per_cta, smem, st, iter, do_b, do_f, h->d2_scratch_per_group);
+  } else {
+    const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
+    const size_t smem = h->group == 32 ? (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta : 0;
+    cfrb::cfr_launch_iter<real>(s.dev, h->group, blocks, 32 * h->groups_per_cta, smem, st, iter, do_b, do_f, h->scratch_per_group);
+  }
   ++h->launches;
   CK(cudaGetLastError());
   return CFRB_OK;
@@ -355,7 +378,7 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   CK(cudaSetDevice(cfg->device));
   if (cfg->num_dice < 1 || cfg->num_faces < 1 || cfg->max_depth < 1 || cfg->max_subgames < 1)
     return fail(CFRB_EINVAL, "num_dice, num_faces, max_depth, max_subgames must be >= 1");
-  if (cfg->net_mode < CFRB_NET_ZERO || cfg->net_mode > CFRB_NET_TC_F16) return fail(CFRB_EINVAL, "bad net_mode");
+  if (cfg->net_mode < CFRB_NET_ZERO || cfg->net_mode > CFRB_NET_TC_F16X2) return fail(CFRB_EINVAL, "bad net_mode");
   if (cfg->state_dtype != CFRB_STATE_F64 && cfg->state_dtype != CFRB_STATE_F32) return fail(CFRB_EINVAL, "bad state_dtype");
   if (cfg->net_mode != CFRB_NET_ZERO && cfg->hidden != 256) return fail(CFRB_EINVAL, "only hidden == 256 is built");
   h->f64 = cfg->state_dtype == CFRB_STATE_F64;
@@ -389,6 +412,7 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     term_node.insert(term_node.end(), t.term_node.begin(), t.term_node.end());
     for (int n : t.term_node) term_node.push_back(t.last_bid[t.parent[n]]);   // challenged bid
     for (int n : t.term_node) term_node.push_back(t.depth[n]);
+    h->max_levels = std::max(h->max_levels, t.levels);
     h->Nmax = std::max(h->Nmax, t.N); h->Lmax = std::max(h->Lmax, t.L); h->Tmax = std::max(h->Tmax, t.T);
   }
   std::vector<unsigned char> matches((size_t)g.H * g.F);
@@ -421,7 +445,7 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   CK(h->d_out.alloc(rows_cap * h->Hout));
   CK(cudaMemset(h->d_wave.p, 0, 2 * sizeof(int)));
   CK(cudaMemset(h->d_out.p, 0, rows_cap * h->Hout * sizeof(float)));
-  if (cfg->net_mode == CFRB_NET_TC_F16) {
+  if (is_tc(cfg->net_mode)) {
     if (g.H > cfrb::tc::kNout) return fail(CFRB_EINVAL, "CFRB_NET_TC_F16 supports num_hands <= 16");
     const size_t tiles = (rows_cap + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
     CK(h->d_Xh.alloc(tiles * cfrb::tc::kTileM * h->Qpad));
@@ -429,8 +453,10 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     CK(h->d_dbg.alloc(2 * cfrb::tc::kTileM * cfrb::tc::kHid));
     const cfrb::tc::BlobLayout L(h->Qpad);
     if (L.smem_bytes > max_optin) return fail(CFRB_EINVAL, "tensor-core value net does not fit shared memory for this game shape");
-    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
-    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
   }
   CK(cudaFuncSetAttribute(cfrb::leaf_mlp_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)cfrb::leaf_mlp_fp32_smem(256)));
@@ -502,7 +528,7 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
   const float* w3 = be2 + hid; const float* b3 = w3 + (size_t)H * hid;
   // ordered after work already enqueued on the handle's stream (ModelLocker::updateModel waits for in-flight forwards)
   CK(cudaStreamSynchronize(h->own_stream));
-  if (h->cfg.net_mode == CFRB_NET_TC_F16) {
+  if (is_tc(h->cfg.net_mode)) {
     // tensor-core blob: fp16 weights in UMMA K-major core-matrix order + fp32 {bias, gamma, beta} per feature
     const cfrb::tc::BlobLayout L(Qp);
     std::vector<uint8_t> blob(L.blob_bytes, 0);
@@ -610,12 +636,20 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
     }
     CK(cudaEventRecord(h->net_ev[h->net_ev_used], st));
   }
-  if (h->cfg.net_mode == CFRB_NET_TC_F16) {
+  if (is_tc(h->cfg.net_mode)) {
     const cfrb::tc::BlobLayout L(h->Qpad);
-    cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, dbg1, dbg2};
+    cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, dbg1, dbg2, nullptr};
     const int tiles = (h->rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
-    if (dbg1 || dbg2) cfrb::tc::leaf_mlp_tc_kernel<true><<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
-    else cfrb::tc::leaf_mlp_tc_kernel<false><<<std::min(tiles, h->num_sms), cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+    const int grid = std::min(tiles, h->num_sms);
+    const bool x2 = h->cfg.net_mode == CFRB_NET_TC_F16X2;
+    a.trace = h->dbg_trace;
+    if (dbg1 || dbg2 || a.trace) {
+      if (x2) cfrb::tc::leaf_mlp_tc_kernel<true, true><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+      else cfrb::tc::leaf_mlp_tc_kernel<true, false><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+    } else {
+      if (x2) cfrb::tc::leaf_mlp_tc_kernel<false, true><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+      else cfrb::tc::leaf_mlp_tc_kernel<false, false><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+    }
   } else {
     const int blocks = (h->rows + cfrb::kMlpRows - 1) / cfrb::kMlpRows;
     cfrb::leaf_mlp_fp32_kernel<256><<<blocks, 256, cfrb::leaf_mlp_fp32_smem(256), st>>>(h->net, h->d_X.p, h->d_wave.p + 1, h->d_out.p);
@@ -737,7 +771,7 @@ int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, double* s
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
   const int rows = std::min<int>(h->rows, cap_rows), Q = h->g.Q;
-  if (rows > 0 && queries && h->cfg.net_mode == CFRB_NET_TC_F16) {
+  if (rows > 0 && queries && is_tc(h->cfg.net_mode)) {
     const int tiles = (rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
     std::vector<__half> x((size_t)tiles * cfrb::tc::kTileM * h->Qpad);
     CK(cudaMemcpy(x.data(), h->d_Xh.p, x.size() * sizeof(__half), cudaMemcpyDeviceToHost));
@@ -762,8 +796,29 @@ int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, double* s
   return h->rows;
 }
 
+int cfrb_debug_net_trace(cfrb_handle* h, long long* out, int n) {
+  if (!h || !is_tc(h->cfg.net_mode)) return fail(CFRB_EINVAL, "trace exists only for the tensor-core value net");
+  if (!h->have_weights || h->rows == 0) return fail(CFRB_ESTATE, "no weights or no leaf rows");
+  if (n < 2048) return fail(CFRB_EINVAL, "trace buffer must hold 2048 stamps");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  long long* d = nullptr;
+  CK(cudaMalloc(&d, 2048 * sizeof(long long)));
+  CK(cudaMemset(d, 0, 2048 * sizeof(long long)));
+  const int prof = h->profiling;
+  h->profiling = 0;
+  h->dbg_trace = d;
+  int rc = launch_net(h, h->own_stream, nullptr, nullptr);
+  h->dbg_trace = nullptr;
+  h->profiling = prof;
+  if (!rc && cudaStreamSynchronize(h->own_stream) != cudaSuccess) rc = fail(CFRB_ECUDA, "trace launch failed");
+  if (!rc) cudaMemcpy(out, d, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return rc;
+}
+
 int cfrb_debug_net_taps(cfrb_handle* h, float* d1, float* d2) {
-  if (!h || h->cfg.net_mode != CFRB_NET_TC_F16) return fail(CFRB_EINVAL, "taps exist only for CFRB_NET_TC_F16");
+  if (!h || !is_tc(h->cfg.net_mode)) return fail(CFRB_EINVAL, "taps exist only for CFRB_NET_TC_F16");
   if (!h->have_weights || h->rows == 0) return fail(CFRB_ESTATE, "no weights or no leaf rows");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());

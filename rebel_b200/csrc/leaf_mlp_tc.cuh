@@ -31,6 +31,7 @@ constexpr int kNout = 16;                 // output features padded to the minim
 constexpr int kParts = 4;                    // column quarters per row
 constexpr int kColsPerThread = kHid / kParts;   // 64
 constexpr int kEpiThreads = 128 * kParts;    // 16 epilogue warps
+constexpr int kSubChunks = 4;                // A-operand hand-over granularity: 16 features per thread
 constexpr int kThreads = kEpiThreads + 32;   // + allocator / MMA-issuer warp
 constexpr uint32_t kColD = 0, kColA = 256, kColD3 = 384, kTmemCols = 512;
 
@@ -51,7 +52,7 @@ struct BlobLayout {
     off_x = (blob_bytes + 127) / 128 * 128;
     off_part = off_x + kTileM * kp * 2;       // LayerNorm partial sums: [2 layers][kParts][128 rows] float2
     off_bar = off_part + 2 * kParts * kTileM * 8;
-    smem_bytes = off_bar + 64;
+    smem_bytes = off_bar + 192;            // 16 mbarriers + TMEM base slot
   }
 };
 
@@ -136,6 +137,11 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])                                              \
       : "memory")
 
+#define CFRB_TMEM_ST8(taddr, v)                                                                                           \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),  \
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])                                           \
+               : "memory")
+
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -153,14 +159,29 @@ __device__ __forceinline__ float gelu_tc(float y) {
   return y * r;
 }
 
+// The same function on a packed pair of fp16 values: y * Phi(y) = hy + hy * tanh(y (c0 + c1 y^2 + c2 y^4)), hy = y / 2, with
+// HFMA2 arithmetic and one tanh.approx.f16x2 per pair (a quarter of the MUFU work and ~40 % of the instructions of gelu_tc).
+// The fp16 evaluation adds ~1.8e-4 rms (N(0,1) inputs) to the 1.4e-4 rms of rounding the activation to fp16 at all.
+__device__ __forceinline__ uint32_t gelu_tc_x2(float y0, float y1) {
+  const __half2 y = __floats2half2_rn(y0, y1);
+  const __half2 y2 = __hmin2(__hmul2(y, y), __float2half2_rn(52.f));
+  const __half2 p = __hfma2(y2, __hfma2(y2, __float2half2_rn(-3.5151e-4f), __float2half2_rn(3.70057e-2f)), __float2half2_rn(0.797496f));
+  const __half2 u = __hmul2(y, p);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 hy = __hmul2(y, __float2half2_rn(0.5f));
+  const __half2 g = __hfma2(hy, *reinterpret_cast<const __half2*>(&t), hy);
+  return *reinterpret_cast<const uint32_t*>(&g);
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // LayerNorm(eps 1e-5) + GELU of this thread's quarter row: 64 fp32 accumulators (TMEM lane = row, columns part*64..),
 // bias already added by the tensor cores, kept in registers; the four threads of a row exchange (sum, sum of squares)
 // through `part`.  Result as fp16 into the A-operand columns.  ln: float2 {gamma, beta} per feature in smem (broadcast reads).
-template <bool kDebug>
+template <bool kDebug, bool kGeluX2>
 __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id, int row, const float2* __restrict__ ln, float2* part,
-                                                 float* dbg_row) {
+                                                 uint32_t bar_a0, uint32_t bar_dfree, float* dbg_row, long long* tr) {
   uint32_t xr[kColsPerThread];
   {
     uint32_t* lo = xr; uint32_t* hi = xr + 32;
@@ -168,6 +189,7 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
     CFRB_TMEM_LD32(tmem_row + kColD + part_id * kColsPerThread + 32, hi);
     tmem_wait_ld();
   }
+  if (kDebug && tr) tr[0] = clock64();
   float sum = 0.f, sumsq = 0.f;
 #pragma unroll
   for (int i = 0; i < kColsPerThread; ++i) {
@@ -177,7 +199,14 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
     sumsq = fmaf(xv, xv, sumsq);
   }
   part[part_id * kTileM + row] = make_float2(sum, sumsq);
+  if (kDebug && tr) tr[1] = clock64();
   named_bar_sync(1, kEpiThreads);
+  // every accumulator of the tile now lives in registers: the D columns may be overwritten (next tile's layer 1)
+  if (bar_dfree) {
+    tc_fence_before();
+    mbar_arrive(bar_dfree);
+  }
+  if (kDebug && tr) tr[2] = clock64();
   sum = 0.f; sumsq = 0.f;
 #pragma unroll
   for (int p = 0; p < kParts; ++p) {          // fixed order: all four threads of a row get bit-identical statistics
@@ -188,21 +217,31 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
   const float var = fmaxf(sumsq * (1.f / kHid) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float shift = -mean * rstd;
+  // Four sub-chunks of 16 features: sub-chunk s of column quarter q is K-step 4q+s of the next layer's MMA, so after the
+  // s-th arrival of all epilogue threads the issuer can run K-steps {s, 4+s, 8+s, 12+s} while the rest is still being
+  // normalised (only the last quarter of the MMA stays exposed).
 #pragma unroll
-  for (int c = 0; c < kColsPerThread / 32; ++c) {
-    uint32_t pk[16];
+  for (int c = 0; c < kSubChunks; ++c) {
+    uint32_t pk[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int j = c * 32 + 2 * i;
+    for (int i = 0; i < 8; ++i) {
+      const int j = c * 16 + 2 * i;
       const float4 pp = *reinterpret_cast<const float4*>(ln + part_id * kColsPerThread + j);   // {gamma_j, beta_j, gamma_j+1, beta_j+1}
       const float y0 = fmaf(fmaf(__uint_as_float(xr[j]), rstd, shift), pp.x, pp.y);
       const float y1 = fmaf(fmaf(__uint_as_float(xr[j + 1]), rstd, shift), pp.z, pp.w);
-      const __half2 h = __floats2half2_rn(gelu_tc(y0), gelu_tc(y1));
-      pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+      if (kGeluX2) {
+        pk[i] = gelu_tc_x2(y0, y1);
+      } else {
+        const __half2 h = __floats2half2_rn(gelu_tc(y0), gelu_tc(y1));
+        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
     }
-    CFRB_TMEM_ST16(tmem_row + kColA + part_id * (kColsPerThread / 2) + c * 16, pk);
+    CFRB_TMEM_ST8(tmem_row + kColA + part_id * (kColsPerThread / 2) + c * 8, pk);
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(bar_a0 + 8 * c);
   }
-  tmem_wait_st();
+  if (kDebug && tr) tr[3] = clock64();
 }
 
 struct TcArgs {
@@ -213,9 +252,16 @@ struct TcArgs {
   int Kp, H, Hout;
   float* dbg_d1;            // optional [128][256] raw layer-1 accumulators of tile 0
   float* dbg_d2;            // optional [128][256] raw layer-2 accumulators of tile 0
+  long long* trace;         // optional (debug build only): SM clock stamps of CTA 0, [2048]: epilogue thread 0 at
+                            // [iter*16 + e], MMA thread at [1024 + iter*8 + m]
 };
 
-template <bool kDebug>
+#define CFRB_TRACE(slot)                                                      \
+  do {                                                                        \
+    if (kDebug && a.trace && blockIdx.x == 0 && it_no < 60) a.trace[slot] = clock64(); \
+  } while (0)
+
+template <bool kDebug, bool kGeluX2>
 __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
   constexpr int kMmaWarp = kEpiThreads / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -226,9 +272,10 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
   if ((int)blockIdx.x >= ntiles) return;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  // bars: 0 x, 1 d1, 2 d2, 3 d3, 4 dfree, 8..11 a2[sub-chunk], 12..15 a3[sub-chunk]
   const uint32_t bar_x = smem_u32(bars + 0), bar_d1 = smem_u32(bars + 1), bar_d2 = smem_u32(bars + 2), bar_d3 = smem_u32(bars + 3),
-                 bar_a2 = smem_u32(bars + 4), bar_a3 = smem_u32(bars + 5);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+                 bar_dfree = smem_u32(bars + 4), bar_a2 = smem_u32(bars + 8), bar_a3 = smem_u32(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   // ---- one-time setup: weights -> smem, barriers, TMEM
   {
@@ -238,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
   }
   if (tid == 0) {
     mbar_init(bar_x, kEpiThreads); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_d3, 1);
-    mbar_init(bar_a2, kEpiThreads); mbar_init(bar_a3, kEpiThreads);
+    mbar_init(bar_dfree, kEpiThreads);
+    for (int c = 0; c < kSubChunks; ++c) { mbar_init(bar_a2 + 8 * c, kEpiThreads); mbar_init(bar_a3 + 8 * c, kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -260,27 +308,55 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
     if (lane == 0) {
       const uint32_t idesc256 = make_idesc(kTileM, kHid), idesc16 = make_idesc(kTileM, kNout);
       const uint32_t lbo_x = (kTileM / 8) * 128, lbo_w = (kHid / 8) * 128, lbo_w3 = (kNout / 8) * 128;
+      // Layer 1 of tile n+1 is issued inside iteration n, as soon as the epilogue warps hold tile n's layer-2 accumulators in
+      // registers (dfree) — the D columns are free then and the tensor pipe would otherwise idle through epilogue 2.
+      mbar_wait(bar_x, 0);
+      tc_fence_after();
+      for (int k = 0; k < a.Kp / 16; ++k)
+        mma_ss(tmem_base + kColD, make_desc(sx + k * 2 * lbo_x, lbo_x, 128), make_desc(sw1 + k * 2 * lbo_w, lbo_w, 128), idesc256, k > 0);
+      tc_commit(bar_d1);
       uint32_t parity = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
-        // layer 1: D1 = X * W1^T
-        mbar_wait(bar_x, parity);
-        tc_fence_after();
-        for (int k = 0; k < a.Kp / 16; ++k)
-          mma_ss(tmem_base + kColD, make_desc(sx + k * 2 * lbo_x, lbo_x, 128), make_desc(sw1 + k * 2 * lbo_w, lbo_w, 128), idesc256, k > 0);
-        tc_commit(bar_d1);
-        // layer 2: D2 = ones * bias2^T + A2 * W2^T  (A from TMEM: 16 fp16 = 8 columns per K step)
-        mbar_wait(bar_a2, parity);
-        tc_fence_after();
-        mma_ss(tmem_base + kColD, make_desc(sones, lbo_x, 128), make_desc(sbias2, lbo_w, 128), idesc256, 0);
-        for (int k = 0; k < kHid / 16; ++k)
-          mma_ts(tmem_base + kColD, tmem_base + kColA + k * 8, make_desc(sw2 + k * 2 * lbo_w, lbo_w, 128), idesc256, 1);
+      int it_no = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1, ++it_no) {
+        // layer 2: D2 = ones * bias2^T + A2 * W2^T  (A from TMEM: 16 fp16 = 8 columns per K step), K-steps in the order the
+        // epilogue hands them over
+        for (int c = 0; c < kSubChunks; ++c) {
+          mbar_wait(bar_a2 + 8 * c, parity);
+          tc_fence_after();
+          if (c == 0) {
+            CFRB_TRACE(1024 + it_no * 8 + 2);
+            mma_ss(tmem_base + kColD, make_desc(sones, lbo_x, 128), make_desc(sbias2, lbo_w, 128), idesc256, 0);
+          }
+          for (int q = 0; q < kParts; ++q) {
+            const int k = q * kSubChunks + c;
+            mma_ts(tmem_base + kColD, tmem_base + kColA + k * 8, make_desc(sw2 + k * 2 * lbo_w, lbo_w, 128), idesc256, 1);
+          }
+        }
         tc_commit(bar_d2);
+        CFRB_TRACE(1024 + it_no * 8 + 3);
+        // layer 1 of the next tile
+        if (tile + (int)gridDim.x < ntiles) {
+          mbar_wait(bar_dfree, parity);
+          mbar_wait(bar_x, parity ^ 1);
+          tc_fence_after();
+          CFRB_TRACE(1024 + it_no * 8 + 0);
+          for (int k = 0; k < a.Kp / 16; ++k)
+            mma_ss(tmem_base + kColD, make_desc(sx + k * 2 * lbo_x, lbo_x, 128), make_desc(sw1 + k * 2 * lbo_w, lbo_w, 128), idesc256, k > 0);
+          tc_commit(bar_d1);
+          CFRB_TRACE(1024 + it_no * 8 + 1);
+        }
         // layer 3: D3 = A3 * W3^T  (N = 16)
-        mbar_wait(bar_a3, parity);
-        tc_fence_after();
-        for (int k = 0; k < kHid / 16; ++k)
-          mma_ts(tmem_base + kColD3, tmem_base + kColA + k * 8, make_desc(sw3 + k * 2 * lbo_w3, lbo_w3, 128), idesc16, k > 0);
+        for (int c = 0; c < kSubChunks; ++c) {
+          mbar_wait(bar_a3 + 8 * c, parity);
+          tc_fence_after();
+          if (c == 0) CFRB_TRACE(1024 + it_no * 8 + 4);
+          for (int q = 0; q < kParts; ++q) {
+            const int k = q * kSubChunks + c;
+            mma_ts(tmem_base + kColD3, tmem_base + kColA + k * 8, make_desc(sw3 + k * 2 * lbo_w3, lbo_w3, 128), idesc16, (c | q) != 0);
+          }
+        }
         tc_commit(bar_d3);
+        CFRB_TRACE(1024 + it_no * 8 + 5);
       }
     }
   } else {
@@ -303,20 +379,22 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
       mbar_arrive(bar_x);
     }
     uint32_t parity = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+    int it_no = tid == 0 ? 0 : 1 << 20;     // only thread 0 leaves trace stamps
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1, ++it_no) {
       const int next = tile + gridDim.x;
       const bool dbg = (tile == 0);
       // ---- layer-1 accumulators ready; the query tile in smem is free again -> start fetching the next one
       mbar_wait(bar_d1, parity);
       tc_fence_after();
+      CFRB_TRACE(it_no * 16 + 0);
       if (next < ntiles) {
         const int4* xsrc = reinterpret_cast<const int4*>(a.Xh) + (size_t)next * x_tile_int4;
         xr0 = __ldg(xsrc + tid);
         if (tid + kEpiThreads < x_items) xr1 = __ldg(xsrc + tid + kEpiThreads);
       }
-      epilogue_ln_gelu<kDebug>(tmem_row, part_id, row_in_tile, ln1, part1, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr);
-      tc_fence_before();
-      mbar_arrive(bar_a2);
+      epilogue_ln_gelu<kDebug, kGeluX2>(tmem_row, part_id, row_in_tile, ln1, part1, bar_a2, 0u, (dbg && a.dbg_d1) ? a.dbg_d1 + row_in_tile * kHid : nullptr,
+                                        (kDebug && a.trace && blockIdx.x == 0 && it_no < 60) ? a.trace + it_no * 16 + 7 : nullptr);
+      CFRB_TRACE(it_no * 16 + 1);
       if (next < ntiles) {
         xdst[tid] = xr0;
         if (tid + kEpiThreads < x_items) xdst[tid + kEpiThreads] = xr1;
@@ -324,14 +402,18 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
         mbar_arrive(bar_x);
       }
       // ---- layer 2
+      CFRB_TRACE(it_no * 16 + 2);
       mbar_wait(bar_d2, parity);
       tc_fence_after();
-      epilogue_ln_gelu<kDebug>(tmem_row, part_id, row_in_tile, ln2, part2, (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr);
-      tc_fence_before();
-      mbar_arrive(bar_a3);
+      CFRB_TRACE(it_no * 16 + 3);
+      epilogue_ln_gelu<kDebug, kGeluX2>(tmem_row, part_id, row_in_tile, ln2, part2, bar_a3, next < ntiles ? bar_dfree : 0u,
+                                        (dbg && a.dbg_d2) ? a.dbg_d2 + row_in_tile * kHid : nullptr,
+                                        (kDebug && a.trace && blockIdx.x == 0 && it_no < 60) ? a.trace + it_no * 16 + 11 : nullptr);
+      CFRB_TRACE(it_no * 16 + 4);
       // ---- layer 3: raw net outputs (the CFR backward kernel multiplies by the opponent-reach scaler)
       mbar_wait(bar_d3, parity);
       tc_fence_after();
+      CFRB_TRACE(it_no * 16 + 5);
       if (part_id == 0) {
         uint32_t v[16];
         CFRB_TMEM_LD16(tmem_row + kColD3, v);
@@ -343,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc_kernel(TcArgs a) {
           for (int h = 0; h < kNout; ++h) if (h < a.H) o[h] = __uint_as_float(v[h]) + b3[h];
         }
       }
+      CFRB_TRACE(it_no * 16 + 6);
       tc_fence_before();   // order this tile's TMEM reads before the next tile's MMAs (via the a2/a3/x arrivals that follow)
     }
   }

@@ -47,7 +47,7 @@ def main(argv=None):
     ap.add_argument("--no_linear", action="store_true")
     ap.add_argument("--batch_repeats", type=int, default=64)
     ap.add_argument("--wave_capacity", type=int, default=8192)
-    ap.add_argument("--net_mode", type=int, default=None, help="0 zero, 1 fp32 SIMT, 2 tcgen05 fp16 (default with --net)")
+    ap.add_argument("--net_mode", type=int, default=None, help="0 zero, 1 fp32 SIMT, 2 tcgen05 fp16, 3 tcgen05 fp16 + packed-half GELU (default with --net)")
     ap.add_argument("--random_net_seed", type=int, default=None, help="use a random-init Net2 (benchmarks)")
     args = ap.parse_args(argv)
 
@@ -67,7 +67,7 @@ def main(argv=None):
         weights = torch.from_numpy(flatten_state_dict(sd))
     elif args.random_net_seed is not None:
         weights = torch.from_numpy(flatten_state_dict(make_selfplay_net(args.num_dice, args.num_faces, seed=args.random_net_seed).state_dict()))
-    net_mode = args.net_mode if args.net_mode is not None else (2 if weights is not None else 0)
+    net_mode = args.net_mode if args.net_mode is not None else (3 if weights is not None else 0)
 
     cfg = rela.RecursiveSolvingParams()
     cfg.num_dice, cfg.num_faces = args.num_dice, args.num_faces

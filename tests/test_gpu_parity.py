@@ -46,7 +46,9 @@ def steps_after(c):
 # value-noise level of a configuration: what one step may differ from the fp64 oracle in a node value
 def noise_level(rb, state, net):
     if net == rb.NET_TC_F16:
-        return 1e-5          # fp16 operands: ~1e-3 relative on net outputs of scale 1e-2
+        return 1e-5          # fp16 operands: ~5e-4 rms relative on net outputs of scale 1e-2
+    if net == rb.NET_TC_F16X2:
+        return 1.5e-5        # + GELU on packed fp16 pairs: ~8e-4 rms relative (scripts/gelu_probe.py)
     if state == rb.STATE_F32:
         return 4e-7
     if net == rb.NET_FP32:
@@ -100,18 +102,19 @@ def conditioning(tree, R_next, trav, noise):
     return tol, path_tol
 
 
-CONFIGS = [("f64", "zero"), ("f64", "fp32"), ("f32", "zero"), ("f32", "fp32"), ("f64", "tc")]
+CONFIGS = [("f64", "zero"), ("f64", "fp32"), ("f32", "zero"), ("f32", "fp32"), ("f64", "tc"), ("f64", "tcx2")]
+NETS = lambda rb: {"zero": rb.NET_ZERO, "fp32": rb.NET_FP32, "tc": rb.NET_TC_F16, "tcx2": rb.NET_TC_F16X2}
 
 
 @pytest.mark.parametrize("D,F", SHAPES)
 @pytest.mark.parametrize("state_name,net_name", CONFIGS)
 @pytest.mark.parametrize("max_depth", [2, 3])
 def test_teacher_forced_single_step(rb, port, net_weights, D, F, state_name, net_name, max_depth):
-    if net_name == "tc" and max_depth != 2:
+    if net_name in ("tc", "tcx2") and max_depth != 2:
         pytest.skip("tensor-core net is exercised on the data-generation depth")
     A, H, Q = game_dims(D, F)
     state = {"f64": rb.STATE_F64, "f32": rb.STATE_F32}[state_name]
-    net = {"zero": rb.NET_ZERO, "fp32": rb.NET_FP32, "tc": rb.NET_TC_F16}[net_name]
+    net = NETS(rb)[net_name]
     noise = noise_level(rb, state, net)
     # fp32 tables + value net: the reference's 1e-80 smoothing cannot be represented, so the query of a leaf reached with zero
     # probability carries uniform beliefs instead of the reference's epsilon mixture and the net output there differs at
@@ -174,7 +177,7 @@ def test_teacher_forced_single_step(rb, port, net_weights, D, F, state_name, net
                 assert (dS[ok] <= tol[n][ok] + path_tol[n][ok] + 10 * noise).all(), (tag, "sum", n, dS, tol[n], path_tol[n])
             if net != rb.NET_ZERO and o["queries"].shape[1]:
                 q, out, sc = S.leaf_io()
-                qtol = 1e-3 if net == rb.NET_TC_F16 else 2e-6        # fp16 query rows: 2^-11 relative on values <= 1
+                qtol = 1e-3 if net in (rb.NET_TC_F16, rb.NET_TC_F16X2) else 2e-6        # fp16 query rows: 2^-11 relative on values <= 1
                 dq = np.abs(q - o["queries"][ci + 1])
                 lv = np.abs(out * sc[:, None] - o["leaf_values"][ci + 1])
                 if state == rb.STATE_F32:
@@ -243,14 +246,17 @@ def test_zero_net_trajectories_bit_exact_vs_reference(rb, golden, D, F):
 
 # ---------------------------------------------------------------------------------------------- P4
 @pytest.mark.parametrize("D,F", SHAPES)
-@pytest.mark.parametrize("net_name", ["fp32", "tc"])
+@pytest.mark.parametrize("net_name", ["fp32", "tc", "tcx2"])
 def test_long_horizon_within_reference_noise(rb, golden, net_weights, D, F, net_name):
     """1024 iterations with the Net2 value net: root value means vs the reference.  The reference moves by mean 2.1e-4 /
     max 2.8e-3 under a ONE-ulp fp32 perturbation of its net outputs ('pert'); that band, or 3x the
-    reference's own FMA/no-FMA self-noise when larger, is the acceptance criterion."""
+    reference's own FMA/no-FMA self-noise when larger, is the acceptance criterion for the fp32 net.  The tensor-core nets
+    perturb the net outputs by ~5e-4..8e-4 relative (thousands of fp32 ulps, the reference's own `half_inference` regime) and the
+    response is chaotic — a change of the MMA accumulation order alone moves the 1x4f root values by 7e-4 — so their band
+    is 2e-3 mean / 1e-2 max on root values of order 0.1..1."""
     g = golden(f"cfr_net_{D}x{F}.npz")
     n = len(g["roots"])
-    S = rb.WaveSolver(D, F, n, net_mode=rb.NET_FP32 if net_name == "fp32" else rb.NET_TC_F16)
+    S = rb.WaveSolver(D, F, n, net_mode=NETS(rb)[net_name])
     S.set_weights(net_weights(D, F))
     S.begin(g["roots"][:, 0], g["roots"][:, 1], np.stack([g[f"beliefs{i}"] for i in range(n)]))
     S.run(1024)
@@ -260,7 +266,7 @@ def test_long_horizon_within_reference_noise(rb, golden, net_weights, D, F, net_
         self_noise = np.abs(a - b).mean()
         d = np.abs(mu[i] - a)
         _note(f"P4 {D}x{F}f net={net_name} root{i}: mean|dmu|={d.mean():.3e} max={d.max():.3e} ref-self-noise mean={self_noise:.3e}")
-        assert d.mean() <= max(7e-4, 3 * self_noise), (D, F, i, d.mean(), self_noise)
+        assert d.mean() <= max(7e-4 if net_name == "fp32" else 2e-3, 3 * self_noise), (D, F, i, d.mean(), self_noise)
         assert d.max() <= 1e-2, (D, F, i, d.max())
     S.close()
 
@@ -295,12 +301,12 @@ def test_full_tree_exploitability_1x4f(rb, golden, port, state_name):
 
 
 # ---------------------------------------------------------------------------------------------- properties at full size
-@pytest.mark.parametrize("net_name", ["fp32", "tc"])
+@pytest.mark.parametrize("net_name", ["fp32", "tc", "tcx2"])
 def test_full_size_properties_1x6f(rb, port, net_weights, net_name):
     """BASELINE config 2 shape: 8192 concurrent 1x6f subgames (ragged mix of all root templates)."""
     D, F, K = 1, 6, 8192
     A, H, Q = game_dims(D, F)
-    net = rb.NET_FP32 if net_name == "fp32" else rb.NET_TC_F16
+    net = NETS(rb)[net_name]
     rng = np.random.RandomState(0)
     lb = rng.randint(-1, A - 1, size=K).astype(np.int32)
     lb[:64] = -1
