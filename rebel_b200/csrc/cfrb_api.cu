@@ -546,8 +546,10 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
     float* ln1 = reinterpret_cast<float*>(blob.data() + L.off_ln1);
     float* ln2 = reinterpret_cast<float*>(blob.data() + L.off_ln2);
     for (int j = 0; j < hid; ++j) {
-      ln1[2 * j] = g1[j]; ln1[2 * j + 1] = be1[j];
-      ln2[2 * j] = g2[j]; ln2[2 * j + 1] = be2[j];
+      // per feature pair (j even): {gamma_j, gamma_j+1, beta_j, beta_j+1} — the packed operands of the epilogue's fma.f32x2
+      const int o = (j >> 1) * 4 + (j & 1);
+      ln1[o] = g1[j]; ln1[o + 2] = be1[j];
+      ln2[o] = g2[j]; ln2[o + 2] = be2[j];
     }
     std::copy(b3, b3 + H, reinterpret_cast<float*>(blob.data() + L.off_b3));
     if (!h->d_blob.p) CK(h->d_blob.alloc(L.blob_bytes));

@@ -45,7 +45,7 @@ struct BlobLayout {
     off_w3 = off_w2 + kHid * kHid * 2;        // [16 x 256]  fp16
     off_ones = off_w3 + kNout * kHid * 2;     // [128 x 16]  fp16, column 0 = 1
     off_bias2 = off_ones + kTileM * 16 * 2;   // [256 x 16]  fp16, column 0 = bias 2
-    off_ln1 = off_bias2 + kHid * 16 * 2;      // float2 {gamma, beta} per feature
+    off_ln1 = off_bias2 + kHid * 16 * 2;      // float4 {gamma_j, gamma_j+1, beta_j, beta_j+1} per feature pair
     off_ln2 = off_ln1 + kHid * 8;
     off_b3 = off_ln2 + kHid * 8;
     blob_bytes = off_b3 + kNout * 4;
@@ -145,6 +145,25 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2): one issue slot for two lanes' worth of LayerNorm arithmetic.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // GELU(y) = y * Phi(y), Phi(y) = 0.5 (1 + erf(y / sqrt 2)).  erf(z) = tanh(z (a + b z^2 + c z^4)) to 1.0e-4 (fitted, max error
 // of the resulting GELU 2.5e-5 absolute — 20x below the fp16 rounding of the activation it feeds), evaluated as a logistic
 // with ex2 / rcp so it is branch-free: y / (1 + 2^(-2 log2(e) u)), u = y (c0 + c1 y^2 + c2 y^4).
@@ -190,13 +209,22 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
     tmem_wait_ld();
   }
   if (kDebug && tr) tr[0] = clock64();
-  float sum = 0.f, sumsq = 0.f;
+  float sum, sumsq;
+  {
+    f32x2 s2 = pack2(0.f, 0.f), q2 = pack2(0.f, 0.f);     // even / odd features accumulate separately
 #pragma unroll
-  for (int i = 0; i < kColsPerThread; ++i) {
-    const float xv = __uint_as_float(xr[i]);
-    if (kDebug && dbg_row) dbg_row[part_id * kColsPerThread + i] = xv;
-    sum += xv;
-    sumsq = fmaf(xv, xv, sumsq);
+    for (int i = 0; i < kColsPerThread; i += 2) {
+      if (kDebug && dbg_row) {
+        dbg_row[part_id * kColsPerThread + i] = __uint_as_float(xr[i]);
+        dbg_row[part_id * kColsPerThread + i + 1] = __uint_as_float(xr[i + 1]);
+      }
+      const f32x2 x2 = pack2(__uint_as_float(xr[i]), __uint_as_float(xr[i + 1]));
+      s2 = add2(s2, x2);
+      q2 = fma2(x2, x2, q2);
+    }
+    float a0, a1, b0, b1;
+    unpack2(s2, a0, a1); unpack2(q2, b0, b1);
+    sum = a0 + a1; sumsq = b0 + b1;
   }
   part[part_id * kTileM + row] = make_float2(sum, sumsq);
   if (kDebug && tr) tr[1] = clock64();
@@ -217,6 +245,7 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
   const float var = fmaxf(sumsq * (1.f / kHid) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float shift = -mean * rstd;
+  const f32x2 rstd2 = pack2(rstd, rstd), shift2 = pack2(shift, shift);
   // Four sub-chunks of 16 features: sub-chunk s of column quarter q is K-step 4q+s of the next layer's MMA, so after the
   // s-th arrival of all epilogue threads the issuer can run K-steps {s, 4+s, 8+s, 12+s} while the rest is still being
   // normalised (only the last quarter of the MMA stays exposed).
@@ -226,9 +255,9 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int j = c * 16 + 2 * i;
-      const float4 pp = *reinterpret_cast<const float4*>(ln + part_id * kColsPerThread + j);   // {gamma_j, beta_j, gamma_j+1, beta_j+1}
-      const float y0 = fmaf(fmaf(__uint_as_float(xr[j]), rstd, shift), pp.x, pp.y);
-      const float y1 = fmaf(fmaf(__uint_as_float(xr[j + 1]), rstd, shift), pp.z, pp.w);
+      const float4 pp = *reinterpret_cast<const float4*>(ln + part_id * kColsPerThread + j);   // {gamma_j, gamma_j+1, beta_j, beta_j+1}
+      float y0, y1;
+      unpack2(fma2(fma2(pack2(__uint_as_float(xr[j]), __uint_as_float(xr[j + 1])), rstd2, shift2), pack2(pp.x, pp.y), pack2(pp.z, pp.w)), y0, y1);
       if (kGeluX2) {
         pk[i] = gelu_tc_x2(y0, y1);
       } else {

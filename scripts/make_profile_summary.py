@@ -4,10 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
-out = [f"# Round 1 profile summary ({tag}): tcgen05 value net + fp64 CFR wave kernels on B200\n"]
+out = [f"# Profile summary ({tag}): tcgen05 value net + fp64 CFR wave kernels on B200\n"]
 
 # ---- launch list (ncu --metrics gpu__time_duration.sum)
-lc = os.path.join(G, "launches_tc.csv")
+lc = os.path.join(G, f"launches_{tag}.csv")
+if not os.path.exists(lc): lc = os.path.join(G, "launches_tc.csv")
 if os.path.exists(lc):
     rows = list(csv.reader(open(lc)))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -19,15 +20,16 @@ if os.path.exists(lc):
             agg.setdefault(r[ki], []).append(float(r[vi].replace(",", "")))
     tot = sum(sum(v) for v in agg.values())
     out.append("## Launch list\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv python bench.py --steps 1 --warmup 1 "
-               "--iters 100 --no-cpu-baseline` (raw: `" + tag + "_launches_tc.csv`; cold-cache, serialised: compare SHARES).\n")
+               "--iters 100 --no-cpu-baseline` (raw: `" + tag + "_launches.csv`; cold-cache, serialised: compare SHARES).\n")
     out.append("| kernel | launches | avg us | share |\n|---|---|---|---|")
     for k, v in agg.items():
         out.append(f"| `{k[:78]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {100 * sum(v) / tot:.1f}% |")
-    with open(os.path.join(P, f"{tag}_launches_tc.csv"), "w") as f:
+    with open(os.path.join(P, f"{tag}_launches.csv"), "w") as f:
         f.write(open(lc).read())
 
 # ---- full-set capture of the two hot kernels
-rep = os.path.join(G, "prof_r1b.ncu-rep")
+rep = os.path.join(G, f"prof_{tag}.ncu-rep")
+if not os.path.exists(rep): rep = os.path.join(G, "prof_r1b.ncu-rep")
 if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -71,10 +73,11 @@ if os.path.exists(rep):
         out.append("")
 
 # ---- bench line
-bj = os.path.join(G, "bench_r1_tc.json")
+bj = os.path.join(G, f"bench_{tag}.json")
+if not os.path.exists(bj): bj = os.path.join(G, "bench_r1_tc.json")
 if os.path.exists(bj):
-    b = json.loads(open(bj).read().strip().splitlines()[0])
-    open(os.path.join(P, f"{tag}_bench_tc.json"), "w").write(json.dumps(b, indent=1))
+    b = json.loads(open(bj).read().strip().splitlines()[-1])
+    open(os.path.join(P, f"{tag}_bench.json"), "w").write(json.dumps(b, indent=1))
     r = b["roofline"]
     out.append("## bench.py (no profiler attached), same build\n")
     out.append(f"* value = {b['value']:.4e} subgame-iters/s ({b['ms_per_step']:.1f} ms per 8192x1024 wave), e2e = {b['e2e']['value']:.4e}; "
@@ -87,5 +90,5 @@ pn = os.path.join(G, "parity_notes.log")
 if os.path.exists(pn):
     open(os.path.join(P, f"{tag}_parity_notes.log"), "w").write(open(pn).read())
     out.append(f"\nMeasured parity numbers of the same build: `{tag}_parity_notes.log`.")
-open(os.path.join(P, f"{tag}_summary_tc.md"), "w").write("\n".join(out) + "\n")
+open(os.path.join(P, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:3000])

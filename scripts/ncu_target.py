@@ -8,7 +8,7 @@ D, F, K = 1, 6, 8192
 state = rb.STATE_F32 if len(sys.argv) > 1 and sys.argv[1] == "f32" else rb.STATE_F64
 w = flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict())
 b = np.random.RandomState(1).rand(K, 2, 6); b /= b.sum(-1, keepdims=True)
-S = rb.WaveSolver(D, F, K, net_mode=rb.NET_TC_F16, state_dtype=state)
+S = rb.WaveSolver(D, F, K, net_mode=rb.NET_TC_F16X2, state_dtype=state)
 S.set_weights(w)
 S.begin(np.full(K, -1, np.int32), np.zeros(K, np.int32), b)
 S.run(8); S.sync()
