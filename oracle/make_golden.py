@@ -24,6 +24,14 @@ def weights(D, F):
     return flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict())
 
 
+VARIANTS = {
+    "vanilla": dict(linear_update=False),
+    "dcfr": dict(linear_update=False, dcfr=True, dcfr_alpha=1.5, dcfr_beta=0.0, dcfr_gamma=2.0),
+    "dcfr_sat": dict(linear_update=False, dcfr=True, dcfr_alpha=5.0, dcfr_beta=-5.0, dcfr_gamma=1.0),
+}
+VARIANT_NAMES = list(VARIANTS)
+
+
 def recursive_eval_reference(lib, D, F, num_iters, num_repeats, net_w=None, keep=2):
     """The accumulation loop of the reference's recursive_eval main (recursive_eval.cc:343-369) around its own
     compute_sampled_strategy_recursive_to_leaf and compute_stategy_stats, float32 tensors emulated with numpy."""
@@ -77,6 +85,19 @@ def main():
             for k in ("regrets", "last", "sum", "avg", "root_means"):
                 out[f"{k}{i}"] = s[k]
         np.savez_compressed(os.path.join(OUT, f"cfr_zero_{D}x{F}.npz"), **out)
+
+    # ---- discounting variants of CFR::step (subgame_solving.cc:592-617): vanilla (no discount), DCFR(1.5, 0, 2) — the
+    # recursive_eval --dcfr setting (recursive_eval.cc:250-254) — and DCFR with the alpha >= 5 / beta <= -5 shortcuts
+    out = {"checkpoints": np.array([1, 2, 3, 8]), "variants": np.array(VARIANT_NAMES)}
+    for (D, F) in SHAPES:
+        A, H, Q = game_dims(D, F)
+        b = R.synthetic_beliefs(H, 2000)
+        out[f"beliefs_{D}x{F}"] = b
+        for name, kw in VARIANTS.items():
+            s = R.cfr_solve(D, F, b, [1, 2, 3, 8], 1, 1, num_iters=8, **kw)
+            for k in ("regrets", "last", "sum", "avg", "root_means"):
+                out[f"{k}_{name}_{D}x{F}"] = s[k]
+    np.savez_compressed(os.path.join(OUT, "cfr_variants.npz"), **out)
 
     # ---- Net2 depth-2 trajectories: short horizon states + long-horizon root means from both builds
     cps_net = [1, 2, 16]

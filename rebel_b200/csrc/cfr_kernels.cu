@@ -2,6 +2,7 @@
 // operation is an individually rounded IEEE operation in the same order as the reference's scalar C++ (built without
 // contraction), which makes the CFRB_STATE_F64 path reproduce the reference bit for bit between value-net calls.
 #include "cfr_kernels.cuh"
+#include "br_kernel.cuh"
 
 namespace cfrb {
 
@@ -45,6 +46,8 @@ void cfr_launch_iter(const CfrDev<real>& p, int group, int blocks, int threads, 
     cfr_iter_kernel<real, 256, 0><<<blocks, 256, 0, st>>>(p, iter, do_b, do_f, scratch_per_group);
   }
 }
+
+void br_launch(const BrDev& p, cudaStream_t st) { br_kernel<<<2, 1024, 0, st>>>(p); }
 
 template <typename real>
 cudaError_t cfr_configure_d2(int smem_bytes) {

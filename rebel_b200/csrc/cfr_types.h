@@ -50,6 +50,18 @@ __host__ __device__ inline int cfr_scratch_reals(int N, int H, int L, int T) { r
 // Depth <= 2 kernel (cfr_iter_d2_kernel): slot[N*H] | bel[2*H] | hist[10*T] | lsum[2*L]
 __host__ __device__ inline int cfr_scratch_reals_d2(int N, int H, int L, int T) { return N * H + 2 * H + cfr_tmp_reals(N, H, L, T) + 2 * (L > 0 ? L : 1); }
 
+// Full-tree best response (br_kernel.cuh).  Arrays describe ONE full-depth tree rooted at the initial state.
+struct BrDev {
+  int N, T, levels, H, F;
+  const int* parent; const int* child_begin; const int* nchild; const int* level_begin;   // level_begin: [levels + 1]
+  const int* term_node;           // [3][T]: node id, challenged bid, depth
+  const unsigned char* matches;   // [H][F]
+  const double* strategy;         // compact [edge = child - 1][H]
+  double* scratch; size_t scratch_stride;   // per traverser: reach0[N*H] | reach1[N*H] | val[N*H] | hist[10*T]
+  double* out;                    // [2]
+};
+void br_launch(const BrDev& p, cudaStream_t st);
+
 // Launchers implemented in cfr_kernels.cu (explicitly instantiated for float and double).  `group` is 32 (one warp per
 // subgame, shared-memory scratch) or 256 (one CTA per subgame, global scratch).
 template <typename real> cudaError_t cfr_configure(int group, int smem_bytes);

@@ -88,6 +88,14 @@ struct cfrb_handle {
   DevBuf<cfrb::TemplateDev> d_tmpl;
   DevBuf<int> d_parent, d_child_begin, d_nchild, d_last_bid, d_level_begin, d_pleaf_node, d_term_node;
   DevBuf<unsigned char> d_matches;
+  // full-depth tree for cfrb_exploitability, built on first use
+  struct BrState {
+    bool ready = false;
+    cfrb::TreeTemplate t;
+    DevBuf<int> parent, child_begin, nchild, level_begin, term_node;
+    DevBuf<double> strategy, scratch, out;
+    size_t scratch_stride = 0;
+  } br;
   DevBuf<__half> d_qconst;
   // device: wave (untyped part)
   DevBuf<int> d_wave;      // [0] = n, [1] = rows
@@ -355,6 +363,8 @@ int cfrb_destroy(cfrb_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   h->d_tmpl.release(); h->d_parent.release(); h->d_child_begin.release(); h->d_nchild.release(); h->d_last_bid.release();
+  h->br.parent.release(); h->br.child_begin.release(); h->br.nchild.release(); h->br.level_begin.release(); h->br.term_node.release();
+  h->br.strategy.release(); h->br.scratch.release(); h->br.out.release();
   h->d_level_begin.release(); h->d_pleaf_node.release(); h->d_term_node.release(); h->d_matches.release(); h->d_qconst.release();
   h->d_wave.release(); h->d_sg_tmpl.release(); h->d_sg_player.release(); h->d_sg_row_off.release(); h->d_sg_act.release();
   h->d_steps.release(); h->d_X.release(); h->d_out.release(); h->d_dbg.release(); h->d_Xh.release();
@@ -837,8 +847,49 @@ int cfrb_debug_net_taps(cfrb_handle* h, float* d1, float* d2) {
 }
 
 int cfrb_exploitability(cfrb_handle* h, const double* full_strategy, double* out2) {
-  (void)h; (void)full_strategy; (void)out2;
-  return fail(CFRB_EINVAL, "cfrb_exploitability: best-response kernel (SURVEY 8f-1) is not built yet");
+  if (!h || !full_strategy || !out2) return fail(CFRB_EINVAL, "cfrb_exploitability: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  auto& b = h->br;
+  const auto& g = h->g;
+  if (!b.ready) {
+    if (g.A > 26) return fail(CFRB_EINVAL, "cfrb_exploitability: full tree too large (2^A - 1 nodes)");
+    b.t = cfrb::build_template(g, -1, 1 << 30);
+    const auto& t = b.t;
+    std::vector<int> term(t.term_node.begin(), t.term_node.end());
+    for (int n : t.term_node) term.push_back(t.last_bid[t.parent[n]]);   // challenged bid (:287)
+    for (int n : t.term_node) term.push_back(t.depth[n]);
+    auto up = [&](auto& buf, const auto& v) -> cudaError_t {
+      cudaError_t e = buf.alloc(v.size());
+      if (e != cudaSuccess) return e;
+      return cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice);
+    };
+    CK(up(b.parent, t.parent)); CK(up(b.child_begin, t.child_begin)); CK(up(b.nchild, t.nchild));
+    CK(up(b.level_begin, t.level_begin)); CK(up(b.term_node, term));
+    b.scratch_stride = (size_t)3 * t.N * g.H + (size_t)10 * std::max(t.T, 1);
+    CK(b.scratch.alloc(2 * b.scratch_stride));
+    CK(b.strategy.alloc((size_t)std::max(t.N - 1, 1) * g.H));
+    CK(b.out.alloc(2));
+    b.ready = true;
+  }
+  const auto& t = b.t;
+  // dense [n][h][a] -> compact [edge = child - 1][h]
+  std::vector<double> compact((size_t)std::max(t.N - 1, 1) * g.H, 0.0);
+  for (int n = 0; n < t.N; ++n)
+    for (int j = 0; j < t.nchild[n]; ++j)
+      for (int hd = 0; hd < g.H; ++hd)
+        compact[(size_t)(t.child_begin[n] + j - 1) * g.H + hd] = full_strategy[((size_t)n * g.H + hd) * g.A + t.act_lo[n] + j];
+  CK(cudaMemcpyAsync(b.strategy.p, compact.data(), compact.size() * sizeof(double), cudaMemcpyHostToDevice, h->own_stream));
+  cfrb::BrDev d{};
+  d.N = t.N; d.T = t.T; d.levels = t.levels; d.H = g.H; d.F = g.F;
+  d.parent = b.parent.p; d.child_begin = b.child_begin.p; d.nchild = b.nchild.p; d.level_begin = b.level_begin.p;
+  d.term_node = b.term_node.p; d.matches = h->d_matches.p; d.strategy = b.strategy.p;
+  d.scratch = b.scratch.p; d.scratch_stride = b.scratch_stride; d.out = b.out.p;
+  cfrb::br_launch(d, h->own_stream);
+  ++h->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out2, b.out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->own_stream));
+  CK(cudaStreamSynchronize(h->own_stream));
+  return CFRB_OK;
 }
 
 int64_t cfrb_kernel_launches(const cfrb_handle* h) { return h ? h->launches : 0; }

@@ -150,7 +150,9 @@ class RecursiveEvaluator {
         finalize(res);
         std::vector<double> s(res.final_strategy.begin(), res.final_strategy.end());
         res.checkpoints.push_back(done);
-        res.exploitability.push_back(best_response_values(cfg_.num_dice, cfg_.num_faces, full_, s));
+        std::array<double, 2> e{};   // best response of both players on the GPU (cfrb_exploitability = compute_exploitability2)
+        if (cfrb_exploitability(h_, s.data(), e.data()) < 0) throw std::runtime_error(cfrb_last_error());
+        res.exploitability.push_back(e);
       }
     }
     return res;

@@ -244,6 +244,36 @@ def test_zero_net_trajectories_bit_exact_vs_reference(rb, golden, D, F):
     S.close()
 
 
+@pytest.mark.parametrize("D,F", SHAPES)
+@pytest.mark.parametrize("max_depth", [2, 3])
+def test_discount_variants_vs_reference(rb, golden, port, D, F, max_depth):
+    """Vanilla CFR (no discounting) is bit-identical to the reference like linear CFR; DCFR evaluates n^alpha with CUDA's pow,
+    which may differ from glibc's by an ulp, so its 8-iteration trajectories are compared to 1e-12."""
+    from oracle.make_golden import VARIANTS
+    g = golden("cfr_variants.npz")
+    cps = list(g["checkpoints"])
+    b = g[f"beliefs_{D}x{F}"]
+    for name, kw in VARIANTS.items():
+        S = rb.WaveSolver(D, F, 2, max_depth=max_depth, net_mode=rb.NET_ZERO, **kw)
+        S.begin(np.array([1, 1], np.int32), np.array([1, 1], np.int32), np.stack([b, b]))
+        ref = port.cfr_solve(D, F, b, cps, 1, 1, num_iters=8, max_depth=max_depth, **kw)
+        done = 0
+        for ci, c in enumerate(cps):
+            S.run(c - done); done = c
+            f = S.fetch(("root_means", "last", "sum", "regrets", "avg"))
+            for k in ("regrets", "last", "sum", "avg"):
+                x, y = f[k][0, :ref[k].shape[1]], ref[k][ci]
+                if max_depth == 2:
+                    assert np.array_equal(y, g[f"{k}_{name}_{D}x{F}"][ci])     # the port run IS the golden reference run
+                if name == "vanilla":
+                    assert np.array_equal(x, y), (name, k, c)
+                else:
+                    assert np.abs(x - y).max() < 1e-12, (name, k, c, np.abs(x - y).max())
+            assert np.abs(f["root_means"][0] - ref["root_means"][ci]).max() < 1e-12
+            assert np.array_equal(f["regrets"][0], f["regrets"][1])
+        S.close()
+
+
 # ---------------------------------------------------------------------------------------------- P4
 @pytest.mark.parametrize("D,F", SHAPES)
 @pytest.mark.parametrize("net_name", ["fp32", "tc", "tcx2"])
@@ -271,6 +301,35 @@ def test_long_horizon_within_reference_noise(rb, golden, net_weights, D, F, net_
     S.close()
 
 
+@pytest.mark.parametrize("D,F", [(1, 2), (1, 3), (1, 4), (1, 6), (2, 3)])
+def test_gpu_best_response_bit_exact(rb, golden, port, D, F):
+    """cfrb_exploitability (SURVEY 8f-1: BRSolver::compute_br + compute_exploitability2 on the GPU) against the golden
+    exploitabilities of the compiled reference and, on random strategies over the whole tree, against the oracle."""
+    A, H, Q = game_dims(D, F)
+    S = rb.WaveSolver(D, F, 1, net_mode=rb.NET_ZERO)
+    if (D, F) in ((1, 2), (1, 3), (1, 4)):
+        g = golden("fulltree.npz")
+        assert np.array_equal(S.exploitability(g[f"avg16_{D}x{F}"]), g[f"expl_{D}x{F}_nofma"][0])
+    else:
+        g = golden("recursive_eval_zero.npz")
+        ss, sr = g[f"summed_strategy_{D}x{F}"], g[f"summed_reach_{D}x{F}"]
+        assert np.array_equal(S.exploitability((ss / (sr + np.float32(1e-6))).astype(np.float64)), g[f"exploitability_{D}x{F}"][-1])
+    tree = port.unroll_tree(D, F)
+    rng = np.random.RandomState(3)
+    for rep in range(2):
+        s = np.zeros((len(tree), H, A))
+        for n, (lb, pl, cb, ce, par, dep) in enumerate(tree):
+            if ce > cb:
+                lo = 0 if lb < 0 else lb + 1
+                x = rng.rand(H, ce - cb) ** 3
+                if rep:
+                    x[rng.rand(H, ce - cb) < 0.5] = 0        # sparse strategies: zero reach below many nodes
+                    x[:, 0] += 1e-3
+                s[n, :, lo:lo + ce - cb] = x / x.sum(-1, keepdims=True)
+        assert np.array_equal(S.exploitability(s), port.exploitability(D, F, s)), rep
+    S.close()
+
+
 @pytest.mark.parametrize("state_name", ["f64", "f32"])
 def test_full_tree_exploitability_1x4f(rb, golden, port, state_name):
     """BASELINE config 0 on the GPU: full-depth 1x4f tree (511 nodes, CTA-per-subgame path), 1024 linear-CFR iterations,
@@ -286,6 +345,9 @@ def test_full_tree_exploitability_1x4f(rb, golden, port, state_name):
     avg = S.fetch(("avg",))["avg"][0]
     e16 = port.exploitability(D, F, avg16).mean()
     e = port.exploitability(D, F, avg).mean()
+    # the GPU best response (cfrb_exploitability, K5) is bit-identical to compute_exploitability2
+    assert np.array_equal(S.exploitability(avg16), port.exploitability(D, F, avg16))
+    assert np.array_equal(S.exploitability(avg), port.exploitability(D, F, avg))
     ref_a, ref_b = g["expl_1x4_nofma"][1].mean(), g["expl_1x4_fast"][1].mean()
     _note(f"full-tree 1x4f {state_name} exploitability: @16 gpu={e16:.4e} ref={g['expl_1x4_nofma'][0].mean():.4e}; "
           f"@1024 gpu={e:.4e} ref_nofma={ref_a:.4e} ref_fast={ref_b:.4e}")

@@ -142,6 +142,18 @@ def test_cfr_zero_net_bit_exact_vs_golden(port, golden, D, F):
 
 
 @pytest.mark.parametrize("D,F", SHAPES)
+def test_cfr_discount_variants_bit_exact_vs_golden(port, golden, D, F):
+    """Vanilla CFR and DCFR (subgame_solving.cc:592-617, incl. the alpha >= 5 / beta <= -5 shortcuts): the C port follows
+    the compiled reference bit for bit (both use glibc pow)."""
+    from oracle.make_golden import VARIANTS
+    g = golden("cfr_variants.npz")
+    for name, kw in VARIANTS.items():
+        s = port.cfr_solve(D, F, g[f"beliefs_{D}x{F}"], list(g["checkpoints"]), 1, 1, num_iters=8, **kw)
+        for k in ("regrets", "last", "sum", "avg", "root_means"):
+            assert np.array_equal(s[k], g[f"{k}_{name}_{D}x{F}"]), (name, k)
+
+
+@pytest.mark.parametrize("D,F", SHAPES)
 def test_cfr_net_short_horizon_vs_golden(port, golden, net_weights, D, F):
     g = golden(f"cfr_net_{D}x{F}.npz")
     w = net_weights(D, F)
