@@ -67,6 +67,13 @@ enum {
                              fp32 LayerNorm: ~40 % fewer epilogue instructions, ~1.6x the activation rounding noise */
 };
 
+/* Subgame solver.  In FP mode cfrb_fetch's "last" is FP::last_strategies (belief x best response), "avg" is
+ * FP::average_strategies (also the sampling / belief-propagation strategy, subgame_solving.h:76-83) and "regrets" is empty. */
+enum {
+  CFRB_SOLVER_CFR = 0,    /* CFR (subgame_solving.cc:508-715), params.use_cfr = true */
+  CFRB_SOLVER_FP = 1      /* fictitious play (subgame_solving.cc:364-506), params.use_cfr = false */
+};
+
 /* Arithmetic type of the per-infoset CFR tables (regrets, strategies, reach, values). */
 enum {
   CFRB_STATE_F64 = 0,     /* double, like the reference's TreeStrategy (default) */
@@ -87,6 +94,8 @@ typedef struct {
   int32_t net_mode;         /* CFRB_NET_* */
   int32_t hidden;           /* Net2 n_hidden (256); n_layers = 2, LayerNorm on */
   int32_t state_dtype;      /* CFRB_STATE_* */
+  int32_t solver;           /* CFRB_SOLVER_*: which ISubgameSolver build_solver would return (subgame_solving.cc:791-800) */
+  int32_t optimistic;       /* FP only: SubgameSolvingParams::optimistic (subgame_solving.h:50, util.h:52-63) */
 } cfrb_config;
 
 /* One node of an unrolled subgame tree: UnrolledTreeNode (tree.h:31-47). */

@@ -451,6 +451,111 @@ int orc_cfr_solve(int D, int F, int last_bid, int player_id, const double* belie
   return N;
 }
 
+/* ------------------------------------------------------------------ fictitious play: FP, subgame_solving.cc:364-506 */
+/* update_sum_strat (:391-421): the traverser's beliefs flow down through its own best-response actions. */
+static void fp_update_sum_strat(orc_cfr* s, int node, int traverser, const double* br, const double* beliefs) {
+  int H = s->g.H;
+  const orc_node* nd = &s->tree[node];
+  int nc = nd->children_end - nd->children_begin;
+  if (!nc) return;
+  if (nd->player_id == traverser) {
+    int lo, hi; game_bid_range(&s->g, nd->last_bid, &lo, &hi);
+    double* nb = (double*)malloc(sizeof(double) * H);
+    for (int c = nd->children_begin, a = lo; c < nd->children_end; ++c, ++a) {
+      for (int h = 0; h < H; ++h) {
+        s->sum[IDX3(s, node, h, a)] += beliefs[h] * br[IDX3(s, node, h, a)];
+        s->last[IDX3(s, node, h, a)] = beliefs[h] * br[IDX3(s, node, h, a)];
+      }
+      for (int h = 0; h < H; ++h) nb[h] = beliefs[h] * br[IDX3(s, node, h, a)];
+      fp_update_sum_strat(s, c, traverser, br, nb);
+    }
+    free(nb);
+  } else {
+    for (int c = nd->children_begin; c < nd->children_end; ++c) fp_update_sum_strat(s, c, traverser, br, beliefs);
+  }
+}
+
+/* FP::step (:423-460) with BRSolver::compute_br (:316-358).  `num_strategies` lives in num_steps[0] + num_steps[1];
+ * s->regrets is reused for the best-response strategy. */
+static void orc_fp_step(orc_cfr* s, int traverser, int optimistic) {
+  int H = s->g.H, A = s->g.A;
+  double* br = s->regrets;
+  compute_reach(s, s->avg, s->beliefs, 0, s->reach[0]);          /* precompute_reaches (:210-218) */
+  compute_reach(s, s->avg, s->beliefs + H, 1, s->reach[1]);
+  precompute_all_leaf_values(s, traverser);
+  for (int n = s->N; n-- > 0;) {
+    const orc_node* nd = &s->tree[n];
+    int nc = nd->children_end - nd->children_begin;
+    if (!nc) continue;
+    int lo, hi; game_bid_range(&s->g, nd->last_bid, &lo, &hi);
+    double* value = s->values + IDX2(s, n, 0);
+    for (int h = 0; h < H; ++h) value[h] = 0.0;
+    if (nd->player_id == traverser) {
+      for (int h = 0; h < H; ++h) {
+        int best = lo;
+        for (int c = nd->children_begin, a = lo; c < nd->children_end; ++c, ++a) {
+          double nv = s->values[IDX2(s, c, h)];
+          if (c == nd->children_begin || nv > value[h]) { value[h] = nv; best = a; }
+        }
+        for (int a = 0; a < A; ++a) br[IDX3(s, n, h, a)] = 0.;
+        br[IDX3(s, n, h, best)] = 1.0;
+      }
+    } else {
+      for (int c = nd->children_begin; c < nd->children_end; ++c)
+        for (int h = 0; h < H; ++h) value[h] += s->values[IDX2(s, c, h)];
+    }
+  }
+  int num_strategies = s->num_steps[0] + s->num_steps[1];
+  int num_update = num_strategies / 2 + 1;
+  {
+    double alpha = s->linear ? 2. / (num_update + 1) : 1. / num_update;
+    if (!s->root_means_set[traverser]) { for (int h = 0; h < H; ++h) s->root_means[traverser][h] = 0; s->root_means_set[traverser] = 1; }
+    for (int h = 0; h < H; ++h) s->root_means[traverser][h] += (s->values[IDX2(s, 0, h)] - s->root_means[traverser][h]) * alpha;
+  }
+  fp_update_sum_strat(s, 0, traverser, br, s->beliefs + traverser * H);
+  for (int n = 0; n < s->N; ++n) {
+    int nc = s->tree[n].children_end - s->tree[n].children_begin;
+    if (!nc || s->tree[n].player_id != traverser) continue;
+    for (int h = 0; h < H; ++h) {
+      double* sm = s->sum + IDX3(s, n, h, 0); double* ls = s->last + IDX3(s, n, h, 0); double* av = s->avg + IDX3(s, n, h, 0);
+      if (s->linear) for (int a = 0; a < A; ++a) sm[a] *= (double)(num_update + 1) / (num_update + 2);
+      if (optimistic) {            /* util.h:52-63 */
+        double t0 = 0, t1 = 0;
+        for (int a = 0; a < A; ++a) t0 += sm[a];
+        for (int a = 0; a < A; ++a) t1 += ls[a];
+        double tot = t0 + t1;
+        for (int a = 0; a < A; ++a) av[a] = (sm[a] + ls[a]) / tot;
+      } else {                     /* util.h:20-34 */
+        double tot = 0;
+        for (int a = 0; a < A; ++a) tot += sm[a];
+        for (int a = 0; a < A; ++a) av[a] = sm[a] / tot;
+      }
+    }
+  }
+  ++s->num_steps[traverser];
+}
+
+/* Same signature and semantics as ref_fp_solve in oracle/ref_harness.cc. */
+int orc_fp_solve(int D, int F, int last_bid, int player_id, const double* beliefs, int num_iters, int max_depth,
+                 int linear_update, int optimistic, const float* net_w, int hidden, int n_checkpoints,
+                 const int32_t* checkpoints, double* last, double* sum, double* avg, double* root_means) {
+  orc_cfr* s = orc_cfr_create(D, F, last_bid, player_id, beliefs, num_iters, max_depth, linear_update, 0, 0, 0, 0, net_w, hidden);
+  int H = s->g.H, A = s->g.A, N = s->N;
+  size_t dense = (size_t)N * H * A;
+  int done = 0;
+  for (int c = 0; c < n_checkpoints; ++c) {
+    for (; done < checkpoints[c]; ++done) orc_fp_step(s, done % 2, optimistic);
+    dump(s->last, last ? last + c * dense : 0, dense);
+    dump(s->sum, sum ? sum + c * dense : 0, dense);
+    dump(s->avg, avg ? avg + c * dense : 0, dense);
+    if (root_means)
+      for (int p = 0; p < 2; ++p)
+        for (int h = 0; h < H; ++h) root_means[(c * 2 + p) * H + h] = s->root_means_set[p] ? s->root_means[p][h] : 0.0;
+  }
+  orc_cfr_destroy(s);
+  return N;
+}
+
 /* ------------------------------------------------------------------ best response / exploitability */
 /* BRSolver::compute_br + compute_exploitability2, subgame_solving.cc:316-358,802-816 (full tree, no net) */
 int orc_exploitability(int D, int F, const double* strategy, double* out2) {

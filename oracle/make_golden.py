@@ -30,6 +30,9 @@ VARIANTS = {
     "dcfr_sat": dict(linear_update=False, dcfr=True, dcfr_alpha=5.0, dcfr_beta=-5.0, dcfr_gamma=1.0),
 }
 VARIANT_NAMES = list(VARIANTS)
+FP_CPS = [1, 2, 3, 8, 33]
+FP_CASES = [(True, False, 2), (False, False, 2), (True, True, 2), (True, False, 3), (True, False, 100)]   # linear, optimistic, max_depth
+FP_ROOTS = [(-1, 0), (2, 1)]
 
 
 def recursive_eval_reference(lib, D, F, num_iters, num_repeats, net_w=None, keep=2):
@@ -99,6 +102,21 @@ def main():
                 out[f"{k}_{name}_{D}x{F}"] = s[k]
     np.savez_compressed(os.path.join(OUT, "cfr_variants.npz"), **out)
 
+    # ---- fictitious play (FP, subgame_solving.cc:364-506), zero net: linear / plain / optimistic, depth 2 and full depth
+    out = {"checkpoints": np.array(FP_CPS), "cases": np.array([f"{int(l)}{int(o)}{md}" for l, o, md in FP_CASES])}
+    for (D, F) in SHAPES:
+        A, H, Q = game_dims(D, F)
+        b = R.synthetic_beliefs(H, 3000)
+        out[f"beliefs_{D}x{F}"] = b
+        for (lin, opt, md) in FP_CASES:
+            if md > 3 and (D, F) != (1, 4):
+                continue
+            for (lb, pl) in FP_ROOTS:
+                s = R.fp_solve(D, F, b, FP_CPS, lb, pl, num_iters=max(FP_CPS), max_depth=md, linear_update=lin, optimistic=opt)
+                for k in ("last", "sum", "avg", "root_means"):
+                    out[f"{k}_{int(lin)}{int(opt)}{md}_{lb}_{D}x{F}"] = s[k]
+    np.savez_compressed(os.path.join(OUT, "fp_zero.npz"), **out)
+
     # ---- Net2 depth-2 trajectories: short horizon states + long-horizon root means from both builds
     cps_net = [1, 2, 16]
     for (D, F) in SHAPES:
@@ -140,6 +158,10 @@ def main():
             q, v = R.rl_runner(D, F, seed=7, n_games=4, num_iters=32, sample_leaf=bool(sl))
             out[f"q_{D}x{F}_{sl}"] = q
             out[f"v_{D}x{F}_{sl}"] = v
+    for (D, F) in SHAPES:   # the same walk with the fictitious-play solver (use_cfr = false)
+        q, v = R.rl_runner(D, F, seed=7, n_games=4, num_iters=32, sample_leaf=True, use_cfr=False)
+        out[f"q_fp_{D}x{F}"] = q
+        out[f"v_fp_{D}x{F}"] = v
     np.savez_compressed(os.path.join(OUT, "selfplay_zero.npz"), **out)
 
     # ---- recursive evaluation (recursive_eval.cc:117-191,343-369) with the zero net: sampled recursive strategies of

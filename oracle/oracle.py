@@ -135,6 +135,26 @@ class Oracle:
                    term=np.nonzero(tree[:, 0] == A - 1)[0])
         return out
 
+    def fp_solve(self, D, F, beliefs, checkpoints, last_bid=-1, player_id=0, num_iters=1024, max_depth=2, linear_update=True,
+                 optimistic=False, net_w=None, hidden=256):
+        """Fictitious play (FP, subgame_solving.cc:364-506): dict of [C,N,H,A] tables last / sum / avg and root_means."""
+        A, H, Q = game_dims(D, F)
+        N = len(self.unroll_tree(D, F, last_bid, player_id, max_depth))
+        cps = np.ascontiguousarray(checkpoints, np.int32)
+        b = np.ascontiguousarray(beliefs, np.float64).reshape(2, H)
+        w = None if net_w is None else np.ascontiguousarray(net_w, np.float32)
+        bufs = {k: np.zeros((len(cps), N, H, A), np.float64) for k in ("last", "sum", "avg")}
+        rm = np.zeros((len(cps), 2, H), np.float64)
+        f = self._f("fp_solve")
+        f.argtypes = [C.c_int] * 4 + [_dp] + [C.c_int] * 4 + [_fp, C.c_int, C.c_int, _ip] + [_dp] * 4
+        n = f(int(D), int(F), int(last_bid), int(player_id), _ptr(b, _dp), int(num_iters), int(max_depth), int(linear_update),
+              int(optimistic), _ptr(w, _fp), hidden, len(cps), _ptr(cps, _ip), _ptr(bufs["last"], _dp), _ptr(bufs["sum"], _dp),
+              _ptr(bufs["avg"], _dp), _ptr(rm, _dp))
+        assert n == N, (n, N)
+        out = dict(bufs)
+        out["root_means"] = rm
+        return out
+
     def exploitability(self, D, F, strategy):
         s = np.ascontiguousarray(strategy, np.float64)
         out = np.zeros(2, np.float64)
@@ -143,12 +163,12 @@ class Oracle:
         return out
 
     def rl_runner(self, D, F, seed, n_games, num_iters=1024, max_depth=2, linear_update=True,
-                  random_action_prob=0.25, sample_leaf=True, net_w=None, hidden=256, cap=4096):
+                  random_action_prob=0.25, sample_leaf=True, net_w=None, hidden=256, cap=4096, use_cfr=True):
         A, H, Q = game_dims(D, F)
         q = np.zeros((cap, Q), np.float32)
         v = np.zeros((cap, H), np.float32)
         w = None if net_w is None else np.ascontiguousarray(net_w, np.float32)
-        f = self._f("rl_runner")
+        f = self._f("rl_runner" if use_cfr else "rl_runner_fp")      # the FP walk exists in the reference builds only
         f.argtypes = [C.c_int] * 5 + [C.c_float] + [C.c_int] * 3 + [_fp, C.c_int, _fp, _fp, C.c_int]
         n = f(D, F, num_iters, max_depth, int(linear_update), random_action_prob, int(sample_leaf), seed, n_games,
               _ptr(w, _fp), hidden, _ptr(q, _fp), _ptr(v, _fp), cap)

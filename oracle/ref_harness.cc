@@ -272,6 +272,48 @@ int ref_cfr_solve(int D, int F, int last_bid, int player_id, const double* belie
   }
 }
 
+// The reference's other solver, fictitious play (FP, subgame_solving.cc:364-506): same dumps as ref_cfr_solve minus regrets.
+int ref_fp_solve(int D, int F, int last_bid, int player_id, const double* beliefs, int num_iters, int max_depth,
+                 int linear_update, int optimistic, const float* net_w, int hidden, int n_checkpoints,
+                 const int32_t* checkpoints, double* last, double* sum, double* avg, double* root_means /*[C][2][H]*/) {
+  try {
+    Game game(D, F);
+    const int H = game.num_hands(), A = game.num_actions();
+    auto params = make_params(num_iters, max_depth, linear_update, 0, 0, 0, 0);
+    params.use_cfr = false;
+    params.optimistic = optimistic != 0;
+    PartialPublicState root{last_bid, player_id};
+    auto tree = unroll_tree(game, root, max_depth);
+    bool has_pleaf = false;
+    for (auto& n : tree) has_pleaf |= (!n.num_children() && !game.is_terminal(n.state));
+    std::shared_ptr<IValueNet> net;
+    if (net_w) {
+      net = std::make_shared<FlatNet2>(net_w, 2 + A + 2 * H, hidden, H);
+    } else if (has_pleaf) {
+      net = create_zero_net(H, false);
+    }
+    FP fp(game, root, net, to_beliefs(beliefs, H), params);
+    const size_t N = fp.tree.size();
+    const size_t dense = N * H * A;
+    int done = 0;
+    for (int c = 0; c < n_checkpoints; ++c) {
+      for (; done < checkpoints[c]; ++done) fp.step(done % 2);
+      dump_dense(fp.last_strategies, last ? last + c * dense : nullptr);
+      dump_dense(fp.sum_strategies, sum ? sum + c * dense : nullptr);
+      dump_dense(fp.average_strategies, avg ? avg + c * dense : nullptr);
+      if (root_means) {
+        for (int p = 0; p < 2; ++p)
+          for (int h = 0; h < H; ++h)
+            root_means[(c * 2 + p) * H + h] = (int)fp.root_values_means[p].size() == H ? fp.root_values_means[p][h] : 0.0;
+      }
+    }
+    return (int)N;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // Full-tree exploitability of a dense [N][H][A] strategy (subgame_solving.cc:802-816).
 int ref_exploitability(int D, int F, const double* strategy, double* out2) {
   try {
@@ -295,9 +337,25 @@ int ref_exploitability(int D, int F, const double* strategy, double* out2) {
 
 // Runs RlRunner::step (recursive_solving.cc:160-182) `n_games` times with seed, recording every
 // training example.  net_w == nullptr -> zero net.  Returns #examples, fills up to cap.
+static int rl_runner_impl(int D, int F, int num_iters, int max_depth, int linear_update, float random_action_prob,
+                          int sample_leaf, int seed, int n_games, const float* net_w, int hidden, float* q_out, float* v_out,
+                          int cap, bool use_cfr);
 int ref_rl_runner(int D, int F, int num_iters, int max_depth, int linear_update,
                   float random_action_prob, int sample_leaf, int seed, int n_games,
                   const float* net_w, int hidden, float* q_out, float* v_out, int cap) {
+  return rl_runner_impl(D, F, num_iters, max_depth, linear_update, random_action_prob, sample_leaf, seed, n_games, net_w, hidden,
+                        q_out, v_out, cap, true);
+}
+// Same walk with the fictitious-play solver (SubgameSolvingParams::use_cfr = false, the YAML default).
+int ref_rl_runner_fp(int D, int F, int num_iters, int max_depth, int linear_update,
+                     float random_action_prob, int sample_leaf, int seed, int n_games,
+                     const float* net_w, int hidden, float* q_out, float* v_out, int cap) {
+  return rl_runner_impl(D, F, num_iters, max_depth, linear_update, random_action_prob, sample_leaf, seed, n_games, net_w, hidden,
+                        q_out, v_out, cap, false);
+}
+static int rl_runner_impl(int D, int F, int num_iters, int max_depth, int linear_update, float random_action_prob,
+                          int sample_leaf, int seed, int n_games, const float* net_w, int hidden, float* q_out, float* v_out,
+                          int cap, bool use_cfr) {
   try {
     Game game(D, F);
     const int H = game.num_hands(), A = game.num_actions(), Q = 2 + A + 2 * H;
@@ -307,6 +365,7 @@ int ref_rl_runner(int D, int F, int num_iters, int max_depth, int linear_update,
     cfg.random_action_prob = random_action_prob;
     cfg.sample_leaf = sample_leaf != 0;
     cfg.subgame_params = make_params(num_iters, max_depth, linear_update, 0, 0, 0, 0);
+    cfg.subgame_params.use_cfr = use_cfr;
     std::vector<float>*eq, *ev;
     std::shared_ptr<IValueNet> net;
     if (net_w) {

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfrb200.so")
 
 NET_ZERO, NET_FP32, NET_TC_F16, NET_TC_F16X2 = 0, 1, 2, 3
+SOLVER_CFR, SOLVER_FP = 0, 1
 STATE_F64, STATE_F32 = 0, 1
 
 
@@ -25,7 +26,7 @@ class Config(C.Structure):
         ("linear_update", C.c_int32), ("dcfr", C.c_int32),
         ("dcfr_alpha", C.c_double), ("dcfr_beta", C.c_double), ("dcfr_gamma", C.c_double),
         ("max_subgames", C.c_int32), ("device", C.c_int32), ("net_mode", C.c_int32), ("hidden", C.c_int32),
-        ("state_dtype", C.c_int32),
+        ("state_dtype", C.c_int32), ("solver", C.c_int32), ("optimistic", C.c_int32),
     ]
 
 
@@ -102,10 +103,10 @@ class WaveSolver:
 
     def __init__(self, num_dice, num_faces, max_subgames, max_depth=2, num_iters=1024, linear_update=True, dcfr=False,
                  dcfr_alpha=0.0, dcfr_beta=0.0, dcfr_gamma=0.0, net_mode=NET_FP32, hidden=256, device=0,
-                 state_dtype=STATE_F64):
+                 state_dtype=STATE_F64, solver=SOLVER_CFR, optimistic=False):
         L = lib()
         self.cfg = Config(num_dice, num_faces, max_depth, num_iters, int(linear_update), int(dcfr), dcfr_alpha, dcfr_beta,
-                          dcfr_gamma, max_subgames, device, net_mode, hidden, state_dtype)
+                          dcfr_gamma, max_subgames, device, net_mode, hidden, state_dtype, int(solver), int(optimistic))
         self._h = C.c_void_p()
         _check(L.cfrb_create(C.byref(self.cfg), C.byref(self._h)))
         self.A = L.cfrb_num_actions(self._h)

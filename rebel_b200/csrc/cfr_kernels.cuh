@@ -314,6 +314,119 @@ __device__ void cfr_backward(const CfrDev<real>& p, int k, int trav, real* val, 
   if (lane == 0) p.steps[2 * k + trav] = s + 1;
 }
 
+// Backward half of a FICTITIOUS-PLAY iteration with traverser `trav` (FP::step, subgame_solving.cc:423-460): best response
+// against the average strategy (BRSolver::compute_br :316-358), root value running mean, update_sum_strat (:391-421), linear
+// discount and re-normalisation of the average strategy.  Table roles in FP mode: Sg = average_strategies (the strategy
+// the reach / queries / sampling use), S = sum_strategies, R = last_strategies (belief x best response).
+template <typename real, int G, int HC>
+__device__ void fp_backward(const CfrDev<real>& p, int k, int trav, real* val, real* rt, int lane) {
+  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
+  const int H = HC > 0 ? HC : p.H;
+  const int rp = p.sg_player[k];
+  real* __restrict__ Last = p.R + (size_t)k * p.table_stride;
+  real* __restrict__ Avg = p.Sg + (size_t)k * p.table_stride;
+  real* __restrict__ S = p.S + (size_t)k * p.table_stride;
+  const int* __restrict__ parent = p.parent + t.node_off;
+  const int* __restrict__ nchild = p.nchild + t.node_off;
+  const int* __restrict__ child_begin = p.child_begin + t.node_off;
+  const int row0 = p.sg_row_off[k];
+  for (int it = lane; it < t.L * H; it += G) {
+    const int r = it / H, h = it % H;
+    const int n = p.pleaf_node[t.pleaf_off + r];
+    val[n * H + h] = p.use_net ? (real)(float)((real)p.net_out[(size_t)(row0 + r) * p.Hout + h] * p.scaler[row0 + r]) : (real)0;
+  }
+  const real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
+  for (int it = lane; it < t.T * H; it += G) {
+    const int z = it / H, h = it % H;
+    val[p.term_node[t.term_off + z] * H + h] = vt[z * H + h];
+  }
+  group_sync<G>();
+  // ---- bottom-up best response: max over the children at the traverser's nodes (first child wins ties, :336-337; the
+  // one-hot br_strategies go to rt as 0/1 flags in the children's slots), plain sums at the opponent's
+  for (int d = t.levels - 2; d >= 0; --d) {
+    const int nb = p.level_begin[t.level_off + d], ne = p.level_begin[t.level_off + d + 1];
+    const bool mine = (rp ^ (d & 1)) == trav;
+    for (int it = lane; it < (ne - nb) * H; it += G) {
+      const int n = nb + it / H, h = it % H;
+      const int nc = nchild[n];
+      if (!nc) continue;
+      const int c0 = child_begin[n];
+      real v = 0;
+      if (mine) {
+        int best = 0;
+        v = val[c0 * H + h];
+        for (int j = 1; j < nc; ++j) {
+          const real nv = val[(c0 + j) * H + h];
+          if (nv > v) { v = nv; best = j; }
+        }
+        for (int j = 0; j < nc; ++j) rt[(c0 + j) * H + h] = (j == best) ? (real)1 : (real)0;
+      } else {
+        for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h];
+      }
+      val[n * H + h] = v;
+    }
+    group_sync<G>();
+  }
+  // ---- root value running mean (:428-440): num_update = num_strategies / 2 + 1 = steps[trav] + 1 for alternating traversers
+  const int s = p.steps[2 * k + trav];
+  {
+    const real alpha = p.linear ? (real)2 / (s + 2) : (real)1 / (s + 1);
+    real* mu = p.mu + ((size_t)k * 2 + trav) * H;
+    for (int h = lane; h < H; h += G) mu[h] += (val[h] - mu[h]) * alpha;
+  }
+  const real disc = (real)(s + 2) / (s + 3);        // (num_update + 1) / (num_update + 2), :447-449
+  group_sync<G>();
+  // ---- top-down update_sum_strat: val now carries the traverser's beliefs (belief x best response along the path)
+  const real* __restrict__ b = p.beliefs + ((size_t)k * 2 + trav) * H;
+  for (int h = lane; h < H; h += G) val[h] = b[h];
+  group_sync<G>();
+  for (int d = 0; d + 1 < t.levels; ++d) {
+    const int nb = p.level_begin[t.level_off + d], ne = p.level_begin[t.level_off + d + 1];
+    const int cb = ne, ce = p.level_begin[t.level_off + d + 2];
+    const bool mine = (rp ^ (d & 1)) == trav;
+    if (mine) {
+      for (int it = lane; it < (ce - cb) * H; it += G) {
+        const int c = cb + it / H, h = it % H;
+        const int e = (c - 1) * H + h;
+        const real x = val[parent[c] * H + h] * rt[c * H + h];     // traverser_beliefs * br_strategies
+        real sn = S[e] + x;
+        if (p.linear) sn = sn * disc;
+        S[e] = sn; Last[e] = x;
+        val[c * H + h] = x;                                        // beliefs of the child
+        rt[c * H + h] = sn;
+      }
+      group_sync<G>();
+      for (int it = lane; it < (ne - nb) * H; it += G) {           // normalize_probabilities (util.h:20-34 / 52-63)
+        const int n = nb + it / H, h = it % H;
+        const int nc = nchild[n];
+        if (!nc) continue;
+        const int c0 = child_begin[n];
+        real tot = 0;
+        for (int j = 0; j < nc; ++j) tot += rt[(c0 + j) * H + h];
+        if (p.optimistic) {
+          real tl = 0;
+          for (int j = 0; j < nc; ++j) tl += val[(c0 + j) * H + h];
+          tot = tot + tl;
+        }
+        val[n * H + h] = tot;
+      }
+      group_sync<G>();
+      for (int it = lane; it < (ce - cb) * H; it += G) {
+        const int c = cb + it / H, h = it % H;
+        const real tot = val[parent[c] * H + h];
+        Avg[(c - 1) * H + h] = (p.optimistic ? rt[c * H + h] + val[c * H + h] : rt[c * H + h]) / tot;
+      }
+    } else {
+      for (int it = lane; it < (ce - cb) * H; it += G) {
+        const int c = cb + it / H, h = it % H;
+        val[c * H + h] = val[parent[c] * H + h];
+      }
+    }
+    group_sync<G>();
+  }
+  if (lane == 0) p.steps[2 * k + trav] = s + 1;
+}
+
 // iter: global iteration index of the forward half.  do_b: run backward half of iteration iter-1 first.
 template <typename real, int G, int HC>
 __global__ void __launch_bounds__(512) cfr_iter_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
@@ -328,7 +441,8 @@ __global__ void __launch_bounds__(512) cfr_iter_kernel(CfrDev<real> p, int iter,
   real* bufA = base; real* bufB = base + p.nh_max; real* tmp = base + 2 * p.nh_max; real* lsum = tmp + p.tmp_reals;
   const int tb = (iter - 1) & 1;
   if (do_b) {
-    cfr_backward<real, G, HC>(p, k, tb, bufA, bufB, lane);   // leaves the reach of player tb (new strategy) in bufB
+    if (p.fp) fp_backward<real, G, HC>(p, k, tb, bufA, bufB, lane);
+    else cfr_backward<real, G, HC>(p, k, tb, bufA, bufB, lane);   // leaves the reach of player tb (new strategy) in bufB
     group_sync<G>();
   }
   // sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
@@ -338,7 +452,7 @@ __global__ void __launch_bounds__(512) cfr_iter_kernel(CfrDev<real> p, int iter,
     for (int i = lane; i < (t.N - 1) * p.H; i += G) Sn[i] = Sg[i];
   }
   if (do_f) {
-    if (do_b) cfr_forward<real, G, HC>(p, k, iter & 1, tb == 0 ? bufB : bufA, tb == 0 ? bufA : bufB, tb, lsum, tmp, lane);
+    if (do_b && !p.fp) cfr_forward<real, G, HC>(p, k, iter & 1, tb == 0 ? bufB : bufA, tb == 0 ? bufA : bufB, tb, lsum, tmp, lane);
     else      cfr_forward<real, G, HC>(p, k, iter & 1, bufA, bufB, -1, lsum, tmp, lane);
   }
 }
@@ -653,7 +767,7 @@ __global__ void __launch_bounds__(512) cfr_init_kernel(CfrDev<real> p, int scrat
       const real u = (real)1 / nchild[par];
       const real a0 = reach0[par * H + h], a1 = reach1[par * H + h];
       Sg[e] = u;
-      R[e] = 0;
+      R[e] = p.fp ? u : (real)0;       // FP: last_strategies starts as the uniform strategy (subgame_solving.cc:375-377)
       S[e] = u * (actor == 0 ? a0 : a1);
       reach0[c * H + h] = actor == 0 ? a0 * u : a0;
       reach1[c * H + h] = actor == 1 ? a1 * u : a1;

@@ -40,6 +40,7 @@ struct CfrDev {
   // params
   int linear, dcfr; real dcfr_alpha, dcfr_beta, dcfr_gamma;
   int use_net;
+  int fp, optimistic;             // fictitious play instead of CFR (FP, subgame_solving.cc:364-506)
 };
 
 // Scratch of a group (reals): bufA[N*H] | bufB[N*H] | hist[10*T] | lsum[2*L]  (hist: per-terminal match-count histogram,

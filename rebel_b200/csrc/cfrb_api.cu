@@ -149,7 +149,7 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
     const int smem_bytes = (int)(per_group_bytes * h->groups_per_cta);
     CK(cfrb::cfr_configure<real>(32, smem_bytes));
     const char* no_d2 = std::getenv("CFRB_NO_D2");
-    if (h->max_levels <= 3 && !(no_d2 && *no_d2 == '1')) {
+    if (h->max_levels <= 3 && h->cfg.solver == CFRB_SOLVER_CFR && !(no_d2 && *no_d2 == '1')) {
       // 4 CTAs of up to 8 warps per SM (register file: 64 registers x 32 warps), each with 1 KB reserved by the runtime
       h->d2 = true;
       h->d2_scratch_per_group = cfrb::cfr_scratch_reals_d2(h->Nmax, h->g.H, h->Lmax, h->Tmax);
@@ -180,6 +180,7 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   d.linear = h->cfg.linear_update; d.dcfr = h->cfg.dcfr;
   d.dcfr_alpha = (real)h->cfg.dcfr_alpha; d.dcfr_beta = (real)h->cfg.dcfr_beta; d.dcfr_gamma = (real)h->cfg.dcfr_gamma;
   d.use_net = h->cfg.net_mode != CFRB_NET_ZERO;
+  d.fp = h->cfg.solver == CFRB_SOLVER_FP; d.optimistic = h->cfg.optimistic;
   return CFRB_OK;
 }
 
@@ -284,10 +285,12 @@ static int fetch_t(cfrb_handle* h, double* root_value_means, double* snapshot_st
   };
   int rc = CFRB_OK;
   if (snapshot_strategy && (rc = pull(s.Snap.p, snapshot_strategy, false))) return rc;
-  if (last_strategy && (rc = pull(s.Sg.p, last_strategy, false))) return rc;
-  if (avg_strategy && (rc = pull(s.S.p, avg_strategy, true))) return rc;
+  const bool fp = h->cfg.solver == CFRB_SOLVER_FP;   // FP: Sg = average_strategies, R = last_strategies
+  if (last_strategy && (rc = pull(fp ? s.R.p : s.Sg.p, last_strategy, false))) return rc;
+  if (avg_strategy && (rc = fp ? pull(s.Sg.p, avg_strategy, false) : pull(s.S.p, avg_strategy, true))) return rc;
   if (sum_strategy && (rc = pull(s.S.p, sum_strategy, false))) return rc;
-  if (regrets && (rc = pull(s.R.p, regrets, false))) return rc;
+  if (regrets && fp) std::fill(regrets, regrets + (size_t)n * dense_sz, 0.0);
+  if (regrets && !fp && (rc = pull(s.R.p, regrets, false))) return rc;
   return CFRB_OK;
 }
 
@@ -390,6 +393,7 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     return fail(CFRB_EINVAL, "num_dice, num_faces, max_depth, max_subgames must be >= 1");
   if (cfg->net_mode < CFRB_NET_ZERO || cfg->net_mode > CFRB_NET_TC_F16X2) return fail(CFRB_EINVAL, "bad net_mode");
   if (cfg->state_dtype != CFRB_STATE_F64 && cfg->state_dtype != CFRB_STATE_F32) return fail(CFRB_EINVAL, "bad state_dtype");
+  if (cfg->solver != CFRB_SOLVER_CFR && cfg->solver != CFRB_SOLVER_FP) return fail(CFRB_EINVAL, "bad solver");
   if (cfg->net_mode != CFRB_NET_ZERO && cfg->hidden != 256) return fail(CFRB_EINVAL, "only hidden == 256 is built");
   h->f64 = cfg->state_dtype == CFRB_STATE_F64;
   h->g = cfrb::GameShape(cfg->num_dice, cfg->num_faces);

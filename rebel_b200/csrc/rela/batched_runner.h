@@ -33,8 +33,9 @@ class BatchedRlRunner {
   BatchedRlRunner(const liars_dice::RecursiveSolvingParams& cfg, int device, int seed)
       : cfg_(cfg), K_(std::max(1, cfg.concurrent_games)) {
     const auto& sp = cfg.subgame_params;
-    if (!sp.use_cfr) throw std::runtime_error("rebel_b200 accelerates the CFR solver: set subgame_params.use_cfr=true");
     cfrb_config c{};
+    c.solver = sp.use_cfr ? CFRB_SOLVER_CFR : CFRB_SOLVER_FP;   // build_solver (subgame_solving.cc:791-800)
+    c.optimistic = sp.optimistic;
     c.num_dice = cfg.num_dice; c.num_faces = cfg.num_faces; c.max_depth = sp.max_depth; c.num_iters = sp.num_iters;
     c.linear_update = sp.linear_update; c.dcfr = sp.dcfr; c.dcfr_alpha = sp.dcfr_alpha; c.dcfr_beta = sp.dcfr_beta;
     c.dcfr_gamma = sp.dcfr_gamma; c.max_subgames = K_; c.device = device; c.net_mode = cfg.net_mode; c.hidden = 256;

@@ -274,6 +274,43 @@ def test_discount_variants_vs_reference(rb, golden, port, D, F, max_depth):
         S.close()
 
 
+@pytest.mark.parametrize("D,F", SHAPES)
+def test_fictitious_play_bit_exact_vs_reference(rb, golden, port, net_weights, D, F):
+    """CFRB_SOLVER_FP (the reference's other ISubgameSolver, build_solver with use_cfr = false): zero net, fp64 tables —
+    33-iteration trajectories of last / sum / average strategies and root value means are bit-identical to the compiled
+    reference for linear, plain and optimistic averaging at depth 2, 3 and full depth; with the fp32 value net two iterations
+    from the initial state agree with the oracle to fp32 accuracy."""
+    from oracle.make_golden import FP_CASES, FP_CPS, FP_ROOTS
+    g = golden("fp_zero.npz")
+    b = g[f"beliefs_{D}x{F}"]
+    for (lin, opt, md) in FP_CASES:
+        if md > 3 and (D, F) != (1, 4):
+            continue
+        S = rb.WaveSolver(D, F, len(FP_ROOTS), max_depth=md, net_mode=rb.NET_ZERO, linear_update=lin, solver=rb.SOLVER_FP, optimistic=opt)
+        S.begin(np.array([r[0] for r in FP_ROOTS], np.int32), np.array([r[1] for r in FP_ROOTS], np.int32), np.stack([b] * len(FP_ROOTS)))
+        done = 0
+        for ci, c in enumerate(FP_CPS):
+            S.run(c - done); done = c
+            f = S.fetch(("root_means", "last", "sum", "avg"))
+            for i, (lb, pl) in enumerate(FP_ROOTS):
+                for k in ("last", "sum", "avg"):
+                    y = g[f"{k}_{int(lin)}{int(opt)}{md}_{lb}_{D}x{F}"][ci]
+                    x = f[k][i, :y.shape[0]]
+                    assert np.array_equal(x, y), (lin, opt, md, lb, k, c, np.abs(x - y).max())
+                assert np.array_equal(f["root_means"][i], g[f"root_means_{int(lin)}{int(opt)}{md}_{lb}_{D}x{F}"][ci]), (lin, opt, md, lb, c)
+        S.close()
+    w = net_weights(D, F)
+    S = rb.WaveSolver(D, F, 1, net_mode=rb.NET_FP32, solver=rb.SOLVER_FP)
+    S.set_weights(w)
+    S.begin([-1], [0], b[None])
+    S.run(2)
+    o = port.fp_solve(D, F, b, [2], -1, 0, num_iters=2, net_w=w)
+    f = S.fetch(("root_means", "avg", "sum"))
+    assert np.abs(f["root_means"][0] - o["root_means"][0]).max() < 3e-6
+    assert np.abs(f["sum"][0, :o["sum"].shape[1]] - o["sum"][0]).max() < 1e-5
+    S.close()
+
+
 # ---------------------------------------------------------------------------------------------- P4
 @pytest.mark.parametrize("D,F", SHAPES)
 @pytest.mark.parametrize("net_name", ["fp32", "tc", "tcx2"])

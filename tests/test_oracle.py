@@ -154,6 +154,21 @@ def test_cfr_discount_variants_bit_exact_vs_golden(port, golden, D, F):
 
 
 @pytest.mark.parametrize("D,F", SHAPES)
+def test_fictitious_play_bit_exact_vs_golden(port, golden, D, F):
+    """FP (subgame_solving.cc:364-506): linear / plain / optimistic averaging, depth 2, 3 and full depth — the C port follows
+    the compiled reference bit for bit (fixture from oracle/make_golden.py)."""
+    from oracle.make_golden import FP_CASES, FP_CPS, FP_ROOTS
+    g = golden("fp_zero.npz")
+    for (lin, opt, md) in FP_CASES:
+        if md > 3 and (D, F) != (1, 4):
+            continue
+        for (lb, pl) in FP_ROOTS:
+            s = port.fp_solve(D, F, g[f"beliefs_{D}x{F}"], FP_CPS, lb, pl, num_iters=max(FP_CPS), max_depth=md, linear_update=lin, optimistic=opt)
+            for k in ("last", "sum", "avg", "root_means"):
+                assert np.array_equal(s[k], g[f"{k}_{int(lin)}{int(opt)}{md}_{lb}_{D}x{F}"]), (lin, opt, md, lb, k)
+
+
+@pytest.mark.parametrize("D,F", SHAPES)
 def test_cfr_net_short_horizon_vs_golden(port, golden, net_weights, D, F):
     g = golden(f"cfr_net_{D}x{F}.npz")
     w = net_weights(D, F)

@@ -187,6 +187,19 @@ def test_batched_walk_reproduces_rlrunner_stream(rela, golden, D, F, sample_leaf
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("D,F", [(1, 4), (1, 6), (2, 3)])
+def test_batched_walk_with_fictitious_play_reproduces_rlrunner_stream(rela, golden, D, F):
+    """use_cfr = false (the YAML default, subgame_solving.h:48): build_solver returns FP; the example stream of one game
+    stream is bit-identical to the reference's RlRunner(seed=7) with the fictitious-play solver."""
+    g = golden("selfplay_zero.npz")
+    gq, gv = g[f"q_fp_{D}x{F}"], g[f"v_fp_{D}x{F}"]
+    cfg = make_cfg(rela, D, F, sample_leaf=True, concurrent_games=1, net_mode=0, state_dtype=0,
+                   subgame_params=dict(num_iters=32, max_depth=2, linear_update=True, use_cfr=False))
+    q, v = rela.run_selfplay_waves(cfg, 0, 7, len(gq) // 2)
+    assert np.array_equal(q.numpy(), gq) and np.array_equal(v.numpy(), gv)
+
+
+@pytest.mark.gpu
 def test_drop_in_datagen_flow(rela):
     """initialize_datagen (selfplay.py:182-260) line for line: ModelLocker per device, replay, create_cfr_thread per
     'thread', Context.start; then update_model, pause/resume, terminate."""
