@@ -11,6 +11,7 @@
 // its leaves, and the accumulation `sum += float(strategy) * float(reach)` runs in strategy_id order per node.
 #pragma once
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -18,6 +19,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -208,16 +210,20 @@ class RecursiveEvaluator {
         act[r][root] = dist(gen);
       }
     }
+    for (int a = 0; a < A_; ++a) tmpl(a - 1);     // build every template up front: the worker threads only read them
     // level 0: the game root with uniform beliefs
     std::vector<Pending> cur, next;
     for (int r = 0; r < count; ++r) cur.push_back(Pending{r, 0, std::vector<double>((size_t)2 * H_, 1.0 / H_), std::vector<double>((size_t)2 * H_, 1.0 / H_)});
     std::vector<int32_t> lb, pl, ai;
-    std::vector<double> bel, snap;
+    std::vector<double> bel;
+    std::vector<double> snap[2];
     while (!cur.empty()) {
       next.clear();
+      // Software pipeline over the chunks of this level: the GPU solves chunk i while the host walks chunk i-1.
+      size_t prev_off = 0; int prev_n = 0, slot = 0;
       for (size_t off = 0; off < cur.size(); off += K_) {
         const int n = (int)std::min<size_t>(K_, cur.size() - off);
-        lb.resize(n); pl.resize(n); ai.resize(n); bel.resize((size_t)n * 2 * H_); snap.resize((size_t)n * stride_);
+        lb.resize(n); pl.resize(n); ai.resize(n); bel.resize((size_t)n * 2 * H_);
         int max_act = 0;
         for (int i = 0; i < n; ++i) {
           const Pending& P = cur[off + i];
@@ -227,32 +233,80 @@ class RecursiveEvaluator {
         }
         const auto t0 = std::chrono::steady_clock::now();
         if (cfrb_begin_wave(h_, n, lb.data(), pl.data(), bel.data(), ai.data()) < 0) throw std::runtime_error(cfrb_last_error());
-        if (cfrb_run(h_, max_act, nullptr) < 0) throw std::runtime_error(cfrb_last_error());
-        if (cfrb_fetch_compact(h_, 0, snap.data()) < 0) throw std::runtime_error(cfrb_last_error());
+        if (cfrb_run(h_, max_act, nullptr) < 0) throw std::runtime_error(cfrb_last_error());   // asynchronous
         res.gpu_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (prev_n) expandChunk(cur, prev_off, prev_n, snap[slot ^ 1].data(), res, next);
+        const auto t1 = std::chrono::steady_clock::now();
+        snap[slot].resize((size_t)n * stride_);
+        if (cfrb_fetch_compact(h_, 0, snap[slot].data()) < 0) throw std::runtime_error(cfrb_last_error());
+        res.gpu_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
         res.subgames_solved += n;
-        for (int i = 0; i < n; ++i) expand(cur[off + i], snap.data() + (size_t)i * stride_, res, next);
+        prev_off = off; prev_n = n; slot ^= 1;
       }
+      if (prev_n) expandChunk(cur, prev_off, prev_n, snap[slot ^ 1].data(), res, next);
       cur.swap(next);
     }
   }
 
-  // BFS over one solved subgame (recursive_solving.cc:97-133): accumulate strategy x reach of its inner nodes, propagate
-  // beliefs / reach to its pseudo-leaves and queue the next-level subgames.
-  void expand(const Pending& P, const double* sigma, RecursiveEvalResult& res, std::vector<Pending>& next) {
-    const auto& t = tmpl(full_[P.root].last_bid);
-    const int rp = full_[P.root].player_id;
-    struct Item { int full, part; std::vector<double> beliefs, reach; };
-    std::deque<Item> q;
-    q.push_back(Item{P.root, 0, P.beliefs, P.reach});
-    while (!q.empty()) {
-      Item it = std::move(q.front());
-      q.pop_front();
-      const int pnc = t[it.part].children_end - t[it.part].children_begin;
-      const int fnc = full_[it.full].children_end - full_[it.full].children_begin;
-      const int pid = full_[it.full].player_id;
+  // Walks the solved subgames cur[off, off+n).  Subgames with the same full-tree root (different repeats) update the same
+  // accumulator entries and must do so in repeat order (float32 sums, recursive_eval.cc:349-355), so the work is split by
+  // root: one thread handles all repeats of a root, in order; different roots touch disjoint nodes.
+  void expandChunk(const std::vector<Pending>& cur, size_t off, int n, const double* snap, RecursiveEvalResult& res,
+                   std::vector<Pending>& next) {
+    std::vector<int> roots;                          // distinct roots in order of first appearance
+    std::vector<std::vector<int>> members;
+    {
+      std::vector<int> slot_of(full_.size(), -1);
+      for (int i = 0; i < n; ++i) {
+        const int r = cur[off + i].root;
+        if (slot_of[r] < 0) { slot_of[r] = (int)roots.size(); roots.push_back(r); members.emplace_back(); }
+        members[slot_of[r]].push_back(i);
+      }
+    }
+    const int G = (int)roots.size();
+    std::vector<std::vector<Pending>> out(G);
+    const int T = std::max(1, std::min<int>({G, (int)std::thread::hardware_concurrency(), 16}));
+    std::atomic<int> nextg{0};
+    auto work = [&]() {
+      std::vector<double> bel, rch;
+      for (;;) {
+        const int g = nextg.fetch_add(1);
+        if (g >= G) break;
+        for (int i : members[g]) expand(cur[off + i], snap + (size_t)i * stride_, res, out[g], bel, rch);
+      }
+    };
+    if (T == 1) {
+      work();
+    } else {
+      std::vector<std::thread> th;
+      for (int i = 0; i < T; ++i) th.emplace_back(work);
+      for (auto& x : th) x.join();
+    }
+    for (auto& v : out)
+      for (auto& P : v) next.push_back(std::move(P));
+  }
+
+  // One solved subgame (recursive_solving.cc:97-133): accumulate strategy x reach of its inner nodes, propagate beliefs /
+  // reach to its pseudo-leaves and queue the next-level subgames.  Node order = the reference's BFS = template index order
+  // (parents before children), so flat per-node arrays replace its queue of belief copies.
+  void expand(const Pending& P, const double* sigma, RecursiveEvalResult& res, std::vector<Pending>& next, std::vector<double>& bel,
+              std::vector<double>& rch) const {
+    const auto& t = trees_[full_[P.root].last_bid + 1];
+    const int n_part = (int)t.size(), W = 2 * H_;
+    bel.resize((size_t)n_part * W); rch.resize((size_t)n_part * W);
+    std::vector<int> full_id(n_part);
+    full_id[0] = P.root;
+    std::copy(P.beliefs.begin(), P.beliefs.end(), bel.begin());
+    std::copy(P.reach.begin(), P.reach.end(), rch.begin());
+    for (int pn = 0; pn < n_part; ++pn) {
+      const int fn = full_id[pn];
+      const int pnc = t[pn].children_end - t[pn].children_begin;
+      const int fnc = full_[fn].children_end - full_[fn].children_begin;
+      const int pid = full_[fn].player_id;
+      double* nb = &bel[(size_t)pn * W];
+      double* nr = &rch[(size_t)pn * W];
       if (pnc == 0 && fnc != 0) {   // non-terminal leaf of the subgame: root of a subgame on the next level (:127-132)
-        Pending C{P.repeat, it.full, std::move(it.beliefs), std::move(it.reach)};
+        Pending C{P.repeat, fn, std::vector<double>(nb, nb + W), std::vector<double>(nr, nr + W)};
         normalize(C.beliefs.data());
         normalize(C.beliefs.data() + H_);
         next.push_back(std::move(C));
@@ -260,19 +314,22 @@ class RecursiveEvaluator {
       }
       // weight of infoset (node, hand) = reach_probabilities[player(node)][node][hand] under the sampled strategy
       // (recursive_eval.cc:143-148; compute_stategy_stats, subgame_solving.cc:839-842), accumulated in float32
-      for (int h = 0; h < H_; ++h) res.summed_reach[(size_t)it.full * H_ + h] += (float)it.reach[(size_t)pid * H_ + h];
+      for (int h = 0; h < H_; ++h) res.summed_reach[(size_t)fn * H_ + h] += (float)nr[(size_t)pid * H_ + h];
       if (pnc == 0) continue;   // terminal node
-      const int lo = t[it.part].last_bid < 0 ? 0 : t[it.part].last_bid + 1;
+      const int lo = t[pn].last_bid < 0 ? 0 : t[pn].last_bid + 1;
       for (int j = 0; j < pnc; ++j) {
-        const int pc = t[it.part].children_begin + j, action = lo + j;
-        Item ch{full_[it.full].children_begin + j, pc, it.beliefs, it.reach};
+        const int pc = t[pn].children_begin + j, action = lo + j;
+        full_id[pc] = full_[fn].children_begin + j;
+        double* cb = &bel[(size_t)pc * W];
+        double* cr = &rch[(size_t)pc * W];
+        std::copy(nb, nb + W, cb);
+        std::copy(nr, nr + W, cr);
         for (int h = 0; h < H_; ++h) {
           const double s = sigma[(size_t)(pc - 1) * H_ + h];
-          res.summed_strategy[((size_t)it.full * H_ + h) * A_ + action] += (float)s * (float)it.reach[(size_t)pid * H_ + h];
-          ch.beliefs[(size_t)pid * H_ + h] *= s;
-          ch.reach[(size_t)pid * H_ + h] *= s;
+          res.summed_strategy[((size_t)fn * H_ + h) * A_ + action] += (float)s * (float)nr[(size_t)pid * H_ + h];
+          cb[(size_t)pid * H_ + h] *= s;
+          cr[(size_t)pid * H_ + h] *= s;
         }
-        q.push_back(std::move(ch));
       }
     }
   }
