@@ -162,8 +162,8 @@ int cfrb_iterations_done(const cfrb_handle* h);
 int cfrb_fetch(cfrb_handle* h, double* root_value_means, double* snapshot_strategy, double* last_strategy,
                double* avg_strategy, double* sum_strategy, double* regrets);
 
-/* Compact fetch for host orchestration (BatchedRlRunner): table `which` (0 snapshot, 1 last strategy, 2 sum strategy,
- * 3 regrets) of every subgame as stored on the device, [n][cfrb_table_stride()] fp64 with entry (child_node - 1) * H + hand
+/* Compact fetch for host orchestration (BatchedRlRunner, evaluators): table `which` (0 snapshot, 1 last strategy, 2 sum strategy,
+ * 3 regrets, 4 average strategy = ISubgameSolver::get_strategy) of every subgame as stored on the device, [n][cfrb_table_stride()] fp64 with entry (child_node - 1) * H + hand
  * holding the value of (parent node, hand, action leading to child_node).  Synchronises. */
 int cfrb_table_stride(const cfrb_handle* h);
 int cfrb_fetch_compact(cfrb_handle* h, int32_t which, double* out);

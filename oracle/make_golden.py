@@ -35,6 +35,19 @@ FP_CASES = [(True, False, 2), (False, False, 2), (True, True, 2), (True, False, 
 FP_ROOTS = [(-1, 0), (2, 1)]
 
 
+EVAL_CASES = [(1, 4, 32), (1, 6, 16), (2, 3, 8)]
+
+
+def eval_weights(D, F, name):
+    """Flat Net2 weights of the evaluation fixtures: seed-0 random init, optionally with the output layer zeroed."""
+    from rebel_b200.models import flatten_state_dict, make_selfplay_net
+    sd = make_selfplay_net(D, F, seed=0).state_dict()
+    if name == "zero_out":
+        sd["output.weight"] = sd["output.weight"] * 0
+        sd["output.bias"] = sd["output.bias"] * 0
+    return flatten_state_dict(sd)
+
+
 def recursive_eval_reference(lib, D, F, num_iters, num_repeats, net_w=None, keep=2):
     """The accumulation loop of the reference's recursive_eval main (recursive_eval.cc:343-369) around its own
     compute_sampled_strategy_recursive_to_leaf and compute_stategy_stats, float32 tensors emulated with numpy."""
@@ -174,6 +187,20 @@ def main():
                 out[f"{k}_{D}x{F}"] = v
         out[f"cfg_{D}x{F}"] = np.array([iters, reps])
     np.savez_compressed(os.path.join(OUT, "recursive_eval_zero.npz"), **out)
+
+    # ---- evaluation entry points of the rela module (pybind.cc:45-84): compute_strategy_recursive / _to_leaf + exploitability +
+    # eval_net, with a Net2 whose output layer is zeroed (exact: the net contributes exact zeros) and with the random-init net
+    out = {"cases": np.array([f"{D}x{F}:{it}" for D, F, it in EVAL_CASES])}
+    for (D, F, it) in EVAL_CASES:
+        for use_cfr in (True, False):
+            for netname in ("zero_out", "random"):
+                r = R.net_evaluation(D, F, eval_weights(D, F, netname), num_iters=it, use_cfr=use_cfr)
+                tag = f"{'cfr' if use_cfr else 'fp'}_{netname}_{D}x{F}"
+                out[f"values_{tag}"] = r["values"]
+                if (D, F) == (1, 4):
+                    out[f"strategy_recursive_{tag}"] = r["strategy_recursive"]
+                    out[f"strategy_to_leaf_{tag}"] = r["strategy_to_leaf"]
+    np.savez_compressed(os.path.join(OUT, "net_evaluation.npz"), **out)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -155,6 +155,23 @@ class Oracle:
         out["root_means"] = rm
         return out
 
+    def net_evaluation(self, D, F, net_w, num_iters=64, max_depth=2, linear_update=True, use_cfr=True, hidden=256, what=3):
+        """rela/pybind.cc:45-84 with flat Net2 weights (reference builds only): dict with strategy_recursive / strategy_to_leaf
+        [N,H,A] and values = [expl(recursive), expl(to_leaf), eval_net mse (net beliefs), eval_net mse (full-tree beliefs)]."""
+        assert self.kind != "port"
+        A, H, Q = game_dims(D, F)
+        N = len(self.unroll_tree(D, F))
+        sr, sl = np.zeros((N, H, A)), np.zeros((N, H, A))
+        out = np.zeros(4)
+        w = np.ascontiguousarray(net_w, np.float32)
+        f = self._f("net_evaluation")
+        f.argtypes = [C.c_int] * 6 + [_fp] + [C.c_int] * 2 + [_dp] * 3
+        n = f(int(D), int(F), int(num_iters), int(max_depth), int(linear_update), int(use_cfr), _ptr(w, _fp), hidden, int(what),
+              _ptr(sr, _dp), _ptr(sl, _dp), _ptr(out, _dp))
+        if n < 0:
+            raise RuntimeError(self._f("last_error")().decode())
+        return {"strategy_recursive": sr, "strategy_to_leaf": sl, "values": out}
+
     def exploitability(self, D, F, strategy):
         s = np.ascontiguousarray(strategy, np.float64)
         out = np.zeros(2, np.float64)

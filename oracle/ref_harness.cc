@@ -46,6 +46,7 @@
 
 #include "real_net.h"
 #include "recursive_solving.h"
+#include "stats.h"
 
 using namespace liars_dice;
 
@@ -308,6 +309,50 @@ int ref_fp_solve(int D, int F, int last_bid, int player_id, const double* belief
       }
     }
     return (int)N;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// What the evaluation entry points of rela/pybind.cc:45-84 compute, with the Net2 weights given flat:
+//   strategy_recursive / out[0]: compute_strategy_recursive + compute_exploitability      (compute_exploitability_with_net)
+//   strategy_to_leaf / out[1..3]: compute_strategy_recursive_to_leaf + exploitability, eval_net with the net strategy and with
+//                                 the full-tree strategy defining the beliefs                 (compute_stats_with_net)
+int ref_net_evaluation(int D, int F, int num_iters, int max_depth, int linear_update, int use_cfr, const float* net_w, int hidden,
+                       int what /*1 recursive, 2 stats, 3 both*/, double* strategy_recursive, double* strategy_to_leaf, double* out4) {
+  try {
+    Game game(D, F);
+    const int H = game.num_hands(), A = game.num_actions();
+    auto params = make_params(num_iters, max_depth, linear_update, 0, 0, 0, 0);
+    params.use_cfr = use_cfr != 0;
+    std::shared_ptr<IValueNet> net = std::make_shared<FlatNet2>(net_w, 2 + A + 2 * H, hidden, H);
+    auto dump = [&](const TreeStrategy& s, double* out) {
+      if (!out) return;
+      size_t k = 0;
+      for (auto& n : s) {
+        if (n.empty()) { k += (size_t)H * A; continue; }
+        for (auto& h : n) for (double v : h) out[k++] = v;
+      }
+    };
+    if (what & 1) {
+      const auto s = compute_strategy_recursive(game, params, net);
+      dump(s, strategy_recursive);
+      out4[0] = compute_exploitability(game, s);
+    }
+    if (what & 2) {
+      const auto net_strategy = compute_strategy_recursive_to_leaf(game, params, net);
+      dump(net_strategy, strategy_to_leaf);
+      out4[1] = compute_exploitability(game, net_strategy);
+      auto full_params = params;
+      full_params.max_depth = 100000;
+      auto fp = build_solver(game, full_params);
+      fp->multistep();
+      const auto& full_strategy = fp->get_strategy();
+      out4[2] = eval_net(game, net_strategy, full_strategy, params.max_depth, params.num_iters, net, true, false);
+      out4[3] = eval_net(game, net_strategy, full_strategy, params.max_depth, params.num_iters, net, false, false);
+    }
+    return (int)unroll_tree(game).size();
   } catch (const std::exception& e) {
     g_err = e.what();
     return -1;

@@ -297,7 +297,10 @@ static int fetch_t(cfrb_handle* h, double* root_value_means, double* snapshot_st
 template <typename real>
 static int fetch_compact_t(cfrb_handle* h, int which, double* out) {
   auto& s = state_of<real>(h);
-  const real* src = which == 0 ? s.Snap.p : which == 1 ? s.Sg.p : which == 2 ? s.S.p : s.R.p;
+  const bool fp = h->cfg.solver == CFRB_SOLVER_FP;
+  // 4 = average strategy (ISubgameSolver::get_strategy): FP keeps it in the Sg table; CFR's is normalise(sum) (:659-660)
+  const bool avg_from_sum = which == 4 && !fp;
+  const real* src = which == 0 ? s.Snap.p : which == 1 ? s.Sg.p : which == 2 ? s.S.p : which == 4 ? (fp ? s.Sg.p : s.S.p) : s.R.p;
   const size_t cnt = (size_t)h->n * h->table_stride;
   if (sizeof(real) == sizeof(double)) {
     CK(cudaMemcpy(out, src, cnt * sizeof(double), cudaMemcpyDeviceToHost));
@@ -305,6 +308,29 @@ static int fetch_compact_t(cfrb_handle* h, int which, double* out) {
     std::vector<real> tmp(cnt);
     CK(cudaMemcpy(tmp.data(), src, cnt * sizeof(real), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < cnt; ++i) out[i] = (double)tmp[i];
+  }
+  if (avg_from_sum) {
+    std::vector<int> steps((size_t)h->n * 2);
+    CK(cudaMemcpy(steps.data(), h->d_steps.p, steps.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const int H = h->g.H;
+    for (int k = 0; k < h->n; ++k) {
+      const auto& t = h->tmpl[h->h_tmpl[k]];
+      double* tk = out + (size_t)k * h->table_stride;
+      for (int nn = 0; nn < t.N; ++nn) {
+        const int nc = t.nchild[nn];
+        if (!nc) continue;
+        // the average of a player stays the uniform initial strategy until that player's first update (same rule as cfrb_fetch)
+        const bool untouched = steps[2 * k + (h->h_player[k] ^ (t.depth[nn] & 1))] == 0;
+        for (int hd = 0; hd < H; ++hd) {
+          double sum = 0;
+          for (int j = 0; j < nc; ++j) sum += tk[(size_t)(t.child_begin[nn] + j - 1) * H + hd];
+          for (int j = 0; j < nc; ++j) {
+            double& v = tk[(size_t)(t.child_begin[nn] + j - 1) * H + hd];
+            v = (sum > 0 && !untouched) ? v / sum : 1.0 / nc;
+          }
+        }
+      }
+    }
   }
   return CFRB_OK;
 }
@@ -737,7 +763,7 @@ int cfrb_fetch(cfrb_handle* h, double* root_value_means, double* snapshot_strate
 int cfrb_table_stride(const cfrb_handle* h) { return h ? h->table_stride : 0; }
 
 int cfrb_fetch_compact(cfrb_handle* h, int32_t which, double* out) {
-  if (!h || !out || which < 0 || which > 3) return fail(CFRB_EINVAL, "bad argument");
+  if (!h || !out || which < 0 || which > 4) return fail(CFRB_EINVAL, "bad argument");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
   if (h->n == 0) return CFRB_OK;

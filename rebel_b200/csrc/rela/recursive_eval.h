@@ -103,8 +103,9 @@ class RecursiveEvaluator {
   RecursiveEvaluator(const liars_dice::RecursiveSolvingParams& cfg, int device, int wave_capacity)
       : cfg_(cfg), K_(std::max(1, wave_capacity)) {
     const auto& sp = cfg.subgame_params;
-    if (!sp.use_cfr) throw std::runtime_error("RecursiveEvaluator: set subgame_params.use_cfr=true");
     cfrb_config c{};
+    c.solver = sp.use_cfr ? CFRB_SOLVER_CFR : CFRB_SOLVER_FP;
+    c.optimistic = sp.optimistic;
     c.num_dice = cfg.num_dice; c.num_faces = cfg.num_faces; c.max_depth = sp.max_depth; c.num_iters = sp.num_iters;
     c.linear_update = sp.linear_update; c.dcfr = sp.dcfr; c.dcfr_alpha = sp.dcfr_alpha; c.dcfr_beta = sp.dcfr_beta;
     c.dcfr_gamma = sp.dcfr_gamma; c.max_subgames = K_; c.device = device; c.net_mode = cfg.net_mode; c.hidden = 256;
@@ -132,6 +133,77 @@ class RecursiveEvaluator {
   int numHands() const { return H_; }
   void setWeights(const std::vector<float>& flat) {
     if (cfrb_set_weights(h_, flat.data(), flat.size(), 1) < 0) throw std::runtime_error(cfrb_last_error());
+  }
+
+  int numNodes() const { return (int)full_.size(); }
+  const std::vector<cfrb_node>& fullTree() const { return full_; }
+  cfrb_handle* handle() const { return h_; }
+
+  // compute_strategy_recursive_to_leaf with use_samplig_strategy = false (recursive_solving.cc:76-134,276-287): every subgame
+  // runs all num_iters iterations; its average strategy (get_strategy) fills the inner nodes and propagates the beliefs.
+  // Dense [N][H][A] fp64.
+  std::vector<double> strategyToLeaf() {
+    std::vector<double> out((size_t)full_.size() * H_ * A_, 0.0);
+    RecursiveEvalResult scratch;
+    scratch.summed_reach.assign((size_t)full_.size() * H_, 0.f);
+    strategy_out_ = out.data();
+    try {
+      runBatch(0, 1, scratch);
+    } catch (...) {
+      strategy_out_ = nullptr;
+      throw;
+    }
+    strategy_out_ = nullptr;
+    return out;
+  }
+
+  // compute_strategy_recursive (recursive_solving.cc:46-74,289-299): a subgame is solved at EVERY non-terminal node of the
+  // full tree; only its root row is kept, and the acting player's beliefs are updated with that row and eps-normalised.
+  std::vector<double> strategyRecursive() {
+    const int N = (int)full_.size(), W = 2 * H_;
+    std::vector<double> out((size_t)N * H_ * A_, 0.0);
+    std::vector<double> bel((size_t)N * W, 0.0);
+    for (int i = 0; i < W; ++i) bel[i] = 1.0 / H_;
+    for (int a = 0; a < A_; ++a) tmpl(a - 1);
+    std::vector<int> level{0}, nextl;
+    std::vector<int32_t> lb, pl;
+    std::vector<double> b, avg;
+    const int iters = cfg_.subgame_params.num_iters;
+    while (!level.empty()) {
+      nextl.clear();
+      for (size_t off = 0; off < level.size(); off += K_) {
+        const int n = (int)std::min<size_t>(K_, level.size() - off);
+        lb.resize(n); pl.resize(n); b.resize((size_t)n * W); avg.resize((size_t)n * stride_);
+        for (int i = 0; i < n; ++i) {
+          const int node = level[off + i];
+          lb[i] = full_[node].last_bid; pl[i] = full_[node].player_id;
+          std::copy(bel.begin() + (size_t)node * W, bel.begin() + (size_t)(node + 1) * W, b.begin() + (size_t)i * W);
+        }
+        if (cfrb_begin_wave(h_, n, lb.data(), pl.data(), b.data(), nullptr) < 0) throw std::runtime_error(cfrb_last_error());
+        if (cfrb_run(h_, iters, nullptr) < 0) throw std::runtime_error(cfrb_last_error());
+        if (cfrb_fetch_compact(h_, 4, avg.data()) < 0) throw std::runtime_error(cfrb_last_error());
+        for (int i = 0; i < n; ++i) {
+          const int node = level[off + i], pid = full_[node].player_id;
+          const int nc = full_[node].children_end - full_[node].children_begin;
+          const int lo = full_[node].last_bid < 0 ? 0 : full_[node].last_bid + 1;
+          const double* sg = avg.data() + (size_t)i * stride_;     // root row: edges 0 .. nc-1
+          for (int j = 0; j < nc; ++j) {
+            const int c = full_[node].children_begin + j;
+            double* cb = &bel[(size_t)c * W];
+            std::copy(bel.begin() + (size_t)node * W, bel.begin() + (size_t)(node + 1) * W, cb);
+            for (int h = 0; h < H_; ++h) {
+              const double s = sg[(size_t)j * H_ + h];
+              out[((size_t)node * H_ + h) * A_ + lo + j] = s;
+              cb[(size_t)pid * H_ + h] *= s;
+            }
+            normalize(cb + (size_t)pid * H_);
+            if (full_[c].children_end != full_[c].children_begin) nextl.push_back(c);
+          }
+        }
+      }
+      level.swap(nextl);
+    }
+    return out;
   }
 
   RecursiveEvalResult run(int num_repeats, int seed0, int batch_repeats) {
@@ -203,7 +275,8 @@ class RecursiveEvaluator {
     std::vector<double> weights;
     for (int i = 0; i < sp.num_iters; ++i) weights.push_back(i % 2 ? 0.0 : (i / 2. + 1));
     std::vector<std::vector<int>> act(count, std::vector<int>(N, -1));
-    for (int r = 0; r < count; ++r) {
+    const bool full_mode = strategy_out_ != nullptr;      // strategyToLeaf: no sampling, all iterations, average strategy
+    for (int r = 0; r < count && !full_mode; ++r) {
       std::mt19937 gen(seed_first + r);
       for (int root : order_) {
         std::discrete_distribution<int> dist(weights.begin(), weights.end());
@@ -228,7 +301,7 @@ class RecursiveEvaluator {
         for (int i = 0; i < n; ++i) {
           const Pending& P = cur[off + i];
           lb[i] = full_[P.root].last_bid; pl[i] = full_[P.root].player_id; ai[i] = act[P.repeat][P.root];
-          max_act = std::max(max_act, ai[i]);
+          max_act = std::max(max_act, full_mode ? sp.num_iters : ai[i]);
           std::copy(P.beliefs.begin(), P.beliefs.end(), bel.begin() + (size_t)i * 2 * H_);
         }
         const auto t0 = std::chrono::steady_clock::now();
@@ -238,7 +311,7 @@ class RecursiveEvaluator {
         if (prev_n) expandChunk(cur, prev_off, prev_n, snap[slot ^ 1].data(), res, next);
         const auto t1 = std::chrono::steady_clock::now();
         snap[slot].resize((size_t)n * stride_);
-        if (cfrb_fetch_compact(h_, 0, snap[slot].data()) < 0) throw std::runtime_error(cfrb_last_error());
+        if (cfrb_fetch_compact(h_, full_mode ? 4 : 0, snap[slot].data()) < 0) throw std::runtime_error(cfrb_last_error());
         res.gpu_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
         res.subgames_solved += n;
         prev_off = off; prev_n = n; slot ^= 1;
@@ -314,7 +387,8 @@ class RecursiveEvaluator {
       }
       // weight of infoset (node, hand) = reach_probabilities[player(node)][node][hand] under the sampled strategy
       // (recursive_eval.cc:143-148; compute_stategy_stats, subgame_solving.cc:839-842), accumulated in float32
-      for (int h = 0; h < H_; ++h) res.summed_reach[(size_t)fn * H_ + h] += (float)nr[(size_t)pid * H_ + h];
+      if (!strategy_out_)
+        for (int h = 0; h < H_; ++h) res.summed_reach[(size_t)fn * H_ + h] += (float)nr[(size_t)pid * H_ + h];
       if (pnc == 0) continue;   // terminal node
       const int lo = t[pn].last_bid < 0 ? 0 : t[pn].last_bid + 1;
       for (int j = 0; j < pnc; ++j) {
@@ -326,7 +400,8 @@ class RecursiveEvaluator {
         std::copy(nr, nr + W, cr);
         for (int h = 0; h < H_; ++h) {
           const double s = sigma[(size_t)(pc - 1) * H_ + h];
-          res.summed_strategy[((size_t)fn * H_ + h) * A_ + action] += (float)s * (float)nr[(size_t)pid * H_ + h];
+          if (strategy_out_) strategy_out_[((size_t)fn * H_ + h) * A_ + action] = s;
+          else res.summed_strategy[((size_t)fn * H_ + h) * A_ + action] += (float)s * (float)nr[(size_t)pid * H_ + h];
           cb[(size_t)pid * H_ + h] *= s;
           cr[(size_t)pid * H_ + h] *= s;
         }
@@ -345,6 +420,7 @@ class RecursiveEvaluator {
 
   const liars_dice::RecursiveSolvingParams cfg_;
   const int K_;
+  double* strategy_out_ = nullptr;   // set while strategyToLeaf() runs
   cfrb_handle* h_ = nullptr;
   int A_ = 0, H_ = 0, stride_ = 0;
   std::vector<cfrb_node> full_;

@@ -10,6 +10,7 @@
 #include "model_locker.h"
 #include "params.h"
 #include "recursive_eval.h"
+#include "evaluation.h"
 #include "replay.h"
 #include "runtime.h"
 
@@ -63,14 +64,72 @@ std::shared_ptr<ThreadLoop> create_cfr_thread(std::shared_ptr<ModelLocker> locke
   return std::make_shared<DataThreadLoop>(std::move(locker), std::move(replay), cfg, seed);
 }
 
-[[noreturn]] void not_on_hot_path(const char* name) {
-  throw std::runtime_error(std::string(name) +
-                           ": evaluation helpers (fictitious play / full-tree recursive strategies, pybind.cc:45-104) are outside "
-                           "the accelerated data-generation path of rebel_b200 (SURVEY.md section 8f); use the reference build for them");
+int eval_device() {
+  const char* e = std::getenv("CFRB_ACTOR_DEVICE");
+  return e && *e ? std::atoi(e) : 0;
 }
-float compute_exploitability_fp(RecursiveSolvingParams) { not_on_hot_path("compute_exploitability_fp"); }
-float compute_exploitability_with_net(RecursiveSolvingParams, const std::string&) { not_on_hot_path("compute_exploitability_with_net"); }
-std::tuple<float, float, float> compute_stats_with_net(RecursiveSolvingParams, const std::string&) { not_on_hot_path("compute_stats_with_net"); }
+
+// compute_exploitability_no_net (pybind.cc:86-104, exported as compute_exploitability_fp): the solver build_solver returns for
+// params.subgame_params at the initial state, without a value net (so the tree must be full depth), with the exploitability
+// printed at powers of two.  The reference never steps the solver inside its loop and returns a shadowed zero; this version
+// does what the loop is written to do and returns the sum of both players' exploitabilities after num_iters iterations.
+float compute_exploitability_fp(RecursiveSolvingParams params) {
+  py::gil_scoped_release nogil;
+  FullTreeSolver solver(params, eval_device(), params.subgame_params.max_depth);
+  std::array<double, 2> v{};
+  int done = 0;
+  for (int iter = 0; iter < params.subgame_params.num_iters; ++iter) {
+    if (((iter + 1) & iter) == 0 || iter + 1 == params.subgame_params.num_iters) {
+      solver.step(iter + 1 - done);
+      done = iter + 1;
+      v = solver.exploitability(solver.strategy());
+      std::printf("Iter=%8d exploitabilities=(%.3e, %.3e) sum=%.3e\n", iter + 1, v[0], v[1], (v[0] + v[1]) / 2.);
+    }
+  }
+  return (float)(v[0] + v[1]);
+}
+
+// compute_exploitability (pybind.cc:45-55, exported as compute_exploitability_with_net): compute_strategy_recursive with the
+// checkpoint's value net, then the exploitability of the assembled full-tree strategy.
+float compute_exploitability_with_net(RecursiveSolvingParams params, const std::string& model_path) {
+  py::gil_scoped_release nogil;
+  auto model = torch::jit::load(model_path, torch::kCPU);
+  RecursiveEvaluator ev(params, eval_device(), 8192);
+  ev.setWeights(flat_weights_of(model));
+  const auto strategy = ev.strategyRecursive();
+  std::array<double, 2> e{};
+  if (cfrb_exploitability(ev.handle(), strategy.data(), e.data()) < 0) throw std::runtime_error(cfrb_last_error());
+  return (float)((e[0] + e[1]) / 2.0);
+}
+
+// compute_stats_with_net (pybind.cc:57-84): exploitability of compute_strategy_recursive_to_leaf with the net, and eval_net's MSE
+// of the net against full-depth solves, with the beliefs defined by the net strategy and by the full-tree strategy.
+std::tuple<float, float, float> compute_stats_with_net(RecursiveSolvingParams params, const std::string& model_path) {
+  py::gil_scoped_release nogil;
+  auto model = torch::jit::load(model_path, torch::kCPU);
+  model.eval();
+  std::vector<double> net_strategy;
+  std::vector<cfrb_node> tree;
+  float exploitability = 0;
+  {
+    RecursiveEvaluator ev(params, eval_device(), 8192);
+    ev.setWeights(flat_weights_of(model));
+    net_strategy = ev.strategyToLeaf();
+    tree = ev.fullTree();
+    std::array<double, 2> e{};
+    if (cfrb_exploitability(ev.handle(), net_strategy.data(), e.data()) < 0) throw std::runtime_error(cfrb_last_error());
+    exploitability = (float)((e[0] + e[1]) / 2.0);
+  }
+  std::vector<double> full_strategy;
+  {
+    FullTreeSolver full(params, eval_device(), 100000);
+    full.step(params.subgame_params.num_iters);
+    full_strategy = full.strategy();
+  }
+  const float mse_net = eval_net(params, eval_device(), tree, net_strategy, full_strategy, model, /*traverse_by_net=*/true, /*verbose=*/true);
+  const float mse_full = eval_net(params, eval_device(), tree, net_strategy, full_strategy, model, /*traverse_by_net=*/false, /*verbose=*/true);
+  return std::make_tuple(exploitability, mse_net, mse_full);
+}
 
 // Synchronous helper for tests / benchmarks: run `waves` waves of a BatchedRlRunner on `device` and return all examples.
 std::tuple<torch::Tensor, torch::Tensor> run_selfplay_waves(const RecursiveSolvingParams& cfg, int device, int seed, int waves,

@@ -46,7 +46,7 @@ def test_surface_matches_reference(rela):
     cfg = make_cfg(rela, 1, 6)
     assert cfg.subgame_params.num_iters == 1024 and cfg.subgame_params.use_cfr        # nested setattr sticks (by reference)
     assert abs(cfg.random_action_prob - 0.25) < 1e-7 and cfg.sample_leaf
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError):          # no CUDA device here: the evaluation helpers fail loudly, there is no CPU path
         rela.compute_exploitability_fp(cfg)
 
 
@@ -197,6 +197,56 @@ def test_batched_walk_with_fictitious_play_reproduces_rlrunner_stream(rela, gold
                    subgame_params=dict(num_iters=32, max_depth=2, linear_update=True, use_cfr=False))
     q, v = rela.run_selfplay_waves(cfg, 0, 7, len(gq) // 2)
     assert np.array_equal(q.numpy(), gq) and np.array_equal(v.numpy(), gv)
+
+
+def _save_eval_model(tmp_path, D, F, netname):
+    from rebel_b200.models import make_selfplay_net
+    net = make_selfplay_net(D, F, seed=0)
+    if netname == "zero_out":
+        with torch.no_grad():
+            net.output.weight.zero_()
+            net.output.bias.zero_()
+    path = str(tmp_path / f"net_{D}x{F}_{netname}.pt")
+    torch.jit.script(net).save(path)
+    return path
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,F", [(1, 4), (1, 6), (2, 3)])
+@pytest.mark.parametrize("use_cfr", [True, False])
+def test_evaluation_entry_points_vs_reference(rela, golden, tmp_path, D, F, use_cfr):
+    """compute_exploitability_with_net and compute_stats_with_net (rela/pybind.cc:45-84, eval_net stats.cc:44-153) against
+    the compiled reference (fixture from oracle/make_golden.py).  With a net whose output layer is zero the solver
+    trajectories are bit-identical, so the exploitabilities agree to float rounding and eval_net's MSE to 1e-6 relative;
+    with the random-init net (fp32 SIMT kernel vs ATen) the strategies agree until regret matching amplifies 1e-7 differences,
+    so the same quantities are compared to a few percent."""
+    g = golden("net_evaluation.npz")
+    iters = {(1, 4): 32, (1, 6): 16, (2, 3): 8}[(D, F)]
+    tag = ("cfr" if use_cfr else "fp")
+    for netname, rel in (("zero_out", 1e-6), ("random", 5e-2)):
+        want = g[f"values_{tag}_{netname}_{D}x{F}"]
+        path = _save_eval_model(tmp_path, D, F, netname)
+        cfg = make_cfg(rela, D, F, net_mode=1, state_dtype=0, subgame_params=dict(num_iters=iters, max_depth=2, linear_update=True, use_cfr=use_cfr))
+        e_rec = rela.compute_exploitability_with_net(cfg, path)
+        e_leaf, mse_net, mse_full = rela.compute_stats_with_net(cfg, path)
+        got = np.array([e_rec, e_leaf, mse_net, mse_full])
+        assert np.all(np.abs(got - want) <= rel * np.abs(want) + 1e-7), (netname, got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_cfr", [True, False])
+def test_compute_exploitability_fp_full_tree(rela, port, use_cfr):
+    """compute_exploitability_fp (pybind.cc:86-104): full-tree solve without a net; the returned sum of exploitabilities equals
+    the oracle's for the same solver, and a depth-limited tree without a net is rejected like the reference does."""
+    D, F, iters = 1, 4, 64
+    cfg = make_cfg(rela, D, F, subgame_params=dict(num_iters=iters, max_depth=100000, linear_update=True, use_cfr=use_cfr))
+    got = rela.compute_exploitability_fp(cfg)
+    b = np.full((2, F ** D), 1.0 / F ** D)
+    s = (port.cfr_solve if use_cfr else port.fp_solve)(D, F, b, [iters], num_iters=iters, max_depth=100000)
+    want = port.exploitability(D, F, s["avg"][0]).sum()
+    assert abs(got - want) <= 1e-6 * abs(want)
+    with pytest.raises(RuntimeError):
+        rela.compute_exploitability_fp(make_cfg(rela, D, F, subgame_params=dict(num_iters=8, max_depth=2, linear_update=True, use_cfr=True)))
 
 
 @pytest.mark.gpu
