@@ -165,25 +165,30 @@ inline float eval_net(const liars_dice::RecursiveSolvingParams& cfg, int device,
       if (cfrb_begin_wave(h, n, lb.data(), pl.data(), bel.data(), nullptr) < 0) throw std::runtime_error(cfrb_last_error());
       if (cfrb_run(h, fp_iters, nullptr) < 0) throw std::runtime_error(cfrb_last_error());
       if (cfrb_fetch(h, mu.data(), nullptr, nullptr, nullptr, nullptr, nullptr) < 0) throw std::runtime_error(cfrb_last_error());
+      // net predictions for the 2n (node, traverser) queries of the chunk in ONE forward (the reference evaluates them one
+      // row at a time, stats.cc:128-133; a [1,Q] forward per row costs milliseconds of thread wake-ups on a many-core host)
+      std::vector<float> q((size_t)2 * n * Q, 0.f);
       for (int i = 0; i < n; ++i) {
         const int node = top[off + i];
-        const double* b0 = &bel[((size_t)i * 2 + 0) * H];
-        const double* b1 = &bel[((size_t)i * 2 + 1) * H];
-        for (int t = 0; t < 2; ++t) {
-          // get_query / write_query_to (subgame_solving.cc:104-123,901-908)
-          std::vector<float> q(Q, 0.f);
-          q[0] = (float)tree[node].player_id; q[1] = (float)t;
-          if (tree[node].last_bid >= 0) q[2 + tree[node].last_bid] = 1.f;
+        for (int t = 0; t < 2; ++t) {   // get_query / write_query_to (subgame_solving.cc:104-123,901-908)
+          float* row = &q[((size_t)i * 2 + t) * Q];
+          row[0] = (float)tree[node].player_id; row[1] = (float)t;
+          if (tree[node].last_bid >= 0) row[2 + tree[node].last_bid] = 1.f;
           for (int p = 0; p < 2; ++p) {
-            const double* b = p ? b1 : b0;
+            const double* b = &bel[((size_t)i * 2 + p) * H];
             double s = 0;
             for (int hh = 0; hh < H; ++hh) s += b[hh] + 1e-80;
-            for (int hh = 0; hh < H; ++hh) q[2 + A + p * H + hh] = (float)((b[hh] + 1e-80) / s);
+            for (int hh = 0; hh < H; ++hh) row[2 + A + p * H + hh] = (float)((b[hh] + 1e-80) / s);
           }
-          torch::NoGradGuard ng;
-          auto reach_t = torch::from_blob(const_cast<double*>(t ? b1 : b0), {H}, torch::kFloat64).clone();
-          auto out = model.forward({torch::from_blob(q.data(), {1, Q}, torch::kFloat32).clone()}).toTensor().squeeze(0);
-          const float net_value = (out * reach_t).sum().item<float>();
+        }
+      }
+      torch::NoGradGuard ng;
+      const auto net_out = model.forward({torch::from_blob(q.data(), {2 * n, Q}, torch::kFloat32).clone()}).toTensor().contiguous();
+      for (int i = 0; i < n; ++i) {
+        const int node = top[off + i];
+        for (int t = 0; t < 2; ++t) {
+          auto reach_t = torch::from_blob(&bel[((size_t)i * 2 + t) * H], {H}, torch::kFloat64).clone();
+          const float net_value = (net_out[i * 2 + t] * reach_t).sum().item<float>();
           auto hv = torch::from_blob(&mu[((size_t)i * 2 + t) * H], {H}, torch::kFloat64).clone();
           const float br_value = (hv * reach_t).sum().item<float>();
           if (verbose)

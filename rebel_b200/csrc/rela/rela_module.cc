@@ -6,6 +6,8 @@
 #include <pybind11/stl.h>
 #include <torch/extension.h>
 
+#include <chrono>
+
 #include "batched_runner.h"
 #include "model_locker.h"
 #include "params.h"
@@ -64,6 +66,16 @@ std::shared_ptr<ThreadLoop> create_cfr_thread(std::shared_ptr<ModelLocker> locke
   return std::make_shared<DataThreadLoop>(std::move(locker), std::move(replay), cfg, seed);
 }
 
+struct PhaseTimer {   // CFRB_EVAL_TIMING=1: wall time of the phases of the evaluation entry points on stderr
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  const bool on = std::getenv("CFRB_EVAL_TIMING") != nullptr;
+  void lap(const char* what) {
+    const auto n = std::chrono::steady_clock::now();
+    if (on) std::fprintf(stderr, "[rebel_b200] %-28s %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+    t = n;
+  }
+};
+
 int eval_device() {
   const char* e = std::getenv("CFRB_ACTOR_DEVICE");
   return e && *e ? std::atoi(e) : 0;
@@ -106,28 +118,37 @@ float compute_exploitability_with_net(RecursiveSolvingParams params, const std::
 // of the net against full-depth solves, with the beliefs defined by the net strategy and by the full-tree strategy.
 std::tuple<float, float, float> compute_stats_with_net(RecursiveSolvingParams params, const std::string& model_path) {
   py::gil_scoped_release nogil;
+  PhaseTimer pt;
   auto model = torch::jit::load(model_path, torch::kCPU);
   model.eval();
+  pt.lap("load model");
   std::vector<double> net_strategy;
   std::vector<cfrb_node> tree;
   float exploitability = 0;
   {
     RecursiveEvaluator ev(params, eval_device(), 8192);
     ev.setWeights(flat_weights_of(model));
+    pt.lap("create evaluator");
     net_strategy = ev.strategyToLeaf();
+    pt.lap("strategy to leaf");
     tree = ev.fullTree();
     std::array<double, 2> e{};
     if (cfrb_exploitability(ev.handle(), net_strategy.data(), e.data()) < 0) throw std::runtime_error(cfrb_last_error());
     exploitability = (float)((e[0] + e[1]) / 2.0);
+    pt.lap("best response");
   }
   std::vector<double> full_strategy;
   {
     FullTreeSolver full(params, eval_device(), 100000);
+    pt.lap("create full-tree solver");
     full.step(params.subgame_params.num_iters);
     full_strategy = full.strategy();
+    pt.lap("full-tree solve");
   }
   const float mse_net = eval_net(params, eval_device(), tree, net_strategy, full_strategy, model, /*traverse_by_net=*/true, /*verbose=*/true);
+  pt.lap("eval_net (net beliefs)");
   const float mse_full = eval_net(params, eval_device(), tree, net_strategy, full_strategy, model, /*traverse_by_net=*/false, /*verbose=*/true);
+  pt.lap("eval_net (full beliefs)");
   return std::make_tuple(exploitability, mse_net, mse_full);
 }
 
