@@ -1,7 +1,7 @@
 """`recursive_eval --cfr` of the reference (csrc/liars_dice/recursive_eval.cc:196-420) on the GPU wave solver: exploitability of
 the reach-weighted average of `--num_repeats` sampled recursive strategies (BASELINE config 5).
 
-    python -m rebel_b200.recursive_eval --num_dice 2 --num_faces 3 --subgame_iters 1024 --num_repeats 4097 [--net model.pt]
+    python -m rebel_b200.recursive_eval --num_dice 2 --num_faces 3 --subgame_iters 1024 --cfr --mdp_depth 2 --num_repeats 4097 [--net model.pt]
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 -m rebel_b200.recursive_eval ...
 
 Flags follow the reference binary (`--num_dice --num_faces --subgame_iters --mdp_depth --num_repeats --net --cfr --no_linear`).
@@ -40,11 +40,14 @@ def main(argv=None):
     ap.add_argument("--num_dice", type=int, default=1)
     ap.add_argument("--num_faces", type=int, default=4)
     ap.add_argument("--subgame_iters", type=int, default=1024)
-    ap.add_argument("--mdp_depth", type=int, default=2)
-    ap.add_argument("--num_repeats", type=int, default=1)
+    ap.add_argument("--mdp_depth", type=int, default=2, help="depth of the recursive subgames (reference default -1 = full-tree solve only)")
+    ap.add_argument("--num_repeats", type=int, default=-1, help="sampled recursive strategies to average (<= 0: skip)")
     ap.add_argument("--net", type=str, default=None, help="TorchScript / state_dict checkpoint of Net2; omitted = zero value net")
-    ap.add_argument("--cfr", action="store_true", default=True)
+    ap.add_argument("--cfr", action="store_true", help="CFR instead of fictitious play (the reference's default solver is FP)")
     ap.add_argument("--no_linear", action="store_true")
+    ap.add_argument("--optimistic", action="store_true")
+    ap.add_argument("--dcfr", type=float, nargs=3, metavar=("ALPHA", "BETA", "GAMMA"), default=None)
+    ap.add_argument("--no_full_tree", action="store_true", help="skip the full-tree solve the reference binary always starts with")
     ap.add_argument("--batch_repeats", type=int, default=64)
     ap.add_argument("--wave_capacity", type=int, default=8192)
     ap.add_argument("--net_mode", type=int, default=None, help="0 zero, 1 fp32 SIMT, 2 tcgen05 fp16, 3 tcgen05 fp16 + packed-half GELU (default with --net)")
@@ -73,7 +76,21 @@ def main(argv=None):
     cfg.num_dice, cfg.num_faces = args.num_dice, args.num_faces
     cfg.net_mode, cfg.state_dtype = net_mode, 0
     sp = cfg.subgame_params
-    sp.num_iters, sp.max_depth, sp.linear_update, sp.use_cfr = args.subgame_iters, args.mdp_depth, not args.no_linear, True
+    sp.num_iters, sp.max_depth, sp.use_cfr, sp.optimistic = args.subgame_iters, args.mdp_depth, args.cfr, args.optimistic
+    sp.linear_update = not args.no_linear and args.dcfr is None                      # recursive_eval.cc:273
+    if args.dcfr is not None:
+        sp.dcfr, (sp.dcfr_alpha, sp.dcfr_beta, sp.dcfr_gamma) = True, args.dcfr
+
+    if rank == 0 and not args.no_full_tree:
+        # "Solving the game for the full tree" (recursive_eval.cc:264-300): exploitability curve at powers of two
+        sp.max_depth = 100000
+        total = rela.compute_exploitability_fp(cfg)
+        print(f"Full {'CFR' if args.cfr else 'FP'} exploitability: {total / 2:.6e}", flush=True)
+        sp.max_depth = args.mdp_depth
+    if args.num_repeats <= 0 or args.mdp_depth <= 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     lo, hi = strategy_ids(rank, world, args.num_repeats)
     t0 = time.time()

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_rela_module.py -x -q -m gpu -k "recursive_eval" 2>&1 | tail -5
 for net in "" "--random_net_seed 0"; do
-  timeout 600 python -m rebel_b200.recursive_eval --num_dice 2 --num_faces 3 --subgame_iters 1024 --num_repeats 64 $net 2>&1 | tail -9
+  timeout 600 python -m rebel_b200.recursive_eval --num_dice 2 --num_faces 3 --subgame_iters 1024 --num_repeats 64 --cfr --no_full_tree $net 2>&1 | tail -9
 done
 timeout 600 python - <<'PY'
 import sys, time
