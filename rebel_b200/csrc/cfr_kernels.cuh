@@ -722,6 +722,27 @@ __global__ void __launch_bounds__(256, 4) cfr_iter_d2_kernel(CfrDev<real> p, int
   real* slot = smem + (size_t)gid * scratch_per_group;
   real* bel = slot + p.nh_max; real* hist = bel + 2 * H; real* lsum = hist + p.tmp_reals;
   for (int i = lane; i < 2 * H; i += 32) bel[i] = p.beliefs[(size_t)k * 2 * H + i];
+  {
+    // The wave's tables (3 x K x 4.3 KB at 1x6f) do not fit in L2 next to the query tiles, so every launch streams them from
+    // HBM.  Ask for this subgame's lines now: the requests overlap the leaf-value phase instead of stalling the phases
+    // that consume them one DRAM round trip at a time.
+    const size_t off = (size_t)k * p.table_stride * sizeof(real);
+    const int lines = ((t.N - 1) * H * (int)sizeof(real) + 127) >> 7;
+    const char* sg = reinterpret_cast<const char*>(p.Sg) + off;
+    for (int i = lane; i < lines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(sg + ((size_t)i << 7)));
+    if (do_b) {   // regrets and sum strategy: only the edges below the previous traverser's level are touched
+      const D2Levels lv = d2_levels(p.level_begin, t);
+      const bool root_acts = p.sg_player[k] == ((iter - 1) & 1);
+      const int e0 = (root_acts ? lv.n1b : lv.n1e) - 1, e1 = (root_acts ? lv.n1e : lv.n2e) - 1;
+      const size_t b0 = (size_t)e0 * H * sizeof(real) & ~(size_t)127, b1 = (size_t)e1 * H * sizeof(real);
+      const char* rr = reinterpret_cast<const char*>(p.R) + off;
+      const char* ss = reinterpret_cast<const char*>(p.S) + off;
+      for (size_t o = b0 + ((size_t)lane << 7); o < b1; o += (size_t)32 << 7) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rr + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ss + o));
+      }
+    }
+  }
   __syncwarp();
   const int tb = (iter - 1) & 1;
   const int rp = p.sg_player[k];

@@ -211,7 +211,10 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
   if (kDebug && tr) tr[0] = clock64();
   float sum, sumsq;
   {
-    f32x2 s2 = pack2(0.f, 0.f), q2 = pack2(0.f, 0.f);     // even / odd features accumulate separately
+    // two independent accumulator pairs: 2 x 2 interleaved chains of 16 packed adds / fmas instead of one chain of 32
+    f32x2 s2[2], q2[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) { s2[u] = pack2(0.f, 0.f); q2[u] = pack2(0.f, 0.f); }
 #pragma unroll
     for (int i = 0; i < kColsPerThread; i += 2) {
       if (kDebug && dbg_row) {
@@ -219,11 +222,12 @@ __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id,
         dbg_row[part_id * kColsPerThread + i + 1] = __uint_as_float(xr[i + 1]);
       }
       const f32x2 x2 = pack2(__uint_as_float(xr[i]), __uint_as_float(xr[i + 1]));
-      s2 = add2(s2, x2);
-      q2 = fma2(x2, x2, q2);
+      s2[(i >> 1) & 1] = add2(s2[(i >> 1) & 1], x2);
+      q2[(i >> 1) & 1] = fma2(x2, x2, q2[(i >> 1) & 1]);
     }
+    const f32x2 st = add2(s2[0], s2[1]), qt = add2(q2[0], q2[1]);
     float a0, a1, b0, b1;
-    unpack2(s2, a0, a1); unpack2(q2, b0, b1);
+    unpack2(st, a0, a1); unpack2(qt, b0, b1);
     sum = a0 + a1; sumsq = b0 + b1;
   }
   part[part_id * kTileM + row] = make_float2(sum, sumsq);
