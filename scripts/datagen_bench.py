@@ -15,12 +15,13 @@ def main():
     ap.add_argument("--games", type=int, default=8192, help="concurrent games per thread loop")
     ap.add_argument("--threads", type=int, default=2, help="thread loops per GPU (selfplay.threads_per_gpu)")
     ap.add_argument("--iters", type=int, default=1024)
+    ap.add_argument("--devices", type=int, default=1, help="GPUs: one ModelLocker per cuda:i like selfplay.py:193-220")
     ap.add_argument("--seconds", type=float, default=20.0)
     ap.add_argument("--warmup", type=float, default=4.0)
     args = ap.parse_args()
     D, F = args.dice, args.faces
-    ref_model = [torch.jit.script(make_selfplay_net(D, F))]
-    locker = rela.ModelLocker(ref_model, "cuda:0")
+    ref_models = [[torch.jit.script(make_selfplay_net(D, F))] for _ in range(args.devices)]
+    lockers = [rela.ModelLocker(m, f"cuda:{i}") for i, m in enumerate(ref_models)]
     replay = rela.ValuePrioritizedReplay(capacity=1 << 22, seed=10001, alpha=1.0, beta=1.0, prefetch=8, use_priority=False,
                                          compressed_values=False)
     cfg = rela.RecursiveSolvingParams()
@@ -29,8 +30,9 @@ def main():
     sp = cfg.subgame_params
     sp.num_iters, sp.max_depth, sp.linear_update, sp.use_cfr = args.iters, 2, True, True
     ctx = rela.Context()
-    for i in range(args.threads):
-        ctx.push_env_thread(rela.create_cfr_thread(locker, replay, cfg, i))
+    for d, locker in enumerate(lockers):
+        for i in range(args.threads):
+            ctx.push_env_thread(rela.create_cfr_thread(locker, replay, cfg, d * 1000 + i))
     ctx.start()
     time.sleep(args.warmup)
     n0, t0 = replay.num_add(), time.time()
@@ -43,7 +45,7 @@ def main():
     while not ctx.terminated():
         time.sleep(0.05)
     ex = (n1 - n0) / (t1 - t0)
-    print(json.dumps({"game": f"{D}x{F}f", "concurrent_games": args.games, "thread_loops": args.threads, "cfr_iters": args.iters,
+    print(json.dumps({"game": f"{D}x{F}f", "concurrent_games": args.games, "devices": args.devices, "thread_loops_per_device": args.threads, "cfr_iters": args.iters,
                       "examples_per_s": ex, "subgames_per_s": ex / 2, "subgame_iters_per_s": ex / 2 * args.iters,
                       "seconds": t1 - t0, "error": ctx.error()}))
 
