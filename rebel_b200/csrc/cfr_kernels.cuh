@@ -646,17 +646,37 @@ __device__ void cfr_forward_d2(const CfrDev<real>& p, int k, int trav, real* slo
   const int leaf_player = rp ^ ((t.levels - 1) & 1);
   const int Qp = p.Qpad;
   if (p.Xh != nullptr) {
+    // fp16 tile in UMMA K-major core-matrix order, one 16-byte store per (row, 8 columns).  The constant columns (one-hot of
+    // the leaf's last bid, the 1 at column Q, zero padding) come from the per-template table qconst; only the acting player /
+    // traverser flags and the 2H belief columns are computed.
     const int kc = Qp >> 3;
+    const int qb0 = 2 + p.A, qb1 = qb0 + H, qb2 = qb1 + H;      // belief columns [qb0, qb1) player 0, [qb1, qb2) player 1
+    const __half* __restrict__ qconst = p.qconst + t.qconst_off;
     for (int it = lane; it < t.L * kc; it += G) {
       const int k8 = it / t.L, r = it % t.L;
-      const int n = p.pleaf_node[t.pleaf_off + r];
-      const int bid = p.last_bid[t.node_off + n];
-      const real* r0 = d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H);
-      const real* r1 = d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H);
-      const real s0 = lsum[2 * r], s1 = lsum[2 * r + 1];
       union { int4 v; __half h[8]; } c;
+      c.v = *reinterpret_cast<const int4*>(qconst + (size_t)r * Qp + k8 * 8);
+      const int q0 = k8 * 8;
+      if (q0 == 0) { c.h[0] = __float2half_rn((float)leaf_player); c.h[1] = __float2half_rn((float)trav); }
+      if (q0 + 8 > qb0 && q0 < qb2) {
+        const int n = p.pleaf_node[t.pleaf_off + r];
+        const real* r0 = d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H);
+        const real* r1 = d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H);
+        const real s0 = lsum[2 * r], s1 = lsum[2 * r + 1];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) c.h[j] = __float2half_rn(query_value(p, k8 * 8 + j, leaf_player, trav, bid, r0, r1, s0, s1));
+        for (int j = 0; j < 8; ++j) {
+          const int q = q0 + j;
+          if (q >= qb0 && q < qb2) {
+            const bool first = q < qb1;
+            const real x = first ? r0[q - qb0] : r1[q - qb1];
+            const real sc = first ? s0 : s1;
+            float f;
+            if (Eps<real>::kLiteral) f = (float)((x + Eps<real>::v) * sc);              // util.h:68-78 (sc = 1 / sum)
+            else f = isfinite(sc) ? (float)(x * sc) : 1.f / H;
+            c.h[j] = __float2half_rn(f);
+          }
+        }
+      }
       const int Rr = row0 + r, rr = Rr & 127;
       *reinterpret_cast<int4*>(p.Xh + (size_t)(Rr >> 7) * 128 * Qp + k8 * 1024 + (rr >> 3) * 64 + (rr & 7) * 8) = c.v;
     }
