@@ -16,6 +16,7 @@
 #include "cfr_tree.h"
 #include "leaf_mlp_simt.cuh"
 #include "leaf_mlp_tc.cuh"
+#include "leaf_mlp_tc2.cuh"
 
 namespace {
 inline bool is_tc(int net_mode) { return net_mode == CFRB_NET_TC_F16 || net_mode == CFRB_NET_TC_F16X2; }
@@ -102,6 +103,7 @@ struct cfrb_handle {
   DevBuf<int> d_sg_tmpl, d_sg_player, d_sg_row_off, d_sg_act, d_steps;
   DevBuf<float> d_X, d_out, d_dbg;
   long long* dbg_trace = nullptr;   // set only inside cfrb_debug_net_trace
+  bool tc2 = false;                 // value net runs the two-tiles-in-flight kernel
   DevBuf<__half> d_Xh;
   WaveState<float> sf;
   WaveState<double> sd;
@@ -497,6 +499,17 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
     CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
     CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    {   // two-tiles-in-flight variant (leaf_mlp_tc2.cuh) when its activation ring fits next to the weights
+      const cfrb::tc::Tc2Layout T2(h->Qpad);
+      // Opt-in (CFRB_TC2=1): bit-identical, but measured SLOWER on B200 (188 vs 166 us per 540 672 rows) — with the A operand in
+      // shared memory the SS MMAs fetch 96 B/clk of operands, which starves the epilogue's own shared-memory traffic.
+      const char* on2 = std::getenv("CFRB_TC2");
+      h->tc2 = T2.smem_bytes <= max_optin && on2 && *on2 == '1';
+      if (h->tc2) {
+        CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2.smem_bytes));
+        CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2.smem_bytes));
+      }
+    }
   }
   CK(cudaFuncSetAttribute(cfrb::leaf_mlp_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)cfrb::leaf_mlp_fp32_smem(256)));
@@ -688,6 +701,10 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
     if (dbg1 || dbg2 || a.trace) {
       if (x2) cfrb::tc::leaf_mlp_tc_kernel<true, true><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
       else cfrb::tc::leaf_mlp_tc_kernel<true, false><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+    } else if (h->tc2) {
+      const cfrb::tc::Tc2Layout T2(h->Qpad);
+      if (x2) cfrb::tc::leaf_mlp_tc2_kernel<true><<<grid, cfrb::tc::kThreads, T2.smem_bytes, st>>>(a);
+      else cfrb::tc::leaf_mlp_tc2_kernel<false><<<grid, cfrb::tc::kThreads, T2.smem_bytes, st>>>(a);
     } else {
       if (x2) cfrb::tc::leaf_mlp_tc_kernel<false, true><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
       else cfrb::tc::leaf_mlp_tc_kernel<false, false><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);

@@ -451,6 +451,30 @@ def test_full_size_properties_1x6f(rb, port, net_weights, net_name):
     S.close()
 
 
+@pytest.mark.parametrize("K", [1, 3, 149, 700])
+def test_two_tile_value_net_kernel_is_bit_identical(rb, net_weights, K):
+    """leaf_mlp_tc2_kernel (CFRB_TC2=1, two tiles in flight, A operand through a shared-memory ring) produces exactly the bits
+    of the default one-tile kernel, for wave sizes that give the CTAs single / odd / even numbers of tiles."""
+    import os
+    D, F = 1, 6
+    H = F ** D
+    rng = np.random.RandomState(K)
+    b = rng.rand(K, 2, H); b /= b.sum(-1, keepdims=True)
+    outs = []
+    for flag in ("0", "1"):
+        os.environ["CFRB_TC2"] = flag
+        try:
+            S = rb.WaveSolver(D, F, K, net_mode=rb.NET_TC_F16X2)
+        finally:
+            os.environ.pop("CFRB_TC2", None)
+        S.set_weights(net_weights(D, F))
+        S.begin(np.full(K, -1, np.int32), np.zeros(K, np.int32), b)
+        S.run(3)
+        outs.append((S.leaf_io()[1], S.fetch(("root_means",))["root_means"]))
+        S.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_snapshot_matches_strategy_at_act_iteration(rb, port):
     D, F = 1, 4
     A, H, Q = game_dims(D, F)
