@@ -599,6 +599,123 @@ __device__ void cfr_backward_d2(const CfrDev<real>& p, int k, int trav, real* va
   __syncwarp();
 }
 
+// Fictitious-play backward half for depth <= 2 templates: fp_backward's arithmetic with the one-buffer discipline of
+// cfr_backward_d2.  The best-response flags (1 / 0) replace the children's values in place, then give way to the discounted
+// sums, and finally to belief x new average strategy = the reach the forward half needs (same `have` protocol as CFR).
+template <typename real, int HC>
+__device__ void fp_backward_d2(const CfrDev<real>& p, int k, int trav, real* val, const real* bel, int lane) {
+  constexpr int G = 32;
+  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
+  const int H = HC > 0 ? HC : p.H;
+  const int rp = p.sg_player[k];
+  real* Last = p.R + (size_t)k * p.table_stride;
+  real* Avg = p.Sg + (size_t)k * p.table_stride;
+  real* S = p.S + (size_t)k * p.table_stride;
+  const int* __restrict__ parent = p.parent + t.node_off;
+  const int* __restrict__ nchild = p.nchild + t.node_off;
+  const int* __restrict__ child_begin = p.child_begin + t.node_off;
+  const int row0 = p.sg_row_off[k];
+  const D2Levels lv = d2_levels(p.level_begin, t);
+  const bool mine0 = rp == trav;
+  for (int it = lane; it < t.L * H; it += G) {
+    const int r = it / H, h = it % H;
+    const int n = p.pleaf_node[t.pleaf_off + r];
+    val[n * H + h] = p.use_net ? (real)(float)((real)p.net_out[(size_t)(row0 + r) * p.Hout + h] * p.scaler[row0 + r]) : (real)0;
+  }
+  const real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
+  for (int it = lane; it < t.T * H; it += G) {
+    const int z = it / H, h = it % H;
+    val[p.term_node[t.term_off + z] * H + h] = vt[z * H + h];
+  }
+  __syncwarp();
+  // ---- bottom-up best response (BRSolver::compute_br :316-358): level 1, then the root
+  if (lv.n2e > lv.n1e) {
+    for (int it = lane; it < (lv.n1e - lv.n1b) * H; it += G) {
+      const int n = lv.n1b + it / H, h = it % H;
+      const int nc = nchild[n];
+      if (!nc) continue;
+      const int c0 = child_begin[n];
+      real v = 0;
+      if (!mine0) {
+        int best = 0;
+        v = val[c0 * H + h];
+        for (int j = 1; j < nc; ++j) {
+          const real nv = val[(c0 + j) * H + h];
+          if (nv > v) { v = nv; best = j; }
+        }
+        for (int j = 0; j < nc; ++j) val[(c0 + j) * H + h] = (j == best) ? (real)1 : (real)0;
+      } else {
+        for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h];
+      }
+      val[n * H + h] = v;
+    }
+    __syncwarp();
+  }
+  for (int h = lane; h < H; h += G) {
+    real v = 0;
+    if (mine0) {
+      int best = lv.n1b;
+      v = val[lv.n1b * H + h];
+      for (int n = lv.n1b + 1; n < lv.n1e; ++n) {
+        const real nv = val[n * H + h];
+        if (nv > v) { v = nv; best = n; }
+      }
+      for (int n = lv.n1b; n < lv.n1e; ++n) val[n * H + h] = (n == best) ? (real)1 : (real)0;
+    } else {
+      for (int n = lv.n1b; n < lv.n1e; ++n) v += val[n * H + h];
+    }
+    val[h] = v;
+  }
+  __syncwarp();
+  const int s = p.steps[2 * k + trav];
+  {
+    const real alpha = p.linear ? (real)2 / (s + 2) : (real)1 / (s + 1);
+    real* mu = p.mu + ((size_t)k * 2 + trav) * H;
+    for (int h = lane; h < H; h += G) mu[h] += (val[h] - mu[h]) * alpha;
+  }
+  const real disc = (real)(s + 2) / (s + 3);
+  __syncwarp();
+  // ---- update_sum_strat (:391-421) on the traverser's level: its beliefs there are its root beliefs
+  const real* bt = bel + trav * H;
+  const int pb = mine0 ? 0 : lv.n1b, pe = mine0 ? 1 : lv.n1e;
+  const int cb = mine0 ? lv.n1b : lv.n1e, ce = mine0 ? lv.n1e : lv.n2e;
+  for (int it = lane; it < (ce - cb) * H; it += G) {
+    const int c = cb + it / H, h = it % H;
+    const int e = (c - 1) * H + h;
+    const real x = bt[h] * val[c * H + h];               // traverser_beliefs * br_strategies
+    real sn = S[e] + x;
+    if (p.linear) sn = sn * disc;
+    S[e] = sn; Last[e] = x;
+    val[c * H + h] = sn;
+  }
+  __syncwarp();
+  for (int it = lane; it < (pe - pb) * H; it += G) {     // normalize_probabilities (util.h:20-34 / 52-63)
+    const int n = pb + it / H, h = it % H;
+    const int nc = nchild[n];
+    if (!nc) continue;
+    const int c0 = child_begin[n];
+    real tot = 0;
+    for (int j = 0; j < nc; ++j) tot += val[(c0 + j) * H + h];
+    if (p.optimistic) {
+      real tl = 0;
+      for (int j = 0; j < nc; ++j) tl += Last[(c0 + j - 1) * H + h];
+      tot = tot + tl;
+    }
+    val[n * H + h] = tot;
+  }
+  __syncwarp();
+  for (int it = lane; it < (ce - cb) * H; it += G) {
+    const int c = cb + it / H, h = it % H;
+    const int e = (c - 1) * H + h;
+    const real tot = val[parent[c] * H + h];
+    const real avg = (p.optimistic ? val[c * H + h] + Last[e] : val[c * H + h]) / tot;
+    Avg[e] = avg;
+    val[c * H + h] = bt[h] * avg;                        // the traverser's reach under the new average strategy
+  }
+  if (lane == 0) p.steps[2 * k + trav] = s + 1;
+  __syncwarp();
+}
+
 // have: level whose slots already hold the reach of the player acting above it (0: level-1 slots = reach_P0 valid,
 // 1: level-2 slots = reach_P1 valid, -1: neither).
 template <typename real, int HC>
@@ -766,7 +883,10 @@ __global__ void __launch_bounds__(256, 4) cfr_iter_d2_kernel(CfrDev<real> p, int
   __syncwarp();
   const int tb = (iter - 1) & 1;
   const int rp = p.sg_player[k];
-  if (do_b) cfr_backward_d2<real, HC>(p, k, tb, slot, bel, lane);
+  if (do_b) {
+    if (p.fp) fp_backward_d2<real, HC>(p, k, tb, slot, bel, lane);
+    else cfr_backward_d2<real, HC>(p, k, tb, slot, bel, lane);
+  }
   // sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
   if (p.sg_act_iter[k] == iter) {
     const real* Sg = p.Sg + (size_t)k * p.table_stride;

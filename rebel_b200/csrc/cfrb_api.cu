@@ -151,7 +151,7 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
     const int smem_bytes = (int)(per_group_bytes * h->groups_per_cta);
     CK(cfrb::cfr_configure<real>(32, smem_bytes));
     const char* no_d2 = std::getenv("CFRB_NO_D2");
-    if (h->max_levels <= 3 && h->cfg.solver == CFRB_SOLVER_CFR && !(no_d2 && *no_d2 == '1')) {
+    if (h->max_levels <= 3 && !(no_d2 && *no_d2 == '1')) {
       // 4 CTAs of up to 8 warps per SM (register file: 64 registers x 32 warps), each with 1 KB reserved by the runtime
       h->d2 = true;
       h->d2_scratch_per_group = cfrb::cfr_scratch_reals_d2(h->Nmax, h->g.H, h->Lmax, h->Tmax);
