@@ -76,7 +76,7 @@ class ClockSampler:
     nvidia-smi CLI at 5 Hz was measured to slow the timed loop by ~9 % (driver-side query cost), NVML calls do not."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=float(os.environ.get("BENCH_SAMPLER_PERIOD", "0.1"))):
         self.index, self.period, self.rows, self.stop_flag, self.t, self.nv, self.h, self.max_mhz = index, period, [], False, None, None, None, None
 
     def start(self):
@@ -114,7 +114,7 @@ class ClockSampler:
         sm = [r[0] for r in self.rows]
         active = sorted(name for name, bit in self.REASONS.items() if any(r[1] & bit for r in self.rows))
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_mhz) if self.max_mhz else None,
-                "reasons": active, "samples": len(sm), "source": "nvml, 10 Hz during the timed steps"}
+                "reasons": active, "samples": len(sm), "source": f"nvml, every {self.period:g} s during the timed steps"}
 
 
 def effective_cores():
@@ -274,22 +274,26 @@ def run_b200(args):
 
     # ================= device-resident throughput (`value`) =================
     S.begin(t_lb.numpy(), t_pl.numpy(), t_b.numpy(), t_act.numpy())
-    for _ in range(args.warmup):
-        S.reset(stream); S.run(iters, stream)
-    S.set_profiling(16)                     # CUDA-event pairs around every 16th value-net launch of the timed steps
+    S.set_profiling(int(os.environ.get("BENCH_PROFILE_EVERY", "16")))   # CUDA-event pairs around every 16th value-net launch of the timed steps
+    for _ in range(args.warmup):            # same launch configuration as the timed steps (the run is replayed from a CUDA graph
+        S.reset(stream); S.run(iters, stream)   # that is built the second time a configuration is requested)
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":
         sampler.start()
     launches0 = S.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     net_ms = 0.0
+    run_ms, wall = [], []
     e0.record()
     for _ in range(args.steps):
+        tw = time.perf_counter()
         flush.fill_(1)                      # evict L2 between steps (inside the timed region)
         S.reset(stream)
         S.run(iters, stream)
-        net_ms += S.last_run_ms()[1]        # waits for this step; value-net kernel time from per-launch CUDA events
+        tr, tn = S.last_run_ms()            # waits for this step; value-net kernel time from per-launch CUDA events
+        net_ms += tn
+        run_ms.append(round(tr, 2)); wall.append(round(1e3 * (time.perf_counter() - tw), 2))
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -305,7 +309,7 @@ def run_b200(args):
         S.run(iters, stream)
         q, v = S.examples()                                                   # D2H: training examples of the wave
         return rbdist.gather_examples(q, v, dev)                              # NCCL gather of the example blocks on rank 0
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(min(args.warmup, 2)):
         e2e_step()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,6 +345,7 @@ def run_b200(args):
     roofline = {"bound": "tensor", "kernel": "leaf value net (Net2 forward over all pseudo-leaf rows of the wave)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                 "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "peak_source": peaks["src"], "avg_launch_ms": avg_net_ms, "launch_timing": "CUDA events around every 16th launch inside the timed steps",
+                "step_run_ms": run_ms, "step_wall_ms": wall,
                 "rows_per_launch": rows,
                 "flops_per_launch": flops_launch, "share_of_step": net_ms / ms if ms > 0 else None,
                 "cfr_tables_algorithmic_GBps": (4 * H * (90 + 6 * 45) + 4 * 66 * (Q + H) + 8 * H) * K * iters * args.steps / max(ms - net_ms, 1e-9) / 1e6

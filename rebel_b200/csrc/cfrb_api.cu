@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <array>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -85,6 +86,11 @@ struct cfrb_handle {
   int net_launch_idx = 0, net_launches_run = 0;
   std::vector<cudaEvent_t> net_ev;   // pairs around value-net launches (profiling mode)
   int net_ev_used = 0;
+  // CUDA graphs of whole cfrb_run calls (2 launches per iteration would otherwise be enqueued one by one by the host)
+  struct GraphEntry { int first, count, prof, has_rows; cudaGraphExec_t exec; int launches, net_launches, ev_used; };
+  std::vector<GraphEntry> graphs;
+  std::vector<std::array<int, 4>> graph_seen;   // keys requested once: a graph is only built for a key that comes back
+  bool capturing = false;           // launch geometry independent of the wave size while a graph is being captured / replayed
   // device: templates
   DevBuf<cfrb::TemplateDev> d_tmpl;
   DevBuf<int> d_parent, d_child_begin, d_nchild, d_last_bid, d_level_begin, d_pleaf_node, d_term_node;
@@ -200,12 +206,13 @@ static int launch_init_t(cfrb_handle* h, cudaStream_t st) {
 template <typename real>
 static int launch_iter_t(cfrb_handle* h, cudaStream_t st, int iter, int do_b, int do_f) {
   auto& s = state_of<real>(h);
+  const int nsg = h->capturing ? h->cfg.max_subgames : h->n;   // surplus groups return at once (k >= *wave_n)
   if (h->d2) {
-    const int blocks = (h->n + h->d2_groups_per_cta - 1) / h->d2_groups_per_cta;
+    const int blocks = (nsg + h->d2_groups_per_cta - 1) / h->d2_groups_per_cta;
     const size_t smem = (size_t)h->d2_scratch_per_group * sizeof(real) * h->d2_groups_per_cta;
     cfrb::cfr_launch_iter_d2<real>(s.dev, blocks, 32 * h->d2_groups_per_cta, smem, st, iter, do_b, do_f, h->d2_scratch_per_group);
   } else {
-    const int blocks = (h->n + h->groups_per_cta - 1) / h->groups_per_cta;
+    const int blocks = (nsg + h->groups_per_cta - 1) / h->groups_per_cta;
     const size_t smem = h->group == 32 ? (size_t)h->scratch_per_group * sizeof(real) * h->groups_per_cta : 0;
     cfrb::cfr_launch_iter<real>(s.dev, h->group, blocks, 32 * h->groups_per_cta, smem, st, iter, do_b, do_f, h->scratch_per_group);
   }
@@ -400,6 +407,7 @@ int cfrb_destroy(cfrb_handle* h) {
   h->d_wave.release(); h->d_sg_tmpl.release(); h->d_sg_player.release(); h->d_sg_row_off.release(); h->d_sg_act.release();
   h->d_steps.release(); h->d_X.release(); h->d_out.release(); h->d_dbg.release(); h->d_Xh.release();
   h->sf.release(); h->sd.release(); h->d_w.release(); h->d_blob.release();
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   for (auto e : h->net_ev) cudaEventDestroy(e);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
@@ -679,6 +687,12 @@ int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const in
   return CFRB_OK;
 }
 
+// Inside a stream capture a plain cudaEventRecord only marks a dependency; cudaEventRecordExternal makes it an event-record
+// NODE, whose timestamps can be synchronised on and read after every launch of the graph.
+static cudaError_t record_event(cfrb_handle* h, cudaEvent_t ev, cudaStream_t st) {
+  return h->capturing ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
+}
+
 static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2) {
   if (h->cfg.net_mode == CFRB_NET_ZERO || h->rows == 0) return CFRB_OK;
   const bool sample = h->profiling > 0 && (h->net_launch_idx % h->profiling) == 0;
@@ -689,13 +703,13 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
       CK(cudaEventCreate(&e));
       h->net_ev.push_back(e);
     }
-    CK(cudaEventRecord(h->net_ev[h->net_ev_used], st));
+    CK(record_event(h, h->net_ev[h->net_ev_used], st));
   }
   if (is_tc(h->cfg.net_mode)) {
     const cfrb::tc::BlobLayout L(h->Qpad);
     cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, dbg1, dbg2, nullptr};
     const int tiles = (h->rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
-    const int grid = std::min(tiles, h->num_sms);
+    const int grid = h->capturing ? h->num_sms : std::min(tiles, h->num_sms);   // surplus CTAs return at once
     const bool x2 = h->cfg.net_mode == CFRB_NET_TC_F16X2;
     a.trace = h->dbg_trace;
     if (dbg1 || dbg2 || a.trace) {
@@ -716,7 +730,7 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
   ++h->launches;
   CK(cudaGetLastError());
   if (sample) {
-    CK(cudaEventRecord(h->net_ev[h->net_ev_used + 1], st));
+    CK(record_event(h, h->net_ev[h->net_ev_used + 1], st));
     h->net_ev_used += 2;
   }
   return CFRB_OK;
@@ -736,6 +750,21 @@ int cfrb_set_profiling(cfrb_handle* h, int32_t on) {
   return CFRB_OK;
 }
 
+static int enqueue_run(cfrb_handle* h, cudaStream_t st, int first, int last) {
+  CK(record_event(h, h->ev_a, st));
+  h->net_ev_used = 0;
+  h->net_launch_idx = 0;
+  for (int i = first; i <= last; ++i) {
+    const int do_b = i > first, do_f = i < last;
+    int rc = DISPATCH_REAL(h, launch_iter_t, h, st, i, do_b, do_f);
+    if (rc) return rc;
+    if (do_f) { rc = launch_net(h, st, nullptr, nullptr); if (rc) return rc; }
+  }
+  CK(record_event(h, h->ev_b, st));
+  h->net_launches_run = h->net_launch_idx;
+  return CFRB_OK;
+}
+
 int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream) {
   if (!h || iters < 0) return fail(CFRB_EINVAL, "bad argument");
   if (h->cfg.net_mode != CFRB_NET_ZERO && !h->have_weights && h->Lmax > 0)
@@ -743,18 +772,70 @@ int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream) {
   if (h->n == 0 || iters == 0) return CFRB_OK;
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
-  CK(cudaEventRecord(h->ev_a, st));
-  h->net_ev_used = 0;
-  h->net_launch_idx = 0;
   const int first = h->iters_done, last = first + iters;
-  for (int i = first; i <= last; ++i) {
-    const int do_b = i > first, do_f = i < last;
-    int rc = DISPATCH_REAL(h, launch_iter_t, h, st, i, do_b, do_f);
-    if (rc) return rc;
-    if (do_f) { rc = launch_net(h, st, nullptr, nullptr); if (rc) return rc; }
+  // Long runs are replayed from a CUDA graph: one host call instead of 2 * iters kernel launches, so a busy or slow host
+  // thread cannot starve the GPU.  The graph bakes in the iteration indices and a wave-size-independent launch geometry; it
+  // is keyed by (first iteration, count, profiling period, "the wave has value-net rows").  The fp32 parity net sizes its grid
+  // by the row count and stays on the eager path, like short runs.
+  static const bool no_graph = [] { const char* e = std::getenv("CFRB_NO_GRAPH"); return e && *e == '1'; }();
+  const bool graphable = !no_graph && iters >= 64 && h->cfg.net_mode != CFRB_NET_FP32;
+  if (graphable) {
+    const int has_rows = h->rows > 0;
+    cfrb_handle::GraphEntry* g = nullptr;
+    for (auto& e : h->graphs)
+      if (e.first == first && e.count == iters && e.prof == h->profiling && e.has_rows == has_rows) { g = &e; break; }
+    if (!g) {
+      // capture + instantiation of ~2 * iters nodes costs ~0.1 s: only worth it for a key that repeats (waves of a self-play
+      // loop, bench steps), not for one-off run lengths (e.g. the evaluator's per-chunk act_iteration maxima)
+      const std::array<int, 4> key{first, iters, h->profiling, has_rows};
+      bool seen = false;
+      for (const auto& k : h->graph_seen) seen |= k == key;
+      if (!seen) {
+        if (h->graph_seen.size() >= 64) h->graph_seen.erase(h->graph_seen.begin());
+        h->graph_seen.push_back(key);
+      }
+      if (seen) {
+      if (h->profiling > 0)   // events are created outside the capture
+        while ((int)h->net_ev.size() < 2 * (iters / h->profiling + 2)) {
+          cudaEvent_t e;
+          CK(cudaEventCreate(&e));
+          h->net_ev.push_back(e);
+        }
+      const int64_t l0 = h->launches;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      h->capturing = true;
+      cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      int rc = CFRB_OK;
+      if (ce == cudaSuccess) {
+        rc = enqueue_run(h, st, first, last);
+        ce = cudaStreamEndCapture(st, &graph);
+        if (rc == CFRB_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+      }
+      h->capturing = false;
+      const int captured = (int)(h->launches - l0);
+      h->launches = l0;
+      if (rc == CFRB_OK && ce == cudaSuccess && exec) {
+        if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+        h->graphs.push_back({first, iters, h->profiling, has_rows, exec, captured, h->net_launches_run, h->net_ev_used});
+        g = &h->graphs.back();
+      } else {
+        cudaGetLastError();   // the stream could not be captured (e.g. a legacy stream): run eagerly
+      }
+      }
+    }
+    if (g) {
+      CK(cudaGraphLaunch(g->exec, st));
+      h->launches += g->launches;
+      h->net_launches_run = g->net_launches;
+      h->net_ev_used = g->ev_used;
+      h->iters_done = last;
+      return CFRB_OK;
+    }
   }
-  CK(cudaEventRecord(h->ev_b, st));
-  h->net_launches_run = h->net_launch_idx;
+  int rc = enqueue_run(h, st, first, last);
+  if (rc) return rc;
   h->iters_done = last;
   return CFRB_OK;
 }
