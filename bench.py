@@ -101,10 +101,14 @@ class ClockSampler:
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:  # noqa: BLE001
                     reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((mhz, reasons))
+                self.rows.append((mhz, reasons, time.perf_counter()))
             except Exception:  # noqa: BLE001
                 pass
             time.sleep(self.period)
+
+    def window(self, t0, t1):
+        """Keep only the samples taken inside the timed region [t0, t1] (perf_counter)."""
+        self.rows = [r for r in self.rows if t0 <= r[2] <= t1]
 
     def stop(self):
         if self.nv is None:
@@ -275,16 +279,17 @@ def run_b200(args):
     # ================= device-resident throughput (`value`) =================
     S.begin(t_lb.numpy(), t_pl.numpy(), t_b.numpy(), t_act.numpy())
     S.set_profiling(int(os.environ.get("BENCH_PROFILE_EVERY", "16")))   # CUDA-event pairs around every 16th value-net launch of the timed steps
+    sampler = ClockSampler(local)           # NVML is initialised and polling before the warm-up: its start-up (driver locks) must not
+    if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":   # land in the timed region; only samples taken inside it are reported
+        sampler.start()
     for _ in range(args.warmup):            # same launch configuration as the timed steps (the run is replayed from a CUDA graph
         S.reset(stream); S.run(iters, stream)   # that is built the second time a configuration is requested)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":
-        sampler.start()
     launches0 = S.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     net_ms = 0.0
     run_ms, wall = [], []
+    t_region0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         tw = time.perf_counter()
@@ -296,6 +301,8 @@ def run_b200(args):
         run_ms.append(round(tr, 2)); wall.append(round(1e3 * (time.perf_counter() - tw), 2))
     e1.record()
     barrier()
+    if rank == 0:
+        sampler.window(t_region0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = S.kernel_launches - launches0
