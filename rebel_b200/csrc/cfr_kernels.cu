@@ -59,10 +59,23 @@ cudaError_t cfr_configure_d2(int smem_bytes) {
   return e;
 }
 
+// Launch with programmatic stream serialization (PDL): the grid may start before its predecessor in the stream has finished;
+// the kernel orders itself with griddepcontrol.wait.  Captured into CUDA graphs as a programmatic dependency edge.
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <typename real>
 void cfr_launch_iter_d2(const CfrDev<real>& p, int blocks, int threads, size_t smem, cudaStream_t st, int iter, int do_b, int do_f,
                         int scratch_per_group) {
-#define CFRB_CALL(HC) cfr_iter_d2_kernel<real, HC><<<blocks, threads, smem, st>>>(p, iter, do_b, do_f, scratch_per_group)
+#define CFRB_CALL(HC) launch_pdl(cfr_iter_d2_kernel<real, HC>, blocks, threads, smem, st, p, iter, do_b, do_f, scratch_per_group)
   CFRB_DISPATCH_H(p.H, CFRB_CALL)
 #undef CFRB_CALL
 }

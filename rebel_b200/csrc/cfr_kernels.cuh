@@ -850,6 +850,9 @@ template <typename real, int HC>
 __global__ void __launch_bounds__(256, 4) cfr_iter_d2_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
+  // Programmatic dependent launch: the value-net kernel that follows may be scheduled as soon as every CTA of this grid has
+  // started (its weight-staging prologue then overlaps this grid's tail) ...
+  asm volatile("griddepcontrol.launch_dependents;");
   const int groups_per_cta = blockDim.x / 32;
   const int gid = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int k = blockIdx.x * groups_per_cta + gid;
@@ -880,6 +883,9 @@ __global__ void __launch_bounds__(256, 4) cfr_iter_d2_kernel(CfrDev<real> p, int
       }
     }
   }
+  // ... and this grid, launched the same way behind the previous value-net kernel, must not touch that kernel's outputs (or
+  // tables a still earlier CFR launch wrote) before the kernel has completed.  A no-op for ordinary launches.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncwarp();
   const int tb = (iter - 1) & 1;
   const int rp = p.sg_player[k];

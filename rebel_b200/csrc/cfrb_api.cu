@@ -720,8 +720,15 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
       if (x2) cfrb::tc::leaf_mlp_tc2_kernel<true><<<grid, cfrb::tc::kThreads, T2.smem_bytes, st>>>(a);
       else cfrb::tc::leaf_mlp_tc2_kernel<false><<<grid, cfrb::tc::kThreads, T2.smem_bytes, st>>>(a);
     } else {
-      if (x2) cfrb::tc::leaf_mlp_tc_kernel<false, true><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
-      else cfrb::tc::leaf_mlp_tc_kernel<false, false><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
+      // programmatic dependent launch: the kernel stages its weights while the CFR kernel before it drains (leaf_mlp_tc.cuh)
+      cudaLaunchConfig_t lc{};
+      lc.gridDim = dim3(grid); lc.blockDim = dim3(cfrb::tc::kThreads); lc.dynamicSmemBytes = L.smem_bytes; lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      if (x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<false, true>, a));
+      else CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<false, false>, a));
     }
   } else {
     const int blocks = (h->rows + cfrb::kMlpRows - 1) / cfrb::kMlpRows;
