@@ -847,7 +847,7 @@ __device__ void cfr_forward_d2(const CfrDev<real>& p, int k, int trav, real* slo
 
 // Scratch of a d2 group (reals): slot[nh_max] | bel[2*H] | hist[tmp_reals] | lsum[2*Lmax]
 template <typename real, int HC>
-__global__ void __launch_bounds__(256, 4) cfr_iter_d2_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
+__global__ void __launch_bounds__(128, 8) cfr_iter_d2_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   // Programmatic dependent launch: the value-net kernel that follows may be scheduled as soon as every CTA of this grid has

@@ -158,12 +158,14 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
     CK(cfrb::cfr_configure<real>(32, smem_bytes));
     const char* no_d2 = std::getenv("CFRB_NO_D2");
     if (h->max_levels <= 3 && !(no_d2 && *no_d2 == '1')) {
-      // 4 CTAs of up to 8 warps per SM (register file: 64 registers x 32 warps), each with 1 KB reserved by the runtime
+      // 32 warps per SM (register file: 64 registers x 32 warps) as 8 CTAs of 4 warps: small CTAs even out the last round
+      // (8192 subgames on 4736 warp slots = 1.73 rounds); each CTA has 1 KB of shared memory reserved by the runtime
       h->d2 = true;
       h->d2_scratch_per_group = cfrb::cfr_scratch_reals_d2(h->Nmax, h->g.H, h->Lmax, h->Tmax);
       const size_t d2_bytes = (size_t)h->d2_scratch_per_group * sizeof(real);
-      const size_t cta_budget = ((size_t)228 * 1024 - 4 * 1024) / 4;
-      h->d2_groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(8, cta_budget / d2_bytes));
+      const size_t cta_budget = ((size_t)228 * 1024 - 8 * 1024) / 8;
+      h->d2_groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(4, cta_budget / d2_bytes));
+      if (const char* e = std::getenv("CFRB_D2_GROUPS")) h->d2_groups_per_cta = std::max(1, std::min(h->d2_groups_per_cta, std::atoi(e)));
       CK(cfrb::cfr_configure_d2<real>((int)(d2_bytes * h->d2_groups_per_cta)));
     }
   } else {
