@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--games", type=int, default=8192, help="concurrent games per thread loop")
     ap.add_argument("--threads", type=int, default=2, help="thread loops per GPU (selfplay.threads_per_gpu)")
     ap.add_argument("--iters", type=int, default=1024)
+    ap.add_argument("--fp", action="store_true", help="fictitious play instead of CFR (use_cfr = false, the YAML default)")
     ap.add_argument("--devices", type=int, default=1, help="GPUs: one ModelLocker per cuda:i like selfplay.py:193-220")
     ap.add_argument("--seconds", type=float, default=20.0)
     ap.add_argument("--warmup", type=float, default=4.0)
@@ -28,7 +29,7 @@ def main():
     cfg.num_dice, cfg.num_faces, cfg.random_action_prob, cfg.sample_leaf = D, F, 0.25, True
     cfg.concurrent_games = args.games
     sp = cfg.subgame_params
-    sp.num_iters, sp.max_depth, sp.linear_update, sp.use_cfr = args.iters, 2, True, True
+    sp.num_iters, sp.max_depth, sp.linear_update, sp.use_cfr = args.iters, 2, True, not args.fp
     ctx = rela.Context()
     for d, locker in enumerate(lockers):
         for i in range(args.threads):
@@ -45,7 +46,7 @@ def main():
     while not ctx.terminated():
         time.sleep(0.05)
     ex = (n1 - n0) / (t1 - t0)
-    print(json.dumps({"game": f"{D}x{F}f", "concurrent_games": args.games, "devices": args.devices, "thread_loops_per_device": args.threads, "cfr_iters": args.iters,
+    print(json.dumps({"game": f"{D}x{F}f", "concurrent_games": args.games, "devices": args.devices, "thread_loops_per_device": args.threads, "solver": "fp" if args.fp else "cfr", "iters": args.iters,
                       "examples_per_s": ex, "subgames_per_s": ex / 2, "subgame_iters_per_s": ex / 2 * args.iters,
                       "seconds": t1 - t0, "error": ctx.error()}))
 
