@@ -18,6 +18,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/cfrb200.h"
@@ -44,6 +45,7 @@ class BatchedRlRunner {
     A_ = cfrb_num_actions(h_); H_ = cfrb_num_hands(h_); Q_ = cfrb_query_size(h_);
     stride_ = cfrb_table_stride(h_);
     trees_.resize(A_);   // root bids -1 .. A-2
+    for (int b = -1; b <= A_ - 2; ++b) tree(b);   // built up front: the per-game walk runs on several threads and only reads them
     games_.resize(K_);
     for (int g = 0; g < K_; ++g) {
       // game 0 carries the caller's seed verbatim (parity with RlRunner(seed)); the others get decorrelated streams
@@ -79,11 +81,23 @@ class BatchedRlRunner {
     check(cfrb_fetch_compact(h_, /*snapshot*/ 0, snap_.data()), "cfrb_fetch_compact");
     check(cfrb_examples(h_, ex_q_.data(), ex_v_.data()), "cfrb_examples");
     subgames_solved_ += K_;
-    for (int g = 0; g < K_; ++g) {
-      Game& G = games_[g];
-      const double* sigma = snap_.data() + (size_t)g * stride_;
-      if (cfg_.sample_leaf) sampleToLeaf(G, sigma); else sampleSingle(G, sigma);
-      if (G.last_bid == A_ - 1) resetGame(G);   // terminal: RlRunner::step returns, the next call starts a new game
+    // every game owns its random stream and beliefs, so the walk is split over a few host threads without changing any result
+    auto walk = [this](int g0, int g1) {
+      for (int g = g0; g < g1; ++g) {
+        Game& G = games_[g];
+        const double* sigma = snap_.data() + (size_t)g * stride_;
+        if (cfg_.sample_leaf) sampleToLeaf(G, sigma); else sampleSingle(G, sigma);
+        if (G.last_bid == A_ - 1) resetGame(G);   // terminal: RlRunner::step returns, the next call starts a new game
+      }
+    };
+    const int T = K_ >= 2048 ? 4 : 1;
+    if (T == 1) {
+      walk(0, K_);
+    } else {
+      std::vector<std::thread> th;
+      for (int i = 1; i < T; ++i) th.emplace_back(walk, (int)((int64_t)K_ * i / T), (int)((int64_t)K_ * (i + 1) / T));
+      walk(0, K_ / T);
+      for (auto& x : th) x.join();
     }
     return sink(ex_q_.data(), Q_, ex_v_.data(), H_, 2 * K_);
   }
