@@ -202,28 +202,31 @@ template <bool kDebug, bool kGeluX2>
 __device__ __forceinline__ void epilogue_ln_gelu(uint32_t tmem_row, int part_id, int row, const float2* __restrict__ ln, float2* part,
                                                  uint32_t bar_a0, uint32_t bar_dfree, float* dbg_row, long long* tr) {
   uint32_t xr[kColsPerThread];
-  {
-    uint32_t* lo = xr; uint32_t* hi = xr + 32;
-    CFRB_TMEM_LD32(tmem_row + kColD + part_id * kColsPerThread, lo);
-    CFRB_TMEM_LD32(tmem_row + kColD + part_id * kColsPerThread + 32, hi);
-    tmem_wait_ld();
-  }
-  if (kDebug && tr) tr[0] = clock64();
   float sum, sumsq;
   {
+    // the second half of the quarter row is still arriving from TMEM while the first half is summed
+    uint32_t* lo = xr; uint32_t* hi = xr + 32;
+    CFRB_TMEM_LD32(tmem_row + kColD + part_id * kColsPerThread, lo);
+    tmem_wait_ld();
+    CFRB_TMEM_LD32(tmem_row + kColD + part_id * kColsPerThread + 32, hi);
+    if (kDebug && tr) tr[0] = clock64();
     // two independent accumulator pairs: 2 x 2 interleaved chains of 16 packed adds / fmas instead of one chain of 32
     f32x2 s2[2], q2[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) { s2[u] = pack2(0.f, 0.f); q2[u] = pack2(0.f, 0.f); }
 #pragma unroll
-    for (int i = 0; i < kColsPerThread; i += 2) {
-      if (kDebug && dbg_row) {
-        dbg_row[part_id * kColsPerThread + i] = __uint_as_float(xr[i]);
-        dbg_row[part_id * kColsPerThread + i + 1] = __uint_as_float(xr[i + 1]);
+    for (int half = 0; half < 2; ++half) {
+      if (half == 1) tmem_wait_ld();
+#pragma unroll
+      for (int i = half * 32; i < half * 32 + 32; i += 2) {
+        if (kDebug && dbg_row) {
+          dbg_row[part_id * kColsPerThread + i] = __uint_as_float(xr[i]);
+          dbg_row[part_id * kColsPerThread + i + 1] = __uint_as_float(xr[i + 1]);
+        }
+        const f32x2 x2 = pack2(__uint_as_float(xr[i]), __uint_as_float(xr[i + 1]));
+        s2[(i >> 1) & 1] = add2(s2[(i >> 1) & 1], x2);
+        q2[(i >> 1) & 1] = fma2(x2, x2, q2[(i >> 1) & 1]);
       }
-      const f32x2 x2 = pack2(__uint_as_float(xr[i]), __uint_as_float(xr[i + 1]));
-      s2[(i >> 1) & 1] = add2(s2[(i >> 1) & 1], x2);
-      q2[(i >> 1) & 1] = fma2(x2, x2, q2[(i >> 1) & 1]);
     }
     const f32x2 st = add2(s2[0], s2[1]), qt = add2(q2[0], q2[1]);
     float a0, a1, b0, b1;
