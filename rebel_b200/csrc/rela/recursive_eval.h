@@ -28,65 +28,6 @@
 
 namespace rela {
 
-// Best response of both players against `strategy` (dense [N][H][A], fp64) on the full tree from uniform beliefs:
-// BRSolver::compute_br + compute_exploitability2 (subgame_solving.cc:316-358, 802-816).
-inline std::array<double, 2> best_response_values(int D, int F, const std::vector<cfrb_node>& tree, const std::vector<double>& strategy) {
-  const int A = 1 + 2 * D * F;
-  int H = 1;
-  for (int i = 0; i < D; ++i) H *= F;
-  const int N = (int)tree.size();
-  auto matches = [&](int hand, int face) { int m = 0; for (int i = 0; i < D; ++i) { int d = hand % F; m += (d == face || d == F - 1); hand /= F; } return m; };
-  std::array<double, 2> out{};
-  std::vector<double> reach((size_t)2 * N * H), val((size_t)N * H);
-  for (int p = 0; p < 2; ++p)   // compute_reach_probabilities (:54-78) from uniform beliefs
-    for (int n = 0; n < N; ++n)
-      for (int h = 0; h < H; ++h) {
-        double& r = reach[((size_t)p * N + n) * H + h];
-        if (n == 0) { r = 1.0 / H; continue; }
-        const int par = tree[n].parent;
-        const double rp = reach[((size_t)p * N + par) * H + h];
-        r = tree[par].player_id == p ? rp * strategy[((size_t)par * H + h) * A + tree[n].last_bid] : rp;
-      }
-  for (int trav = 0; trav < 2; ++trav) {
-    for (int n = N; n-- > 0;) {
-      const int nc = tree[n].children_end - tree[n].children_begin;
-      double* v = &val[(size_t)n * H];
-      if (tree[n].last_bid == A - 1) {   // terminal: compute_expected_terminal_values (:80-98, :765-789)
-        const int bid = tree[tree[n].parent].last_bid, quantity = 1 + bid / F, face = bid % F;
-        const double* ro = &reach[((size_t)(1 - trav) * N + n) * H];
-        std::vector<double> cnt(2 * D + 1, 0.0);
-        double tot = 0;
-        for (int g = 0; g < H; ++g) { cnt[matches(g, face)] += ro[g]; }
-        for (int i = (int)cnt.size() - 1; i-- > 0;) cnt[i] += cnt[i + 1];
-        for (int g = 0; g < H; ++g) tot += ro[g];
-        for (int h = 0; h < H; ++h) {
-          const int left = std::max(0, quantity - matches(h, face));
-          const float pw = (float)cnt[left];
-          double x = (double)pw * 2 - tot;
-          v[h] = tree[n].player_id != trav ? -x : x;
-        }
-        continue;
-      }
-      if (!nc) continue;
-      for (int h = 0; h < H; ++h) v[h] = 0.0;
-      if (tree[n].player_id == trav) {
-        for (int c = tree[n].children_begin; c < tree[n].children_end; ++c)
-          for (int h = 0; h < H; ++h) {
-            const double nv = val[(size_t)c * H + h];
-            if (c == tree[n].children_begin || nv > v[h]) v[h] = nv;   // first child wins ties (:336-337)
-          }
-      } else {
-        for (int c = tree[n].children_begin; c < tree[n].children_end; ++c)
-          for (int h = 0; h < H; ++h) v[h] += val[(size_t)c * H + h];
-      }
-    }
-    double s = 0;
-    for (int h = 0; h < H; ++h) s += val[h];
-    out[trav] = s / H;
-  }
-  return out;
-}
-
 struct RecursiveEvalResult {
   std::vector<float> summed_strategy;   // [N][H][A]
   std::vector<float> summed_reach;      // [N][H]

@@ -216,15 +216,22 @@ py::dict recursive_eval_sampled(const RecursiveSolvingParams& cfg, int device, i
   return d;
 }
 
-// compute_exploitability2 (subgame_solving.cc:802-816) of a dense full-tree strategy [N][H][A]; host code, no GPU needed.
+// compute_exploitability2 (subgame_solving.cc:802-816) of a dense full-tree strategy [N][H][A] on the GPU best-response kernel.
 std::tuple<double, double> exploitability_of_strategy(int num_dice, int num_faces, torch::Tensor strategy) {
   auto s = strategy.to(torch::kCPU, torch::kFloat64).contiguous();
-  std::vector<cfrb_node> tree(1 << 20);
-  const int n = cfrb_unroll_tree(num_dice, num_faces, -1, 0, 1 << 30, tree.data(), (int)tree.size());
-  if (n <= 0 || n > (int)tree.size() || s.dim() != 3 || s.size(0) != n) throw std::runtime_error("exploitability_of_strategy: strategy must be [num_full_tree_nodes, H, A]");
-  tree.resize(n);
-  std::vector<double> v(s.data_ptr<double>(), s.data_ptr<double>() + s.numel());
-  auto e = best_response_values(num_dice, num_faces, tree, v);
+  cfrb_config c{};
+  c.num_dice = num_dice; c.num_faces = num_faces; c.max_depth = 2; c.num_iters = 1; c.max_subgames = 1; c.device = eval_device();
+  c.net_mode = CFRB_NET_ZERO; c.hidden = 256;
+  cfrb_handle* h = nullptr;
+  if (cfrb_create(&c, &h) < 0) throw std::runtime_error(std::string("cfrb_create: ") + cfrb_last_error());
+  const int64_t A = cfrb_num_actions(h), H = cfrb_num_hands(h);
+  const int64_t N = A <= 26 ? ((int64_t)1 << A) - 1 : -1;      // the full Liar's Dice tree has 2^A - 1 nodes
+  std::array<double, 2> e{};
+  int rc = -1;
+  if (s.dim() == 3 && s.size(0) == N && s.size(1) == H && s.size(2) == A) rc = cfrb_exploitability(h, s.data_ptr<double>(), e.data());
+  const std::string err = rc < 0 && s.dim() == 3 && s.size(0) == N ? cfrb_last_error() : "";
+  cfrb_destroy(h);
+  if (rc < 0) throw std::runtime_error(err.empty() ? "exploitability_of_strategy: strategy must be [num_full_tree_nodes, H, A]" : err);
   return std::make_tuple(e[0], e[1]);
 }
 
@@ -302,7 +309,7 @@ PYBIND11_MODULE(rela, m) {
         py::arg("flat_weights") = py::none(),
         "rebel_b200 extension: run `waves` waves of a BatchedRlRunner synchronously and return (queries, values).");
   m.def("exploitability_of_strategy", &exploitability_of_strategy, py::arg("num_dice"), py::arg("num_faces"), py::arg("strategy"),
-        "rebel_b200 extension: compute_exploitability2 of a dense full-tree strategy (host best response).");
+        "rebel_b200 extension: compute_exploitability2 of a dense full-tree strategy (GPU best-response kernel).");
   m.def("recursive_eval_sampled", &recursive_eval_sampled, py::arg("cfg"), py::arg("device"), py::arg("num_repeats"), py::arg("seed") = 0,
         py::arg("batch_repeats") = 64, py::arg("wave_capacity") = 8192, py::arg("flat_weights") = py::none(),
         "rebel_b200 extension: the reference's `recursive_eval --cfr --num_repeats R` (sampled recursive strategies, float32 "

@@ -133,17 +133,19 @@ def test_model_locker_snapshots_weights(rela):
         rela.ModelLocker([torch.nn.Linear(3, 3)], "cuda:0")
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("D,F", [(1, 2), (1, 3), (1, 4)])
-def test_host_best_response_bit_exact(rela, golden, D, F):
-    """exploitability_of_strategy = compute_exploitability2 / BRSolver::compute_br (subgame_solving.cc:316-358,802-816):
-    bit-identical to the compiled reference on the golden 16-iteration full-tree strategies."""
+def test_exploitability_of_strategy_bit_exact(rela, golden, D, F):
+    """exploitability_of_strategy = compute_exploitability2 / BRSolver::compute_br (subgame_solving.cc:316-358,802-816) on the
+    GPU best-response kernel: bit-identical to the compiled reference on the golden 16-iteration full-tree strategies."""
     g = golden("fulltree.npz")
     e = rela.exploitability_of_strategy(D, F, torch.from_numpy(g[f"avg16_{D}x{F}"]))
     assert np.array_equal(np.array(e), g[f"expl_{D}x{F}_nofma"][0])
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("D,F", [(1, 4), (1, 6), (2, 3)])
-def test_host_best_response_on_recursive_eval_golden(rela, golden, D, F):
+def test_exploitability_of_strategy_on_recursive_eval_golden(rela, golden, D, F):
     g = golden("recursive_eval_zero.npz")
     ss, sr = g[f"summed_strategy_{D}x{F}"], g[f"summed_reach_{D}x{F}"]
     e = rela.exploitability_of_strategy(D, F, torch.from_numpy(ss / (sr + np.float32(1e-6))))
