@@ -212,7 +212,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 (CFR) / f32 (value net)", "data": "synthetic",
         # the workload is the B200 arm's (args.subgames concurrent subgames); each step times a bounded sample of it (cpu_baseline.sample)
-        "config": dict(workload_config(args, args.subgames), sample_subgames_per_step=n, parallelism="cpu threads"), "cpu_baseline": info,
+        "config": dict(workload_config(args, args.subgames), parallelism="cpu threads"), "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
