@@ -12,6 +12,10 @@
  * /root/reference (oracle/_ref, see oracle/Makefile + ref_harness.cc) — bit-exact for the zero-net
  * CFR trajectories when both are built with -ffp-contract=off — and against the committed
  * fixtures in tests/golden/ that were generated from oracle/_ref by oracle/make_golden.py.
+ * Covered: game, tree, CFR (linear / vanilla / DCFR), fictitious play (linear / optimistic), terminal
+ * payoffs, query rows, Net2 forward, best response / exploitability, the RlRunner walk and the
+ * sampled recursive strategies of recursive_eval — all bit-identical to the compiled reference
+ * with the zero net.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference/csrc/liars_dice/).
@@ -748,6 +752,106 @@ int orc_rl_runner(int D, int F, int num_iters, int max_depth, int linear_update,
 
 /* ------------------------------------------------------------------ synthetic inputs + timed port baseline */
 /* uniform_real_distribution<double>(0,1) = generate_canonical<double,53> (two draws each). */
+/* ------------------------------------------------------------------ sampled recursive strategies (BASELINE config 5) */
+/* std::discrete_distribution over n weights of any length (the iteration weights: n = num_iters) */
+static int discrete_n(orc_mt* m, const double* w, int n) {
+  if (n < 2) return 0;
+  double sum = 0; for (int i = 0; i < n; ++i) sum += w[i];
+  double* cp = (double*)malloc(sizeof(double) * n);
+  double acc = 0;
+  for (int i = 0; i < n; ++i) { acc += w[i] / sum; cp[i] = acc; }
+  cp[n - 1] = 1.0;
+  double p = canonical_d(m);
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) / 2; if (cp[mid] < p) lo = mid + 1; else hi = mid; }
+  free(cp);
+  return lo;
+}
+
+typedef struct {
+  orc_game g; const orc_node* full; int D, F, num_iters, max_depth, linear, hidden; const float* net_w;
+  const double* weights; orc_mt* gen; double* out;   /* out: dense [N_full][H][A] */
+} sampled_ctx;
+
+/* compute_strategy_recursive_to_leaf with use_samplig_strategy = true (recursive_solving.cc:76-134) under the solver builder of
+ * compute_sampled_strategy_recursive_to_leaf (:301-327): every subgame is solved for act_iteration ~ iteration weights and its
+ * LAST strategy both fills the inner nodes and propagates the beliefs; recursion happens while the BFS pops a non-final leaf. */
+static void sampled_rec(sampled_ctx* c, int node_id, const double* beliefs /*[2][H]*/) {
+  const orc_node* fn = &c->full[node_id];
+  if (game_is_terminal(&c->g, fn->last_bid)) return;
+  const int H = c->g.H, A = c->g.A;
+  const int act_iteration = discrete_n(c->gen, c->weights, c->num_iters);
+  orc_cfr* s = orc_cfr_create(c->D, c->F, fn->last_bid, fn->player_id, beliefs, act_iteration, c->max_depth, c->linear, 0, 0, 0, 0,
+                              c->net_w, c->hidden);
+  for (int it = 0; it < act_iteration; ++it) orc_cfr_step(s, it % 2);
+  int* qfull = (int*)malloc(sizeof(int) * s->N);
+  int* qpart = (int*)malloc(sizeof(int) * s->N);
+  double* qreach = (double*)malloc(sizeof(double) * (size_t)s->N * 2 * H);
+  int head = 0, tail = 0;
+  qfull[tail] = node_id; qpart[tail] = 0; memcpy(qreach, beliefs, sizeof(double) * 2 * H); ++tail;
+  while (head < tail) {
+    const int f = qfull[head], pn = qpart[head];
+    double* reach = qreach + (size_t)head * 2 * H;
+    ++head;
+    memcpy(c->out + (size_t)f * H * A, s->last + IDX3(s, pn, 0, 0), sizeof(double) * H * A);
+    const orc_node* pnode = &s->tree[pn];
+    const orc_node* fnode = &c->full[f];
+    const int pnc = pnode->children_end - pnode->children_begin, fnc = fnode->children_end - fnode->children_begin;
+    int lo, hi; game_bid_range(&c->g, fnode->last_bid, &lo, &hi);
+    for (int i = 0; i < pnc; ++i) {
+      double* cr = qreach + (size_t)tail * 2 * H;
+      memcpy(cr, reach, sizeof(double) * 2 * H);
+      const int pid = fnode->player_id, action = lo + i;
+      for (int h = 0; h < H; ++h) cr[pid * H + h] *= s->last[IDX3(s, pn, h, action)];
+      qfull[tail] = fnode->children_begin + i; qpart[tail] = pnode->children_begin + i; ++tail;
+    }
+    if (pnc == 0 && fnc != 0) {
+      normalize_safe_d(reach, H, 1e-80);
+      normalize_safe_d(reach + H, H, 1e-80);
+      sampled_rec(c, f, reach);
+    }
+  }
+  free(qfull); free(qpart); free(qreach);
+  orc_cfr_destroy(s);
+}
+
+/* Same signature and semantics as ref_sampled_strategy in oracle/ref_harness.cc. */
+int orc_sampled_strategy(int D, int F, int num_iters, int max_depth, int linear_update, int seed, const float* net_w, int hidden,
+                         double* strategy_out) {
+  sampled_ctx c;
+  c.g = game_make(D, F); c.D = D; c.F = F; c.num_iters = num_iters; c.max_depth = max_depth; c.linear = linear_update;
+  c.hidden = hidden; c.net_w = net_w; c.out = strategy_out;
+  int N = 0;
+  orc_node* full = tree_unroll(&c.g, -1, 0, 1000000, &N);
+  c.full = full;
+  double* weights = (double*)malloc(sizeof(double) * (num_iters > 0 ? num_iters : 1));
+  for (int i = 0; i < num_iters; ++i) weights[i] = i % 2 ? 0.0 : (i / 2. + 1);   /* :304-309 */
+  c.weights = weights;
+  orc_mt gen; mt_seed(&gen, (uint32_t)seed);
+  c.gen = &gen;
+  const int H = c.g.H;
+  memset(strategy_out, 0, sizeof(double) * (size_t)N * H * c.g.A);
+  double* beliefs = (double*)malloc(sizeof(double) * 2 * H);
+  for (int i = 0; i < 2 * H; ++i) beliefs[i] = 1. / H;
+  sampled_rec(&c, 0, beliefs);
+  free(beliefs); free(weights); free(full);
+  return N;
+}
+
+/* reach_probabilities of compute_stategy_stats (subgame_solving.cc:823-842): dense [2][N][H] from uniform beliefs. */
+int orc_strategy_reach(int D, int F, const double* strategy, double* reach_out) {
+  orc_cfr* s = (orc_cfr*)calloc(1, sizeof(orc_cfr));
+  s->g = game_make(D, F);
+  s->tree = tree_unroll(&s->g, -1, 0, 1000000, &s->N);
+  const int H = s->g.H, N = s->N;
+  double* beliefs = (double*)malloc(sizeof(double) * H);
+  for (int i = 0; i < H; ++i) beliefs[i] = 1. / H;
+  compute_reach(s, strategy, beliefs, 0, reach_out);
+  compute_reach(s, strategy, beliefs, 1, reach_out + (size_t)N * H);
+  free(beliefs); free(s->tree); free(s);
+  return N;
+}
+
 void orc_synthetic_beliefs(int H, int seed, double* out) {
   orc_mt m; mt_seed(&m, (uint32_t)seed);
   for (int p = 0; p < 2; ++p) {

@@ -193,8 +193,7 @@ class Oracle:
         return q[:n].copy(), v[:n].copy()
 
     def sampled_strategy(self, D, F, seed, num_iters=1024, max_depth=2, linear_update=True, net_w=None, hidden=256):
-        """compute_sampled_strategy_recursive_to_leaf (reference builds only): dense [N_full, H, A]."""
-        assert self.kind != "port"
+        """compute_sampled_strategy_recursive_to_leaf: dense [N_full, H, A]."""
         A, H, Q = game_dims(D, F)
         N = len(self.unroll_tree(D, F))
         out = np.zeros((N, H, A), np.float64)
@@ -208,7 +207,6 @@ class Oracle:
         return out
 
     def strategy_reach(self, D, F, strategy):
-        assert self.kind != "port"
         A, H, Q = game_dims(D, F)
         s = np.ascontiguousarray(strategy, np.float64)
         out = np.zeros((2, s.shape[0], H), np.float64)

@@ -212,6 +212,21 @@ def test_port_vs_compiled_reference_live():
         assert np.array_equal(qa, qb) and np.array_equal(va, vb)
 
 
+@pytest.mark.parametrize("D,F", SHAPES)
+def test_port_recursive_eval_bit_exact_vs_golden(port, golden, D, F):
+    """BASELINE config 5 in the C port: compute_sampled_strategy_recursive_to_leaf (recursive_solving.cc:76-134,301-327) with the
+    restated mt19937 / discrete_distribution, reach weights of compute_stategy_stats and the float32 accumulation loop of
+    recursive_eval.cc:343-369 reproduce the fixture generated from the compiled reference bit for bit."""
+    from oracle.make_golden import recursive_eval_reference
+    g = golden("recursive_eval_zero.npz")
+    iters, reps = (int(x) for x in g[f"cfg_{D}x{F}"])
+    r = recursive_eval_reference(port, D, F, iters, reps)
+    for k in ("summed_strategy", "summed_reach", "checkpoints", "exploitability"):
+        assert np.array_equal(r[k], g[f"{k}_{D}x{F}"]), k
+    if (D, F) == (1, 4):
+        assert np.array_equal(r["first_strategies"], g["first_strategies_1x4"])
+
+
 @pytest.mark.skipif(not available("ref_nofma"), reason="oracle/_ref not built (needs /root/reference)")
 def test_recursive_eval_golden_reproducible_live(golden):
     """The recursive-evaluation fixture (BASELINE config 5 path) is what the compiled reference produces here: its own
