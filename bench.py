@@ -283,7 +283,7 @@ def run_b200(args):
     sampler = ClockSampler(local)           # NVML is initialised and polling before the warm-up: its start-up (driver locks) must not
     if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":   # land in the timed region; only samples taken inside it are reported
         sampler.start()
-    for _ in range(args.warmup):            # exactly a timed step: the L2 flush too (the first launch of torch's fill kernel loads its
+    for _ in range(max(args.warmup, 3)):    # (at least 3: eager, graph capture, replay) exactly a timed step: the L2 flush too (the first launch of torch's fill kernel loads its
         flush.fill_(1)                      # module lazily, ~70 ms of host time), and the same run configuration (the run is replayed
         S.reset(stream); S.run(iters, stream)   # from a CUDA graph that is built the second time a configuration is requested)
     barrier()
@@ -318,7 +318,7 @@ def run_b200(args):
         S.run(iters, stream)
         q, v = S.examples()                                                   # D2H: training examples of the wave
         return rbdist.gather_examples(q, v, dev)                              # NCCL gather of the example blocks on rank 0
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(2):                      # eager, then graph capture of the (unprofiled) run configuration
         e2e_step()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
