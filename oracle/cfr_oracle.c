@@ -13,9 +13,10 @@
  * CFR trajectories when both are built with -ffp-contract=off — and against the committed
  * fixtures in tests/golden/ that were generated from oracle/_ref by oracle/make_golden.py.
  * Covered: game, tree, CFR (linear / vanilla / DCFR), fictitious play (linear / optimistic), terminal
- * payoffs, query rows, Net2 forward, best response / exploitability, the RlRunner walk and the
- * sampled recursive strategies of recursive_eval — all bit-identical to the compiled reference
- * with the zero net.
+ * payoffs, query rows, Net2 forward, best response / exploitability, the RlRunner walk, the
+ * sampled recursive strategies of recursive_eval and the evaluation entry points of rela/pybind.cc
+ * (compute_strategy_recursive[_to_leaf], eval_net) — bit-identical to the compiled reference with
+ * the zero net (eval_net's float32 mean: 1e-7 relative).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference/csrc/liars_dice/).
@@ -849,6 +850,179 @@ int orc_strategy_reach(int D, int F, const double* strategy, double* reach_out) 
   compute_reach(s, strategy, beliefs, 0, reach_out);
   compute_reach(s, strategy, beliefs, 1, reach_out + (size_t)N * H);
   free(beliefs); free(s->tree); free(s);
+  return N;
+}
+
+/* ------------------------------------------------------------------ evaluation entry points (rela/pybind.cc:45-84) */
+static void solve_all(orc_cfr* s, int use_cfr, int iters) {   /* multistep of CFR (:666-670) or FP (:462-466) */
+  for (int it = 0; it < iters; ++it) { if (use_cfr) orc_cfr_step(s, it % 2); else orc_fp_step(s, it % 2, 0); }
+}
+
+typedef struct {
+  orc_game g; const orc_node* full; int D, F, num_iters, max_depth, linear, use_cfr, hidden; const float* net_w; double* out;
+} eval_ctx;
+
+/* compute_strategy_recursive (recursive_solving.cc:46-74): a solver at EVERY non-terminal node; its average strategy's root row is
+ * kept; the acting player's beliefs are multiplied by that row and eps-normalised for each child. */
+static void strategy_recursive_rec(eval_ctx* c, int node_id, const double* beliefs) {
+  const orc_node* fn = &c->full[node_id];
+  if (game_is_terminal(&c->g, fn->last_bid)) return;
+  const int H = c->g.H, A = c->g.A;
+  orc_cfr* s = orc_cfr_create(c->D, c->F, fn->last_bid, fn->player_id, beliefs, c->num_iters, c->max_depth, c->linear, 0, 0, 0, 0,
+                              c->net_w, c->hidden);
+  solve_all(s, c->use_cfr, c->num_iters);
+  memcpy(c->out + (size_t)node_id * H * A, s->avg, sizeof(double) * H * A);   /* get_strategy()[0] */
+  orc_cfr_destroy(s);
+  int lo, hi; game_bid_range(&c->g, fn->last_bid, &lo, &hi);
+  double* nb = (double*)malloc(sizeof(double) * 2 * H);
+  for (int child = fn->children_begin; child < fn->children_end; ++child) {
+    const int action = child - fn->children_begin + lo, pid = fn->player_id;
+    memcpy(nb, beliefs, sizeof(double) * 2 * H);
+    for (int h = 0; h < H; ++h) nb[pid * H + h] *= c->out[((size_t)node_id * H + h) * A + action];
+    normalize_safe_d(nb + pid * H, H, 1e-80);
+    strategy_recursive_rec(c, child, nb);
+  }
+  free(nb);
+}
+
+/* compute_strategy_recursive_to_leaf with use_samplig_strategy = false (:76-134): all iterations, average strategy both as
+ * the strategy and for belief propagation. */
+static void strategy_to_leaf_rec(eval_ctx* c, int node_id, const double* beliefs) {
+  const orc_node* fnr = &c->full[node_id];
+  if (game_is_terminal(&c->g, fnr->last_bid)) return;
+  const int H = c->g.H, A = c->g.A;
+  orc_cfr* s = orc_cfr_create(c->D, c->F, fnr->last_bid, fnr->player_id, beliefs, c->num_iters, c->max_depth, c->linear, 0, 0, 0, 0,
+                              c->net_w, c->hidden);
+  solve_all(s, c->use_cfr, c->num_iters);
+  int* qfull = (int*)malloc(sizeof(int) * s->N);
+  int* qpart = (int*)malloc(sizeof(int) * s->N);
+  double* qreach = (double*)malloc(sizeof(double) * (size_t)s->N * 2 * H);
+  int head = 0, tail = 0;
+  qfull[tail] = node_id; qpart[tail] = 0; memcpy(qreach, beliefs, sizeof(double) * 2 * H); ++tail;
+  while (head < tail) {
+    const int f = qfull[head], pn = qpart[head];
+    double* reach = qreach + (size_t)head * 2 * H;
+    ++head;
+    memcpy(c->out + (size_t)f * H * A, s->avg + IDX3(s, pn, 0, 0), sizeof(double) * H * A);
+    const orc_node* pnode = &s->tree[pn];
+    const orc_node* fnode = &c->full[f];
+    const int pnc = pnode->children_end - pnode->children_begin, fnc = fnode->children_end - fnode->children_begin;
+    int lo, hi; game_bid_range(&c->g, fnode->last_bid, &lo, &hi);
+    for (int i = 0; i < pnc; ++i) {
+      double* cr = qreach + (size_t)tail * 2 * H;
+      memcpy(cr, reach, sizeof(double) * 2 * H);
+      const int pid = fnode->player_id, action = lo + i;
+      for (int h = 0; h < H; ++h) cr[pid * H + h] *= s->avg[IDX3(s, pn, h, action)];
+      qfull[tail] = fnode->children_begin + i; qpart[tail] = pnode->children_begin + i; ++tail;
+    }
+    if (pnc == 0 && fnc != 0) {
+      normalize_safe_d(reach, H, 1e-80);
+      normalize_safe_d(reach + H, H, 1e-80);
+      strategy_to_leaf_rec(c, f, reach);
+    }
+  }
+  free(qfull); free(qpart); free(qreach);
+  orc_cfr_destroy(s);
+}
+
+/* eval_net (stats.cc:44-153); node order = stable sort by decreasing reach (the reference's std::sort may order exact ties
+ * differently, which only permutes a float32 sum). */
+typedef struct { double reach; int node; } reach_key;
+static int reach_cmp(const void* a, const void* b) {
+  const reach_key* x = (const reach_key*)a; const reach_key* y = (const reach_key*)b;
+  if (x->reach > y->reach) return -1;
+  if (x->reach < y->reach) return 1;
+  return x->node - y->node;
+}
+static float eval_net_port(int D, int F, int mdp_depth, int fp_iters, const orc_node* full, int N, const double* net_strategy,
+                           const double* full_strategy, const orc_net* net, int traverse_by_net) {
+  orc_game g = game_make(D, F);
+  const int H = g.H, A = g.A, Q = 2 + A + 2 * H;
+  double* rn = (double*)malloc(sizeof(double) * 2 * (size_t)N * H);
+  double* rt = (double*)malloc(sizeof(double) * 2 * (size_t)N * H);
+  orc_strategy_reach(D, F, net_strategy, rn);
+  orc_strategy_reach(D, F, full_strategy, rt);
+  const double* trav = traverse_by_net ? rn : rt;
+  reach_key* top = (reach_key*)malloc(sizeof(reach_key) * N);
+  int nt = 0;
+  for (int i = 0; i < N; ++i) {
+    if ((full[i].depth == mdp_depth || full[i].depth == 2 * mdp_depth) && !game_is_terminal(&g, full[i].last_bid)) {
+      double s0 = 0, s1 = 0;
+      for (int h = 0; h < H; ++h) { s0 += trav[(size_t)i * H + h]; s1 += trav[((size_t)N + i) * H + h]; }
+      top[nt].reach = s0 * s1; top[nt].node = i; ++nt;
+    }
+  }
+  qsort(top, nt, sizeof(reach_key), reach_cmp);
+  const float kMinReach = 1e-6f;
+  while (nt > 0 && top[nt - 1].reach < kMinReach) --nt;
+  float total = 0.f; int count = 0;
+  double* beliefs = (double*)malloc(sizeof(double) * 2 * H);
+  float* query = (float*)malloc(sizeof(float) * Q);
+  float* out = (float*)malloc(sizeof(float) * H);
+  for (int k = 0; k < nt; ++k) {
+    const int node = top[k].node;
+    for (int p = 0; p < 2; ++p) {   /* normalize_probabilities (util.h:20-34) */
+      const double* r = trav + ((size_t)p * N + node) * H;
+      double sum = 0; for (int h = 0; h < H; ++h) sum += r[h];
+      for (int h = 0; h < H; ++h) beliefs[p * H + h] = r[h] / sum;
+    }
+    orc_cfr* s = orc_cfr_create(D, F, full[node].last_bid, full[node].player_id, beliefs, fp_iters, 10000, 1, 0, 0, 0, 0, NULL, 0);
+    solve_all(s, /*use_cfr=*/0, fp_iters);
+    for (int t = 0; t < 2; ++t) {
+      write_query(&g, t, full[node].last_bid, full[node].player_id, beliefs, beliefs + H, query);
+      net_forward(net, query, 1, out);
+      double nv = 0, bv = 0;
+      for (int h = 0; h < H; ++h) { nv += (double)out[h] * beliefs[t * H + h]; bv += s->root_means[t][h] * beliefs[t * H + h]; }
+      const float d = (float)nv - (float)bv;
+      total += (float)((double)d * (double)d);
+      ++count;
+    }
+    orc_cfr_destroy(s);
+  }
+  free(rn); free(rt); free(top); free(beliefs); free(query); free(out);
+  return count ? total / count : 0.f;
+}
+
+/* Same signature and semantics as ref_net_evaluation in oracle/ref_harness.cc. */
+int orc_net_evaluation(int D, int F, int num_iters, int max_depth, int linear_update, int use_cfr, const float* net_w, int hidden,
+                       int what, double* strategy_recursive, double* strategy_to_leaf, double* out4) {
+  eval_ctx c;
+  c.g = game_make(D, F); c.D = D; c.F = F; c.num_iters = num_iters; c.max_depth = max_depth; c.linear = linear_update;
+  c.use_cfr = use_cfr; c.hidden = hidden; c.net_w = net_w;
+  int N = 0;
+  orc_node* full = tree_unroll(&c.g, -1, 0, 1000000, &N);
+  c.full = full;
+  const int H = c.g.H, A = c.g.A;
+  const size_t dense = (size_t)N * H * A;
+  double* beliefs = (double*)malloc(sizeof(double) * 2 * H);
+  for (int i = 0; i < 2 * H; ++i) beliefs[i] = 1. / H;
+  double e[2];
+  if (what & 1) {
+    double* out = strategy_recursive ? strategy_recursive : (double*)malloc(sizeof(double) * dense);
+    memset(out, 0, sizeof(double) * dense);
+    c.out = out;
+    strategy_recursive_rec(&c, 0, beliefs);
+    orc_exploitability(D, F, out, e);
+    out4[0] = (e[0] + e[1]) / 2.0;
+    if (!strategy_recursive) free(out);
+  }
+  if (what & 2) {
+    double* out = strategy_to_leaf ? strategy_to_leaf : (double*)malloc(sizeof(double) * dense);
+    memset(out, 0, sizeof(double) * dense);
+    c.out = out;
+    strategy_to_leaf_rec(&c, 0, beliefs);
+    orc_exploitability(D, F, out, e);
+    out4[1] = (e[0] + e[1]) / 2.0;
+    /* full-tree solver with the same parameters (pybind.cc:69-73) */
+    orc_cfr* full_solver = orc_cfr_create(D, F, -1, 0, beliefs, num_iters, 100000, linear_update, 0, 0, 0, 0, NULL, 0);
+    solve_all(full_solver, use_cfr, num_iters);
+    orc_net net = net_from_flat(net_w, 2 + A + 2 * H, hidden, H);
+    out4[2] = eval_net_port(D, F, max_depth, num_iters, full, N, out, full_solver->avg, &net, 1);
+    out4[3] = eval_net_port(D, F, max_depth, num_iters, full, N, out, full_solver->avg, &net, 0);
+    orc_cfr_destroy(full_solver);
+    if (!strategy_to_leaf) free(out);
+  }
+  free(beliefs); free(full);
   return N;
 }
 

@@ -156,9 +156,8 @@ class Oracle:
         return out
 
     def net_evaluation(self, D, F, net_w, num_iters=64, max_depth=2, linear_update=True, use_cfr=True, hidden=256, what=3):
-        """rela/pybind.cc:45-84 with flat Net2 weights (reference builds only): dict with strategy_recursive / strategy_to_leaf
+        """rela/pybind.cc:45-84 with flat Net2 weights: dict with strategy_recursive / strategy_to_leaf
         [N,H,A] and values = [expl(recursive), expl(to_leaf), eval_net mse (net beliefs), eval_net mse (full-tree beliefs)]."""
-        assert self.kind != "port"
         A, H, Q = game_dims(D, F)
         N = len(self.unroll_tree(D, F))
         sr, sl = np.zeros((N, H, A)), np.zeros((N, H, A))

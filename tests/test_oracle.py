@@ -227,6 +227,25 @@ def test_port_recursive_eval_bit_exact_vs_golden(port, golden, D, F):
         assert np.array_equal(r["first_strategies"], g["first_strategies_1x4"])
 
 
+@pytest.mark.parametrize("use_cfr", [True, False])
+@pytest.mark.parametrize("netname", ["zero_out", "random"])
+def test_port_evaluation_entry_points_vs_golden(port, golden, use_cfr, netname):
+    """compute_strategy_recursive / _to_leaf + exploitability + eval_net (rela/pybind.cc:45-84, recursive_solving.cc:46-134,
+    stats.cc:44-153) in the C port against the fixture from the compiled reference: strategies bit-identical when the net's output
+    layer is zero, all four numbers within 1e-6 relative (eval_net sums float32 terms in std::sort order; the port's scalar fp32
+    net differs from ATen by ~1e-7)."""
+    from oracle.make_golden import eval_weights
+    g = golden("net_evaluation.npz")
+    D, F, iters = 1, 4, 32
+    tag = f"{'cfr' if use_cfr else 'fp'}_{netname}_{D}x{F}"
+    r = port.net_evaluation(D, F, eval_weights(D, F, netname), num_iters=iters, use_cfr=use_cfr)
+    want = g[f"values_{tag}"]
+    assert np.all(np.abs(r["values"] - want) <= 1e-6 * np.abs(want)), (r["values"], want)
+    if netname == "zero_out":
+        assert np.array_equal(r["strategy_recursive"], g[f"strategy_recursive_{tag}"])
+        assert np.array_equal(r["strategy_to_leaf"], g[f"strategy_to_leaf_{tag}"])
+
+
 @pytest.mark.skipif(not available("ref_nofma"), reason="oracle/_ref not built (needs /root/reference)")
 def test_recursive_eval_golden_reproducible_live(golden):
     """The recursive-evaluation fixture (BASELINE config 5 path) is what the compiled reference produces here: its own
