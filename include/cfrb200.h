@@ -201,6 +201,48 @@ int64_t cfrb_wave_leaf_rows(const cfrb_handle* h);
  * the launching stream; valid after cfrb_sync). */
 int cfrb_last_run_ms(cfrb_handle* h, float* total_ms, float* net_ms);
 
+/* ---- Device-resident self-play: RlRunner::step (recursive_solving.cc:160-275) for n_games games in lock-step, without host
+ * round trips.  Replaces, per wave, RlRunner's act_iteration draw (:168-169), sample_state_to_leaf / sample_state_single
+ * (:192-275), normalize_beliefs_inplace (:41-44) and CFR::update_value_network (subgame_solving.cc:672-676).  Game g owns a
+ * std::mt19937 seeded with seeds[g] on the device and consumes it in the reference's draw order, so it replays
+ * RlRunner(seed = seeds[g]) as long as the solver's strategies agree.  random_action_prob / sample_leaf are
+ * RecursiveSolvingParams' fields (recursive_solving.h:31-38). */
+int cfrb_selfplay_create(cfrb_handle* h, int32_t n_games, const uint32_t* seeds, float random_action_prob, int32_t sample_leaf);
+/* One step of the loop, enqueued asynchronously on `cuda_stream` (NULL = the handle's stream):
+ *   1. if a wave is pending: its 2 * n_games training examples are written to the DEVICE buffers dev_ex_q [2n][Q] /
+ *      dev_ex_v [2n][H] (both NULL = drop them) and every game samples its next public state (a finished game restarts);
+ *   2. if start_next != 0: act_iteration draws, subgame descriptors, CFR constructor and num_iters iterations of the next wave.
+ * Returns the number of example rows written (0 or 2 * n_games) or a negative error. */
+int cfrb_selfplay_wave(cfrb_handle* h, float* dev_ex_q, float* dev_ex_v, int32_t start_next, void* cuda_stream);
+/* Block until the examples written by the most recent cfrb_selfplay_wave are complete (the wave it started keeps running). */
+int cfrb_selfplay_wait_examples(cfrb_handle* h);
+/* Game states (public state and beliefs [n][2][H]) copied to the host; any pointer may be NULL.  Synchronises.  Returns n_games. */
+int cfrb_selfplay_state(cfrb_handle* h, int32_t* last_bid, int32_t* player, double* beliefs);
+/* Block until the work enqueued on `cuda_stream` (NULL = the handle's stream) has finished. */
+int cfrb_stream_wait(cfrb_handle* h, void* cuda_stream);
+
+/* ---- Device-resident example rows: storage of the replay buffer (rela/prioritized_replay.h:224-506 keeps one pair of host
+ * tensors per example; here the rows of the ring live in HBM as two [capacity][dim] fp32 matrices and never visit the host on
+ * their way from the generator kernels to the trainer's batch).  Bookkeeping (head, size, priorities, blocking) stays with the
+ * caller. */
+typedef struct cfrb_rows cfrb_rows;
+int cfrb_rows_create(int32_t device, int64_t capacity_rows, int32_t q_dim, int32_t v_dim, cfrb_rows** out);
+int cfrb_rows_destroy(cfrb_rows* r);
+int cfrb_rows_device(const cfrb_rows* r);
+/* Store n rows at ring position `slot` (wraps around).  kind 0: q / v are host pointers; kind 1: device pointers on CUDA
+ * device src_device (peer copy when that is another GPU).  Returns when the rows are in place. */
+int cfrb_rows_write(cfrb_rows* r, int64_t slot, int32_t n, const float* q, const float* v, int32_t kind, int32_t src_device);
+/* n rows starting at `slot` (wraps around) to host memory (save / extract). */
+int cfrb_rows_read(cfrb_rows* r, int64_t slot, int32_t n, float* q, float* v);
+/* Batch assembly (PrioritizedReplay::sample -> makeBatch, rela/types.cc:19-41): rows ids[0..n) gathered into out_q [n][q_dim] /
+ * out_v [n][v_dim] on out_device (CUDA ordinal, -1 = host memory).  On the ring's own device the gather kernel runs on
+ * `cuda_stream` (the consumer's stream). */
+int cfrb_rows_gather(cfrb_rows* r, const int32_t* ids, int32_t n, float* out_q, float* out_v, int32_t out_device, void* cuda_stream);
+/* Device scratch for the hand-over of one wave's examples from a generator handle to a row store. */
+int cfrb_dev_alloc(int32_t device, size_t bytes, void** out);
+int cfrb_dev_free(int32_t device, void* p);
+int cfrb_dev_to_host(int32_t device, void* dst, const void* src, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

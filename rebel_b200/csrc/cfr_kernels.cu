@@ -1,8 +1,11 @@
 // CFR wave kernels, compiled as their own translation unit with -fmad=false: without fused multiply-adds every fp64
 // operation is an individually rounded IEEE operation in the same order as the reference's scalar C++ (built without
 // contraction), which makes the CFRB_STATE_F64 path reproduce the reference bit for bit between value-net calls.
+#include <algorithm>
+
 #include "cfr_kernels.cuh"
 #include "br_kernel.cuh"
+#include "selfplay_kernels.cuh"
 
 namespace cfrb {
 
@@ -80,12 +83,41 @@ void cfr_launch_iter_d2(const CfrDev<real>& p, int blocks, int threads, size_t s
 #undef CFRB_CALL
 }
 
+void sp_launch_seed(const SpDev& p, const uint32_t* dev_seeds, cudaStream_t st) {
+  sp_seed_kernel<<<(p.K + 127) / 128, 128, 0, st>>>(p, dev_seeds);
+}
+template <typename real>
+void sp_launch_begin(const SpDev& p, real* wave_beliefs, cudaStream_t st) {
+  sp_begin_kernel<real><<<(p.K + 127) / 128, 128, 0, st>>>(p, wave_beliefs);
+  sp_scan_kernel<<<1, 1024, 0, st>>>(p);
+}
+template <typename real>
+void sp_launch_finish(const SpDev& p, const real* mu, const real* snap, float* ex_q, float* ex_v, cudaStream_t st) {
+  if (ex_q) sp_examples_kernel<real><<<(2 * p.K + 127) / 128, 128, 0, st>>>(p, mu, ex_q, ex_v);
+  sp_advance_kernel<real><<<(p.K + 127) / 128, 128, 0, st>>>(p, snap);
+}
+__global__ void rows_gather_kernel(const float* __restrict__ src, int width, const int* __restrict__ ids, int n, float* __restrict__ out) {
+  const size_t total = (size_t)n * width;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / width), c = (int)(i % width);
+    out[i] = src[(size_t)ids[r] * width + c];
+  }
+}
+void rows_launch_gather(const float* src, int width, const int* ids, int n, float* out, cudaStream_t st) {
+  if (n <= 0) return;
+  const size_t total = (size_t)n * width;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  rows_gather_kernel<<<blocks, 256, 0, st>>>(src, width, ids, n, out);
+}
+
 #define CFRB_INSTANTIATE(real)                                                                                             \
   template cudaError_t cfr_configure<real>(int, int);                                                                      \
   template void cfr_launch_init<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int);                      \
   template void cfr_launch_iter<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int, int, int, int);             \
   template cudaError_t cfr_configure_d2<real>(int);                                                                        \
-  template void cfr_launch_iter_d2<real>(const CfrDev<real>&, int, int, size_t, cudaStream_t, int, int, int, int);
+  template void cfr_launch_iter_d2<real>(const CfrDev<real>&, int, int, size_t, cudaStream_t, int, int, int, int);                \
+  template void sp_launch_begin<real>(const SpDev&, real*, cudaStream_t);                                                  \
+  template void sp_launch_finish<real>(const SpDev&, const real*, const real*, float*, float*, cudaStream_t);
 CFRB_INSTANTIATE(float)
 CFRB_INSTANTIATE(double)
 

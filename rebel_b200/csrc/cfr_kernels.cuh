@@ -923,6 +923,11 @@ __global__ void __launch_bounds__(512) cfr_init_kernel(CfrDev<real> p, int scrat
   const int* __restrict__ nchild = p.nchild + t.node_off;
   const real* __restrict__ b = p.beliefs + (size_t)k * 2 * H;
   const int rp = p.sg_player[k];
+  // act_iteration == 0: the sampling strategy RlRunner / the sampled recursive evaluation read is the INITIAL (uniform) one
+  // (recursive_solving.cc:168-174 runs zero steps before sampling), and cfrb_run(0) launches nothing — so the snapshot is
+  // taken here
+  real* __restrict__ Sn = p.Snap + (size_t)k * p.table_stride;
+  const bool snap0 = p.sg_act_iter[k] == 0;
   for (int h = lane; h < H; h += G) { reach0[h] = b[h]; reach1[h] = b[H + h]; }
   group_sync<G>();
   for (int d = 1; d < t.levels; ++d) {
@@ -934,6 +939,7 @@ __global__ void __launch_bounds__(512) cfr_init_kernel(CfrDev<real> p, int scrat
       const real u = (real)1 / nchild[par];
       const real a0 = reach0[par * H + h], a1 = reach1[par * H + h];
       Sg[e] = u;
+      if (snap0) Sn[e] = u;
       R[e] = p.fp ? u : (real)0;       // FP: last_strategies starts as the uniform strategy (subgame_solving.cc:375-377)
       S[e] = u * (actor == 0 ? a0 : a1);
       reach0[c * H + h] = actor == 0 ? a0 * u : a0;

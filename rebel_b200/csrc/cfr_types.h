@@ -63,6 +63,31 @@ struct BrDev {
 };
 void br_launch(const BrDev& p, cudaStream_t st);
 
+// Device-resident self-play (selfplay_kernels.cuh): per-game state of K games advanced in lock-step.
+constexpr int kSpMaxH = 64;       // per-thread belief copies live in local memory: larger games use the host walk
+constexpr int kSpMaxPath = 16;
+struct SpDev {
+  int K, A, H, Q, iters, sample_leaf;
+  float random_action_prob;
+  // per-game state
+  int* g_last_bid; int* g_player;     // [K]
+  double* g_beliefs;                  // [K][2][H]   (fp64 like RlRunner::beliefs_, whatever the table dtype)
+  uint32_t* mt; int* mt_idx;          // [624][K], [K]
+  // tree templates (read-only; the same arrays the CFR kernels index)
+  const TemplateDev* tmpl; const int* child_begin; const int* nchild; const int* last_bid;
+  // wave descriptors
+  int* wave;                          // [0] = number of subgames, [1] = value-net rows
+  int* sg_tmpl; int* sg_player; int* sg_row_off; int* sg_act;
+  int table_stride;
+};
+void sp_launch_seed(const SpDev& p, const uint32_t* dev_seeds, cudaStream_t st);
+// act_iteration draw + subgame descriptors + packed row offsets of the next wave
+template <typename real> void sp_launch_begin(const SpDev& p, real* wave_beliefs, cudaStream_t st);
+// training examples of the finished wave (skipped when ex_q == nullptr) and the sampling step of every game
+template <typename real> void sp_launch_finish(const SpDev& p, const real* mu, const real* snap, float* ex_q, float* ex_v, cudaStream_t st);
+// rows [ids[i]] of a [*, width] fp32 matrix -> out[i]  (replay sampling)
+void rows_launch_gather(const float* src, int width, const int* ids, int n, float* out, cudaStream_t st);
+
 // Launchers implemented in cfr_kernels.cu (explicitly instantiated for float and double).  `group` is 32 (one warp per
 // subgame, shared-memory scratch) or 256 (one CTA per subgame, global scratch).
 template <typename real> cudaError_t cfr_configure(int group, int smem_bytes);

@@ -125,6 +125,20 @@ struct cfrb_handle {
   std::vector<double> h_beliefs;
   int64_t launches = 0;
   float last_total_ms = 0.f, last_net_ms = 0.f;
+  // device-resident self-play (cfrb_selfplay_*): game states, generator streams
+  struct SelfPlay {
+    bool ready = false, pending = false;    // pending: a wave has been run whose games have not been advanced yet
+    int K = 0;
+    DevBuf<int> last_bid, player, mt_idx;
+    DevBuf<double> beliefs;
+    DevBuf<uint32_t> mt, seeds;
+    cfrb::SpDev dev{};
+    int64_t waves = 0;
+    cudaEvent_t ev_examples = nullptr;    // recorded behind the example / advance kernels of the last finished wave
+    bool ev_recorded = false;
+  } sp;
+  bool rows_on_device = false;   // the wave was built on the device: its row count / roots exist only there
+  bool mirror_stale = false;     // ... and the host mirror (h_tmpl, h_beliefs, rows) has not been pulled yet
 };
 
 template <typename real> static WaveState<real>& state_of(cfrb_handle* h);
@@ -388,6 +402,51 @@ static int scalers_t(cfrb_handle* h, double* out, int rows) {
   return CFRB_OK;
 }
 
+// A wave built on the device (cfrb_selfplay_wave) has no host mirror of its subgame descriptors; the inspection entry points
+// (fetch / examples / load_state / reset, used by tests and evaluators, not by the self-play loop) pull it on demand.
+template <typename real>
+static int pull_beliefs_t(cfrb_handle* h) {
+  auto& s = state_of<real>(h);
+  std::vector<real> tmp((size_t)h->n * 2 * h->g.H);
+  CK(cudaMemcpy(tmp.data(), s.beliefs.p, tmp.size() * sizeof(real), cudaMemcpyDeviceToHost));
+  h->h_beliefs.assign(tmp.begin(), tmp.end());
+  return CFRB_OK;
+}
+template <typename real>
+static int selfplay_finish_t(cfrb_handle* h, float* ex_q, float* ex_v, cudaStream_t st) {
+  auto& s = state_of<real>(h);
+  cfrb::sp_launch_finish<real>(h->sp.dev, s.mu.p, s.Snap.p, ex_q, ex_v, st);
+  h->launches += ex_q ? 2 : 1;
+  CK(cudaGetLastError());
+  return CFRB_OK;
+}
+template <typename real>
+static int selfplay_begin_t(cfrb_handle* h, cudaStream_t st) {
+  auto& s = state_of<real>(h);
+  cfrb::sp_launch_begin<real>(h->sp.dev, s.beliefs.p, st);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return CFRB_OK;
+}
+
+static int sync_mirror(cfrb_handle* h) {
+  if (!h->rows_on_device || !h->mirror_stale) return CFRB_OK;
+  CK(cudaDeviceSynchronize());
+  const int n = h->n;
+  int wave[2] = {0, 0};
+  CK(cudaMemcpy(wave, h->d_wave.p, sizeof(wave), cudaMemcpyDeviceToHost));
+  h->rows = wave[1];
+  h->h_tmpl.resize(n); h->h_player.resize(n); h->h_row_off.resize(n); h->h_last_bid.resize(n);
+  CK(cudaMemcpy(h->h_tmpl.data(), h->d_sg_tmpl.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h->h_player.data(), h->d_sg_player.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h->h_row_off.data(), h->d_sg_row_off.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < n; ++k) h->h_last_bid[k] = h->h_tmpl[k] - 1;
+  int rc = DISPATCH_REAL(h, pull_beliefs_t, h);
+  if (rc) return rc;
+  h->mirror_stale = false;
+  return CFRB_OK;
+}
+
 extern "C" {
 
 const char* cfrb_last_error(void) { return g_err.c_str(); }
@@ -409,6 +468,9 @@ int cfrb_destroy(cfrb_handle* h) {
   h->d_wave.release(); h->d_sg_tmpl.release(); h->d_sg_player.release(); h->d_sg_row_off.release(); h->d_sg_act.release();
   h->d_steps.release(); h->d_X.release(); h->d_out.release(); h->d_dbg.release(); h->d_Xh.release();
   h->sf.release(); h->sd.release(); h->d_w.release(); h->d_blob.release();
+  h->sp.last_bid.release(); h->sp.player.release(); h->sp.mt_idx.release(); h->sp.beliefs.release(); h->sp.mt.release();
+  h->sp.seeds.release();
+  if (h->sp.ev_examples) cudaEventDestroy(h->sp.ev_examples);
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   for (auto e : h->net_ev) cudaEventDestroy(e);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -667,7 +729,7 @@ int cfrb_begin_wave(cfrb_handle* h, int32_t n, const int32_t* last_bid, const in
     rows += h->tmpl[tm[k]].L;
     if (act_iteration) act[k] = act_iteration[k];
   }
-  h->n = n; h->rows = rows; h->iters_done = 0;
+  h->n = n; h->rows = rows; h->iters_done = 0; h->rows_on_device = false; h->sp.pending = false;
   h->h_tmpl = tm; h->h_player = pl; h->h_row_off = ro;
   h->h_last_bid.assign(last_bid, last_bid + n);
   h->h_beliefs.assign(beliefs, beliefs + (size_t)n * 2 * H);
@@ -696,7 +758,7 @@ static cudaError_t record_event(cfrb_handle* h, cudaEvent_t ev, cudaStream_t st)
 }
 
 static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2) {
-  if (h->cfg.net_mode == CFRB_NET_ZERO || h->rows == 0) return CFRB_OK;
+  if (h->cfg.net_mode == CFRB_NET_ZERO || (h->rows == 0 && !h->rows_on_device)) return CFRB_OK;
   const bool sample = h->profiling > 0 && (h->net_launch_idx % h->profiling) == 0;
   ++h->net_launch_idx;
   if (sample) {
@@ -711,7 +773,7 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
     const cfrb::tc::BlobLayout L(h->Qpad);
     cfrb::tc::TcArgs a{h->d_blob.p, h->d_Xh.p, h->d_wave.p + 1, h->d_out.p, h->Qpad, h->g.H, h->Hout, dbg1, dbg2, nullptr};
     const int tiles = (h->rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
-    const int grid = h->capturing ? h->num_sms : std::min(tiles, h->num_sms);   // surplus CTAs return at once
+    const int grid = (h->capturing || h->rows_on_device) ? h->num_sms : std::min(tiles, h->num_sms);   // surplus CTAs return at once
     const bool x2 = h->cfg.net_mode == CFRB_NET_TC_F16X2;
     a.trace = h->dbg_trace;
     if (dbg1 || dbg2 || a.trace) {
@@ -733,7 +795,9 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
       else CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<false, false>, a));
     }
   } else {
-    const int blocks = (h->rows + cfrb::kMlpRows - 1) / cfrb::kMlpRows;
+    // a wave built on the device: worst-case grid, CTAs beyond the device-side row count return at once
+    const int64_t rows_host = h->rows_on_device ? (int64_t)h->n * std::max(h->Lmax, 1) : h->rows;
+    const int blocks = (int)((rows_host + cfrb::kMlpRows - 1) / cfrb::kMlpRows);
     cfrb::leaf_mlp_fp32_kernel<256><<<blocks, 256, cfrb::leaf_mlp_fp32_smem(256), st>>>(h->net, h->d_X.p, h->d_wave.p + 1, h->d_out.p);
   }
   ++h->launches;
@@ -789,7 +853,7 @@ int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream) {
   static const bool no_graph = [] { const char* e = std::getenv("CFRB_NO_GRAPH"); return e && *e == '1'; }();
   const bool graphable = !no_graph && iters >= 64 && h->cfg.net_mode != CFRB_NET_FP32;
   if (graphable) {
-    const int has_rows = h->rows > 0;
+    const int has_rows = h->rows > 0 || h->rows_on_device;
     cfrb_handle::GraphEntry* g = nullptr;
     for (auto& e : h->graphs)
       if (e.first == first && e.count == iters && e.prof == h->profiling && e.has_rows == has_rows) { g = &e; break; }
@@ -863,6 +927,7 @@ int cfrb_fetch(cfrb_handle* h, double* root_value_means, double* snapshot_strate
   if (!h) return fail(CFRB_EINVAL, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
+  { int rc = sync_mirror(h); if (rc) return rc; }
   if (h->n == 0) return CFRB_OK;
   return DISPATCH_REAL(h, fetch_t, h, root_value_means, snapshot_strategy, last_strategy, avg_strategy, sum_strategy, regrets);
 }
@@ -873,6 +938,7 @@ int cfrb_fetch_compact(cfrb_handle* h, int32_t which, double* out) {
   if (!h || !out || which < 0 || which > 4) return fail(CFRB_EINVAL, "bad argument");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
+  { int rc = sync_mirror(h); if (rc) return rc; }
   if (h->n == 0) return CFRB_OK;
   return DISPATCH_REAL(h, fetch_compact_t, h, which, out);
 }
@@ -881,6 +947,7 @@ int cfrb_examples(cfrb_handle* h, float* queries, float* values) {
   if (!h || !queries || !values) return fail(CFRB_EINVAL, "null argument");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
+  { int rc = sync_mirror(h); if (rc) return rc; }
   const int n = h->n, H = h->g.H, A = h->g.A, Q = h->g.Q;
   if (n == 0) return CFRB_OK;
   int rc = DISPATCH_REAL(h, examples_values_t, h, values);
@@ -908,6 +975,7 @@ int cfrb_load_state(cfrb_handle* h, const double* regrets, const double* last_st
   if (!h) return fail(CFRB_EINVAL, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
+  { int rc = sync_mirror(h); if (rc) return rc; }
   int rc = DISPATCH_REAL(h, load_state_t, h, regrets, last_strategy, sum_strategy, root_value_means);
   if (rc) return rc;
   if (num_steps) CK(cudaMemcpy(h->d_steps.p, num_steps, (size_t)h->n * 2 * sizeof(int), cudaMemcpyHostToDevice));
@@ -919,6 +987,7 @@ int cfrb_debug_leaf_io(cfrb_handle* h, float* queries, float* net_out, double* s
   if (!h) return fail(CFRB_EINVAL, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
+  { int rc = sync_mirror(h); if (rc) return rc; }
   const int rows = std::min<int>(h->rows, cap_rows), Q = h->g.Q;
   if (rows > 0 && queries && is_tc(h->cfg.net_mode)) {
     const int tiles = (rows + cfrb::tc::kTileM - 1) / cfrb::tc::kTileM;
@@ -1050,6 +1119,269 @@ int cfrb_last_run_ms(cfrb_handle* h, float* total_ms, float* net_ms) {
   h->last_net_ms = net;
   if (total_ms) *total_ms = ms;
   if (net_ms) *net_ms = net;
+  return CFRB_OK;
+}
+
+// ============================================================================================ device-resident self-play
+int cfrb_selfplay_create(cfrb_handle* h, int32_t n_games, const uint32_t* seeds, float random_action_prob, int32_t sample_leaf) {
+  if (!h || !seeds) return fail(CFRB_EINVAL, "null argument");
+  if (n_games < 1 || n_games > h->cfg.max_subgames) return fail(CFRB_EINVAL, "n_games must be in [1, max_subgames]");
+  if (h->g.H > cfrb::kSpMaxH) return fail(CFRB_EINVAL, "device self-play supports num_hands <= 64");
+  if (h->cfg.max_depth > cfrb::kSpMaxPath) return fail(CFRB_EINVAL, "device self-play supports max_depth <= 16");
+  CK(cudaSetDevice(h->cfg.device));
+  auto& sp = h->sp;
+  const int K = n_games, H = h->g.H;
+  sp.last_bid.release(); sp.player.release(); sp.mt_idx.release(); sp.beliefs.release(); sp.mt.release(); sp.seeds.release();
+  CK(sp.last_bid.alloc(K)); CK(sp.player.alloc(K)); CK(sp.mt_idx.alloc(K)); CK(sp.beliefs.alloc((size_t)K * 2 * H));
+  CK(sp.mt.alloc((size_t)624 * K)); CK(sp.seeds.alloc(K));
+  cfrb::SpDev& d = sp.dev;
+  d.K = K; d.A = h->g.A; d.H = H; d.Q = h->g.Q; d.iters = h->cfg.num_iters; d.sample_leaf = sample_leaf;
+  d.random_action_prob = random_action_prob;
+  d.g_last_bid = sp.last_bid.p; d.g_player = sp.player.p; d.g_beliefs = sp.beliefs.p; d.mt = sp.mt.p; d.mt_idx = sp.mt_idx.p;
+  d.tmpl = h->d_tmpl.p; d.child_begin = h->d_child_begin.p; d.nchild = h->d_nchild.p; d.last_bid = h->d_last_bid.p;
+  d.wave = h->d_wave.p; d.sg_tmpl = h->d_sg_tmpl.p; d.sg_player = h->d_sg_player.p; d.sg_row_off = h->d_sg_row_off.p;
+  d.sg_act = h->d_sg_act.p; d.table_stride = h->table_stride;
+  CK(cudaStreamSynchronize(h->own_stream));
+  CK(cudaMemcpyAsync(sp.seeds.p, seeds, (size_t)K * sizeof(uint32_t), cudaMemcpyHostToDevice, h->own_stream));
+  cfrb::sp_launch_seed(d, sp.seeds.p, h->own_stream);
+  ++h->launches;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->own_stream));
+  if (!sp.ev_examples) CK(cudaEventCreateWithFlags(&sp.ev_examples, cudaEventDisableTiming));
+  sp.K = K; sp.ready = true; sp.pending = false; sp.waves = 0; sp.ev_recorded = false;
+  return CFRB_OK;
+}
+
+int cfrb_selfplay_wave(cfrb_handle* h, float* dev_ex_q, float* dev_ex_v, int32_t start_next, void* cuda_stream) {
+  if (!h) return fail(CFRB_EINVAL, "null handle");
+  if (!h->sp.ready) return fail(CFRB_ESTATE, "cfrb_selfplay_create has not been called");
+  if ((dev_ex_q == nullptr) != (dev_ex_v == nullptr)) return fail(CFRB_EINVAL, "example buffers: both or none");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  int rows_out = 0;
+  if (h->sp.pending) {
+    if (!h->rows_on_device || h->n != h->sp.K || h->iters_done != h->cfg.num_iters)
+      return fail(CFRB_ESTATE, "the pending self-play wave was replaced or not run to num_iters");
+    int rc = DISPATCH_REAL(h, selfplay_finish_t, h, dev_ex_q, dev_ex_v, st);
+    if (rc) return rc;
+    h->sp.pending = false;
+    rows_out = dev_ex_q ? 2 * h->sp.K : 0;
+    CK(cudaEventRecord(h->sp.ev_examples, st));
+    h->sp.ev_recorded = true;
+  }
+  if (start_next) {
+    int rc = DISPATCH_REAL(h, selfplay_begin_t, h, st);
+    if (rc) return rc;
+    h->n = h->sp.K; h->rows = 0; h->rows_on_device = true; h->mirror_stale = true; h->iters_done = 0;
+    rc = DISPATCH_REAL(h, launch_init_t, h, st);
+    if (rc) return rc;
+    rc = cfrb_run(h, h->cfg.num_iters, st);
+    if (rc) return rc;
+    h->sp.pending = true;
+    ++h->sp.waves;
+  }
+  return rows_out;
+}
+
+int cfrb_selfplay_wait_examples(cfrb_handle* h) {
+  if (!h || !h->sp.ready) return fail(CFRB_ESTATE, "no self-play session");
+  if (!h->sp.ev_recorded) return CFRB_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->sp.ev_examples));
+  return CFRB_OK;
+}
+
+int cfrb_selfplay_state(cfrb_handle* h, int32_t* last_bid, int32_t* player, double* beliefs) {
+  if (!h || !h->sp.ready) return fail(CFRB_ESTATE, "no self-play session");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  const int K = h->sp.K;
+  if (last_bid) CK(cudaMemcpy(last_bid, h->sp.last_bid.p, K * sizeof(int), cudaMemcpyDeviceToHost));
+  if (player) CK(cudaMemcpy(player, h->sp.player.p, K * sizeof(int), cudaMemcpyDeviceToHost));
+  if (beliefs) CK(cudaMemcpy(beliefs, h->sp.beliefs.p, (size_t)K * 2 * h->g.H * sizeof(double), cudaMemcpyDeviceToHost));
+  return K;
+}
+
+int cfrb_stream_wait(cfrb_handle* h, void* cuda_stream) {
+  if (!h) return fail(CFRB_EINVAL, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream));
+  return CFRB_OK;
+}
+
+// ============================================================================================ device-resident example rows
+struct cfrb_rows {
+  int device = 0, q_dim = 0, v_dim = 0;
+  int64_t cap = 0;
+  float* q = nullptr; float* v = nullptr;
+  // id staging for gathers (a small ring: a gather on the consumer's stream is not waited for, its staging slot is reused only
+  // after its completion event) and the staging area for batches that leave the device
+  struct IdSlot { int* dev = nullptr; int* pin = nullptr; int cap = 0; cudaEvent_t done = nullptr; bool used = false; };
+  IdSlot ids[4];
+  int next_id = 0;
+  float* stage_q = nullptr; float* stage_v = nullptr; int64_t stage_rows = 0;
+  cudaStream_t st = nullptr;
+};
+
+int cfrb_rows_destroy(cfrb_rows* r) {
+  if (!r) return CFRB_OK;
+  cudaSetDevice(r->device);
+  cudaDeviceSynchronize();
+  if (r->st) cudaStreamDestroy(r->st);
+  if (r->q) cudaFree(r->q);
+  if (r->v) cudaFree(r->v);
+  for (auto& s : r->ids) {
+    if (s.dev) cudaFree(s.dev);
+    if (s.pin) cudaFreeHost(s.pin);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (r->stage_q) cudaFree(r->stage_q);
+  if (r->stage_v) cudaFree(r->stage_v);
+  delete r;
+  return CFRB_OK;
+}
+
+int cfrb_rows_create(int32_t device, int64_t capacity_rows, int32_t q_dim, int32_t v_dim, cfrb_rows** out) {
+  if (!out || capacity_rows < 1 || q_dim < 1 || v_dim < 1) return fail(CFRB_EINVAL, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(CFRB_ENODEV, "no CUDA device"); }
+  if (device < 0 || device >= ndev) return fail(CFRB_EINVAL, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  auto* r = new cfrb_rows();
+  r->device = device; r->q_dim = q_dim; r->v_dim = v_dim; r->cap = capacity_rows;
+  cudaError_t e = cudaMalloc((void**)&r->q, (size_t)capacity_rows * q_dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&r->v, (size_t)capacity_rows * v_dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->st, cudaStreamNonBlocking);
+  for (auto& s : r->ids)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    cfrb_rows_destroy(r);
+    return fail(CFRB_ENOMEM, std::string("cfrb_rows_create: ") + cudaGetErrorString(e));
+  }
+  *out = r;
+  return CFRB_OK;
+}
+
+int cfrb_rows_device(const cfrb_rows* r) { return r ? r->device : -1; }
+
+// kind: 0 = host source, 1 = device source on `src_device` (peer copy when that is another GPU).  Ring wrap-around handled
+// here.  Ordered after every gather still in flight on a consumer's stream (it may read the slots being replaced); blocks until
+// the rows are in place (the caller publishes them right after).
+int cfrb_rows_write(cfrb_rows* r, int64_t slot, int32_t n, const float* q, const float* v, int32_t kind, int32_t src_device) {
+  if (!r || !q || !v || n < 0 || slot < 0 || slot >= r->cap || n > r->cap) return fail(CFRB_EINVAL, "cfrb_rows_write: bad argument");
+  CK(cudaSetDevice(r->device));
+  for (auto& s : r->ids)
+    if (s.used) CK(cudaStreamWaitEvent(r->st, s.done, 0));
+  auto put = [&](float* dst_base, const float* src, int dim) -> cudaError_t {
+    const int64_t first = std::min<int64_t>(n, r->cap - slot);
+    for (int part = 0; part < 2; ++part) {
+      const int64_t cnt = part == 0 ? first : n - first;
+      if (cnt <= 0) continue;
+      float* dst = dst_base + (size_t)(part == 0 ? slot : 0) * dim;
+      const float* s2 = src + (size_t)(part == 0 ? 0 : first) * dim;
+      const size_t bytes = (size_t)cnt * dim * sizeof(float);
+      cudaError_t e;
+      if (kind == 0) e = cudaMemcpyAsync(dst, s2, bytes, cudaMemcpyHostToDevice, r->st);
+      else if (src_device == r->device) e = cudaMemcpyAsync(dst, s2, bytes, cudaMemcpyDeviceToDevice, r->st);
+      else e = cudaMemcpyPeerAsync(dst, r->device, s2, src_device, bytes, r->st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  CK(put(r->q, q, r->q_dim));
+  CK(put(r->v, v, r->v_dim));
+  CK(cudaStreamSynchronize(r->st));
+  return CFRB_OK;
+}
+
+int cfrb_rows_read(cfrb_rows* r, int64_t slot, int32_t n, float* q, float* v) {
+  if (!r || !q || !v || n < 0 || slot < 0 || slot >= r->cap || n > r->cap) return fail(CFRB_EINVAL, "cfrb_rows_read: bad argument");
+  CK(cudaSetDevice(r->device));
+  const int64_t first = std::min<int64_t>(n, r->cap - slot);
+  CK(cudaMemcpy(q, r->q + (size_t)slot * r->q_dim, (size_t)first * r->q_dim * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(v, r->v + (size_t)slot * r->v_dim, (size_t)first * r->v_dim * sizeof(float), cudaMemcpyDeviceToHost));
+  if (n > first) {
+    CK(cudaMemcpy(q + (size_t)first * r->q_dim, r->q, (size_t)(n - first) * r->q_dim * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v + (size_t)first * r->v_dim, r->v, (size_t)(n - first) * r->v_dim * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return CFRB_OK;
+}
+
+// Rows ids[0..n) -> out_q [n][q_dim], out_v [n][v_dim].  out_device: -1 = host memory, otherwise the CUDA ordinal the output
+// buffers live on.  When the output is on the ring's device and a stream is given, the id upload and the two gather kernels are
+// enqueued on THAT stream (the consumer's: the batch is ordered like any other work of the trainer) and the call returns
+// without waiting; otherwise the batch is staged on the ring's device, copied out and the call waits for it.
+int cfrb_rows_gather(cfrb_rows* r, const int32_t* ids, int32_t n, float* out_q, float* out_v, int32_t out_device, void* cuda_stream) {
+  if (!r || !ids || !out_q || !out_v || n < 0) return fail(CFRB_EINVAL, "cfrb_rows_gather: bad argument");
+  if (n == 0) return CFRB_OK;
+  CK(cudaSetDevice(r->device));
+  auto& sl = r->ids[r->next_id];
+  r->next_id = (r->next_id + 1) % 4;
+  if (sl.used) CK(cudaEventSynchronize(sl.done));
+  if (n > sl.cap) {
+    if (sl.dev) cudaFree(sl.dev);
+    if (sl.pin) cudaFreeHost(sl.pin);
+    sl.dev = nullptr; sl.pin = nullptr; sl.cap = 0;
+    CK(cudaMalloc((void**)&sl.dev, (size_t)n * sizeof(int)));
+    CK(cudaMallocHost((void**)&sl.pin, (size_t)n * sizeof(int)));
+    sl.cap = n;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (ids[i] < 0 || ids[i] >= r->cap) return fail(CFRB_EINVAL, "cfrb_rows_gather: row id out of range");
+    sl.pin[i] = ids[i];
+  }
+  const bool same = out_device == r->device;
+  const bool direct = same && cuda_stream != nullptr;
+  cudaStream_t st = direct ? (cudaStream_t)cuda_stream : r->st;
+  CK(cudaMemcpyAsync(sl.dev, sl.pin, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  float* tq = out_q; float* tv = out_v;
+  if (!same) {
+    if (n > r->stage_rows) {
+      CK(cudaStreamSynchronize(r->st));
+      if (r->stage_q) cudaFree(r->stage_q);
+      if (r->stage_v) cudaFree(r->stage_v);
+      r->stage_q = r->stage_v = nullptr; r->stage_rows = 0;
+      CK(cudaMalloc((void**)&r->stage_q, (size_t)n * r->q_dim * sizeof(float)));
+      CK(cudaMalloc((void**)&r->stage_v, (size_t)n * r->v_dim * sizeof(float)));
+      r->stage_rows = n;
+    }
+    tq = r->stage_q; tv = r->stage_v;
+  }
+  cfrb::rows_launch_gather(r->q, r->q_dim, sl.dev, n, tq, st);
+  cfrb::rows_launch_gather(r->v, r->v_dim, sl.dev, n, tv, st);
+  CK(cudaGetLastError());
+  if (!same) {
+    const size_t bq = (size_t)n * r->q_dim * sizeof(float), bv = (size_t)n * r->v_dim * sizeof(float);
+    if (out_device < 0) {
+      CK(cudaMemcpyAsync(out_q, tq, bq, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(out_v, tv, bv, cudaMemcpyDeviceToHost, st));
+    } else {
+      CK(cudaMemcpyPeerAsync(out_q, out_device, tq, r->device, bq, st));
+      CK(cudaMemcpyPeerAsync(out_v, out_device, tv, r->device, bv, st));
+    }
+  }
+  CK(cudaEventRecord(sl.done, st));
+  sl.used = true;
+  if (!direct) CK(cudaStreamSynchronize(st));
+  return CFRB_OK;
+}
+
+// Scratch device buffers for hand-over between a generator handle and a row store (examples of one wave).
+int cfrb_dev_alloc(int32_t device, size_t bytes, void** out) {
+  if (!out) return fail(CFRB_EINVAL, "null argument");
+  CK(cudaSetDevice(device));
+  CK(cudaMalloc(out, std::max<size_t>(bytes, 1)));
+  return CFRB_OK;
+}
+int cfrb_dev_free(int32_t device, void* p) {
+  if (!p) return CFRB_OK;
+  CK(cudaSetDevice(device));
+  CK(cudaFree(p));
+  return CFRB_OK;
+}
+int cfrb_dev_to_host(int32_t device, void* dst, const void* src, size_t bytes) {
+  CK(cudaSetDevice(device));
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
   return CFRB_OK;
 }
 

@@ -1,16 +1,26 @@
 // BatchedRlRunner: self-play of K Liar's Dice games in lock-step on one GPU — the B200 counterpart of the reference's
 // RlRunner (recursive_solving.h:40-86, recursive_solving.cc:160-275), which plays ONE game per CPU thread.
 //
-// A "wave" solves the current subgame of every game at once through the C ABI (include/cfrb200.h): cfrb_begin_wave ->
-// cfrb_run(num_iters) -> snapshot of the sampling strategy at each game's act_iteration + training examples.  Everything
-// the reference does per game on the host stays per game on the host, with the reference's own random-number draw order
-// and fp64 belief arithmetic, so that game 0 of a runner seeded with s replays RlRunner(seed = s) exactly as long as the
-// solver's strategies agree:
+// A "wave" solves the current subgame of every game at once through the C ABI (include/cfrb200.h).  Two drivers:
+//
+//   * DEVICE walk (default): cfrb_selfplay_wave — the act_iteration draws, the sampling of the next public state, the belief
+//     updates and the training examples are all produced by kernels (csrc/selfplay_kernels.cuh), every game owning a
+//     std::mt19937 stream in device memory.  The loop is a software pipeline: wave w+1 is enqueued (one CUDA-graph launch)
+//     BEFORE the host waits for the examples of wave w, which it hands to the sink as DEVICE pointers (the replay appends
+//     them with one device-to-device copy).  The host never sees a strategy, a belief or an example.
+//   * HOST walk (cfg.host_walk, parity mode): cfrb_begin_wave -> cfrb_run -> cfrb_fetch_compact, and the reference's
+//     per-game code on the host with std::mt19937 itself.  Kept as the executable specification of the device walk: the tests
+//     require both drivers to emit bit-identical example streams.
+//
+// Either way everything follows the reference's random-number draw order and fp64 belief arithmetic:
 //   act_iteration ~ U{0..num_iters}                                   recursive_solving.cc:168-169
 //   sample_state_to_leaf / sample_state_single                        :192-246 / :248-275
 //       br_sampler ~ U{0,1}; per node eps ~ U[0,1) (float); random action or hand ~ beliefs, action ~ policy[hand]
 //   belief update + eps-normalisation                                 :41-44, :235-245
 //   two training examples per solved subgame                          subgame_solving.cc:672-676
+// Game g of a runner seeded with s uses the generator seed s + 1 000 000 g (cfvpy/selfplay.py:250 seeds its loops with
+// rank * 1000 + i, so these never collide with another loop's games), and replays the reference's RlRunner(seed = s + 10^6 g)
+// exactly as long as the solver's strategies agree.
 #pragma once
 #include <cstdint>
 #include <functional>
@@ -26,37 +36,57 @@
 
 namespace rela {
 
-// Receives blocks of examples: q [n][Q], v [n][H].  Returns false to stop the runner (e.g. replay closed).
+// Receives blocks of examples: q [n][Q], v [n][H] in HOST memory.  Returns false to stop the runner.
 using ExampleSink = std::function<bool(const float* q, int q_dim, const float* v, int v_dim, int n)>;
+// The same with DEVICE pointers on CUDA device `device` (valid until the next call of stepDevice returns).
+using DeviceExampleSink = std::function<bool(const float* dev_q, int q_dim, const float* dev_v, int v_dim, int n, int device)>;
+
+inline uint32_t game_seed(int loop_seed, int g) { return (uint32_t)loop_seed + 1000000u * (uint32_t)g; }
 
 class BatchedRlRunner {
  public:
   BatchedRlRunner(const liars_dice::RecursiveSolvingParams& cfg, int device, int seed)
-      : cfg_(cfg), K_(std::max(1, cfg.concurrent_games)) {
+      : cfg_(cfg), K_(std::max(1, cfg.concurrent_games)), device_(device) {
     const auto& sp = cfg.subgame_params;
     cfrb_config c{};
     c.solver = sp.use_cfr ? CFRB_SOLVER_CFR : CFRB_SOLVER_FP;   // build_solver (subgame_solving.cc:791-800)
     c.optimistic = sp.optimistic;
     c.num_dice = cfg.num_dice; c.num_faces = cfg.num_faces; c.max_depth = sp.max_depth; c.num_iters = sp.num_iters;
     c.linear_update = sp.linear_update; c.dcfr = sp.dcfr; c.dcfr_alpha = sp.dcfr_alpha; c.dcfr_beta = sp.dcfr_beta;
-    c.dcfr_gamma = sp.dcfr_gamma; c.max_subgames = K_; c.device = device; c.net_mode = cfg.net_mode; c.hidden = 256;
+    c.dcfr_gamma = sp.dcfr_gamma; c.max_subgames = K_; c.device = device; c.net_mode = liars_dice::effective_net_mode(cfg); c.hidden = 256;
     c.state_dtype = cfg.state_dtype;
     check(cfrb_create(&c, &h_), "cfrb_create");
     A_ = cfrb_num_actions(h_); H_ = cfrb_num_hands(h_); Q_ = cfrb_query_size(h_);
     stride_ = cfrb_table_stride(h_);
     trees_.resize(A_);   // root bids -1 .. A-2
     for (int b = -1; b <= A_ - 2; ++b) tree(b);   // built up front: the per-game walk runs on several threads and only reads them
-    games_.resize(K_);
-    for (int g = 0; g < K_; ++g) {
-      // game 0 carries the caller's seed verbatim (parity with RlRunner(seed)); the others get decorrelated streams
-      games_[g].gen.seed(g == 0 ? (uint32_t)seed : (uint32_t)(seed * 1000003u + 7919u * (uint32_t)g));
-      resetGame(games_[g]);
-    }
-    last_bid_.resize(K_); player_.resize(K_); act_.resize(K_);
-    beliefs_.resize((size_t)K_ * 2 * H_); snap_.resize((size_t)K_ * stride_);
+    host_walk_ = cfg.host_walk != 0;
     ex_q_.resize((size_t)K_ * 2 * Q_); ex_v_.resize((size_t)K_ * 2 * H_);
+    if (host_walk_) {
+      games_.resize(K_);
+      for (int g = 0; g < K_; ++g) {
+        games_[g].gen.seed(game_seed(seed, g));
+        resetGame(games_[g]);
+      }
+      last_bid_.resize(K_); player_.resize(K_); act_.resize(K_);
+      beliefs_.resize((size_t)K_ * 2 * H_); snap_.resize((size_t)K_ * stride_);
+    } else {
+      std::vector<uint32_t> seeds(K_);
+      for (int g = 0; g < K_; ++g) seeds[g] = game_seed(seed, g);
+      check(cfrb_selfplay_create(h_, K_, seeds.data(), cfg.random_action_prob, cfg.sample_leaf ? 1 : 0), "cfrb_selfplay_create");
+      for (int b = 0; b < 2; ++b) {   // double-buffered example hand-over
+        check(cfrb_dev_alloc(device_, (size_t)K_ * 2 * Q_ * sizeof(float), (void**)&dev_q_[b]), "cfrb_dev_alloc");
+        check(cfrb_dev_alloc(device_, (size_t)K_ * 2 * H_ * sizeof(float), (void**)&dev_v_[b]), "cfrb_dev_alloc");
+      }
+    }
   }
-  ~BatchedRlRunner() { if (h_) cfrb_destroy(h_); }
+  ~BatchedRlRunner() {
+    if (h_) {
+      cfrb_sync(h_);
+      for (int b = 0; b < 2; ++b) { cfrb_dev_free(device_, dev_q_[b]); cfrb_dev_free(device_, dev_v_[b]); }
+      cfrb_destroy(h_);
+    }
+  }
   BatchedRlRunner(const BatchedRlRunner&) = delete;
   BatchedRlRunner& operator=(const BatchedRlRunner&) = delete;
 
@@ -65,10 +95,49 @@ class BatchedRlRunner {
   }
   uint64_t weightsVersion() const { return cfrb_weights_version(h_); }
   int games() const { return K_; }
+  int device() const { return device_; }
+  bool hostWalk() const { return host_walk_; }
   int64_t subgamesSolved() const { return subgames_solved_; }
+  cfrb_handle* handle() const { return h_; }
 
-  // One wave: solve the current subgame of every game, emit 2 examples per subgame, advance every game.
+  // One wave through the device pipeline: hands the examples of one finished wave to `sink` as device pointers while the next
+  // wave is already running.  (Weights installed with setWeights take effect for the wave enqueued by the NEXT call.)
+  bool stepDevice(const DeviceExampleSink& sink) {
+    if (host_walk_) throw std::runtime_error("BatchedRlRunner::stepDevice needs the device walk");
+    if (!started_) {       // prime the pipeline: wave 0
+      check(cfrb_selfplay_wave(h_, nullptr, nullptr, 1, nullptr), "cfrb_selfplay_wave");
+      started_ = true;
+    }
+    const int b = buf_ ^= 1;
+    // finish the pending wave (examples -> dev_*_[b], games advance) and start the next one, all asynchronous
+    const int rows = cfrb_selfplay_wave(h_, dev_q_[b], dev_v_[b], 1, nullptr);
+    check(rows, "cfrb_selfplay_wave");
+    check(cfrb_selfplay_wait_examples(h_), "cfrb_selfplay_wait_examples");
+    subgames_solved_ += K_;
+    return sink(dev_q_[b], Q_, dev_v_[b], H_, rows, device_);
+  }
+  // Drain: finish the wave in flight without starting another (its examples are delivered; used at shutdown / by tests).
+  bool finishDevice(const DeviceExampleSink& sink) {
+    if (host_walk_ || !started_) return true;
+    const int b = buf_ ^= 1;
+    const int rows = cfrb_selfplay_wave(h_, dev_q_[b], dev_v_[b], 0, nullptr);
+    check(rows, "cfrb_selfplay_wave");
+    check(cfrb_selfplay_wait_examples(h_), "cfrb_selfplay_wait_examples");
+    started_ = false;
+    if (rows == 0) return true;
+    subgames_solved_ += K_;
+    return sink(dev_q_[b], Q_, dev_v_[b], H_, rows, device_);
+  }
+
+  // One wave, examples delivered in host memory.  Device walk: a synchronous wrapper around the pipeline (tests, tools).
   bool step(const ExampleSink& sink) {
+    if (!host_walk_) {
+      return stepDevice([&](const float* dq, int qd, const float* dv, int vd, int n, int dev) {
+        check(cfrb_dev_to_host(dev, ex_q_.data(), dq, (size_t)n * qd * sizeof(float)), "cfrb_dev_to_host");
+        check(cfrb_dev_to_host(dev, ex_v_.data(), dv, (size_t)n * vd * sizeof(float)), "cfrb_dev_to_host");
+        return sink(ex_q_.data(), qd, ex_v_.data(), vd, n);
+      });
+    }
     const int iters = cfg_.subgame_params.num_iters;
     for (int g = 0; g < K_; ++g) {
       Game& G = games_[g];
@@ -203,6 +272,11 @@ class BatchedRlRunner {
 
   const liars_dice::RecursiveSolvingParams cfg_;
   const int K_;
+  const int device_;
+  bool host_walk_ = false, started_ = false;
+  int buf_ = 0;
+  float* dev_q_[2] = {nullptr, nullptr};
+  float* dev_v_[2] = {nullptr, nullptr};
   cfrb_handle* h_ = nullptr;
   int A_ = 0, H_ = 0, Q_ = 0, stride_ = 0;
   std::vector<std::vector<cfrb_node>> trees_;

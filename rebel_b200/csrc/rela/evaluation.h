@@ -27,6 +27,17 @@ inline std::vector<float> flat_weights_of(torch::jit::Module& m) {
   static const char* kOrder[] = {"body.0.weight", "body.0.bias", "body.1.weight", "body.1.bias", "body.4.weight",
                                  "body.4.bias",   "body.5.weight", "body.5.bias", "output.weight", "output.bias"};
   std::vector<float> flat;
+  // only Net2(n_hidden=256, n_layers=2, use_layer_norm=True) is accelerated: any further parameter (a deeper body) is an error,
+  // not something to drop silently
+  for (const auto& p : m.named_parameters()) {
+    bool known = false;
+    for (const char* name : kOrder) known |= p.name == name;
+    if (!known)
+      throw std::runtime_error("value net has an unexpected parameter '" + p.name +
+                               "': rebel_b200 accelerates Net2(n_hidden=256, n_layers=2, use_layer_norm=True) only");
+    if (p.name == "body.0.weight" && (p.value.dim() != 2 || p.value.size(0) != 256))
+      throw std::runtime_error("value net: n_hidden must be 256");
+  }
   for (const char* name : kOrder) {
     bool found = false;
     for (const auto& p : m.named_parameters()) {

@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -26,6 +27,13 @@ class ModelLocker {
   ModelLocker(std::vector<py::object> py_models, const std::string& device) : device(device), py_models_(std::move(py_models)) {
     if (py_models_.empty()) throw std::runtime_error("ModelLocker: need at least one model");
     snapshot(py_models_[0]);
+    if (this->device.rfind("cuda", 0) != 0 && !std::getenv("CFRB_ACTOR_DEVICE")) {
+      // "cpu" lockers (selfplay.cpu_gen_threads) generate on a GPU: the slot is fixed here, once, on the constructing thread
+      static std::atomic<int> next{0};
+      cpu_slot_ = next++;
+      std::fprintf(stderr, "[rebel_b200] ModelLocker(device=\"%s\"): no CPU generation path; this locker generates on a GPU\n",
+                   this->device.c_str());
+    }
   }
 
   // Called on the Python thread (GIL held), like the reference (model_locker.h:69-79).
@@ -50,12 +58,7 @@ class ModelLocker {
       return pos == std::string::npos ? 0 : std::stoi(device.substr(pos + 1));
     }
     if (const char* e = std::getenv("CFRB_ACTOR_DEVICE")) return std::atoi(e);
-    static std::atomic<int> next{0};
-    if (cpu_slot_ < 0) {
-      cpu_slot_ = next++;
-      std::fprintf(stderr, "[rebel_b200] ModelLocker(device=\"%s\"): no CPU generation path; this locker generates on a GPU\n", device.c_str());
-    }
-    return cpu_slot_;   // taken modulo the device count by the loop
+    return cpu_slot_ < 0 ? 0 : cpu_slot_;   // taken modulo the device count by the loop
   }
 
   const std::string device;
@@ -66,11 +69,26 @@ class ModelLocker {
                                    "body.5.weight", "body.5.bias", "output.weight", "output.bias"};
     py::dict sd = model.attr("state_dict")();
     auto flat = std::make_shared<std::vector<float>>();
+    // The accelerated net is Net2(n_hidden=256, n_layers=2, use_layer_norm=True) and nothing else: a deeper Net2 (the
+    // reference's own default is n_layers=3) also has these ten keys, so every OTHER parameter is rejected instead of being
+    // dropped silently (the kernels would evaluate a truncated network), and the hidden width is checked explicitly.
+    for (auto item : sd) {
+      const std::string key = py::str(item.first);
+      bool known = false;
+      for (const char* k : kOrder) known |= key == k;
+      if (!known)
+        throw std::runtime_error("ModelLocker: unexpected parameter '" + key +
+                                 "': rebel_b200 accelerates Net2(n_hidden=256, n_layers=2, use_layer_norm=True) only");
+    }
     for (const char* key : kOrder) {
       if (!sd.contains(key))
         throw std::runtime_error(std::string("ModelLocker: state_dict has no '") + key +
-                                 "' (rebel_b200 accelerates Net2 with n_layers=2 and use_layer_norm=True)");
+                                 "' (rebel_b200 accelerates Net2 with n_hidden=256, n_layers=2 and use_layer_norm=True)");
       torch::Tensor t = sd[key].cast<torch::Tensor>().detach().to(torch::kCPU, torch::kFloat32).contiguous();
+      if (std::string(key) == "body.0.weight" && (t.dim() != 2 || t.size(0) != 256))
+        throw std::runtime_error("ModelLocker: n_hidden must be 256 (got " + std::to_string(t.dim() == 2 ? (long)t.size(0) : -1L) + ")");
+      if (std::string(key) == "body.4.weight" && (t.dim() != 2 || t.size(0) != 256 || t.size(1) != 256))
+        throw std::runtime_error("ModelLocker: body.4.weight must be [256, 256] (n_hidden=256)");
       const float* p = t.data_ptr<float>();
       flat->insert(flat->end(), p, p + t.numel());
     }
@@ -85,7 +103,7 @@ class ModelLocker {
   mutable std::mutex m_;
   std::shared_ptr<const std::vector<float>> weights_;
   std::atomic<uint64_t> version_{0};
-  mutable int cpu_slot_ = -1;
+  int cpu_slot_ = -1;
 };
 
 }  // namespace rela

@@ -12,7 +12,7 @@ struct SubgameSolvingParams {
   int num_iters = 10;
   int max_depth = 2;
   bool linear_update = false;
-  bool use_cfr = false;   // the reference's other solver (fictitious play) is not on the accelerated path
+  bool use_cfr = false;   // false = fictitious play (the YAML default), true = CFR; both run on the GPU
   bool optimistic = false;
   bool dcfr = false;
   double dcfr_alpha = 0;
@@ -35,6 +35,14 @@ struct RecursiveSolvingParams {
   int concurrent_games = env_int("CFRB_CONCURRENT_GAMES", 1024);   // self-play games advanced in lock-step per thread loop
   int net_mode = env_int("CFRB_NET_MODE", 3);                      // include/cfrb200.h CFRB_NET_*: 3 = tcgen05 fp16, packed-half GELU
   int state_dtype = env_int("CFRB_STATE_DTYPE", 0);                // CFRB_STATE_*: 0 = fp64 tables
+  int host_walk = env_int("CFRB_HOST_WALK", 0);                    // 1 = per-game sampling on the host (parity mode of the device walk)
 };
+
+// The tensor-core value net packs at most 16 output features (num_hands <= 16); larger games run the fp32 SIMT net.
+inline int effective_net_mode(const RecursiveSolvingParams& p) {
+  long hands = 1;
+  for (int i = 0; i < p.num_dice; ++i) hands *= p.num_faces;
+  return (p.net_mode >= 2 && hands > 16) ? 1 : p.net_mode;
+}
 
 }  // namespace liars_dice

@@ -29,11 +29,17 @@ class DataThreadLoop : public ThreadLoop {
  public:
   DataThreadLoop(std::shared_ptr<ModelLocker> locker, std::shared_ptr<ValuePrioritizedReplay> replay,
                  const RecursiveSolvingParams& cfg, int seed)
-      : locker_(std::move(locker)), replay_(std::move(replay)), cfg_(cfg), seed_(seed) {}
+      : locker_(std::move(locker)), replay_(std::move(replay)), cfg_(cfg), seed_(seed) {
+    // configuration errors surface here, on the Python thread that builds the loop, not inside the worker
+    if (cfg_.num_dice < 1 || cfg_.num_faces < 1) throw std::runtime_error("create_cfr_thread: num_dice / num_faces not set");
+    if (cfg_.subgame_params.max_depth < 1 || cfg_.subgame_params.num_iters < 1)
+      throw std::runtime_error("create_cfr_thread: subgame_params.max_depth and num_iters must be >= 1");
+    if (cfg_.concurrent_games < 1) throw std::runtime_error("create_cfr_thread: concurrent_games must be >= 1");
+  }
 
   void terminate() override {
     ThreadLoop::terminate();
-    replay_->close();   // a producer blocked on a full buffer must wake up
+    replay_->wake();   // a producer blocked on a full buffer re-checks terminated(); the buffer stays open for everyone else
   }
 
   void mainLoop() final {
@@ -41,24 +47,34 @@ class DataThreadLoop : public ThreadLoop {
     if (ndev <= 0) throw std::runtime_error("rebel_b200: no CUDA device (there is no CPU generation path)");
     BatchedRlRunner runner(cfg_, locker_->cudaOrdinal() % ndev, seed_);
     uint64_t have = 0;
-    auto sink = [this](const float* q, int qd, const float* v, int vd, int n) { return replay_->addRows(q, qd, v, vd, n, nullptr); };
+    const std::function<bool()> cancelled = [this] { return terminated(); };
+    auto host_sink = [&](const float* q, int qd, const float* v, int vd, int n) { return replay_->addRows(q, qd, v, vd, n, nullptr, cancelled); };
+    auto dev_sink = [&](const float* q, int qd, const float* v, int vd, int n, int dev) {
+      return replay_->addRowsDevice(q, qd, v, vd, n, dev, cancelled);
+    };
     while (!terminated()) {
       if (paused()) waitUntilResume();
       if (terminated()) break;
       const uint64_t ver = locker_->version();
-      if (ver != have) {   // ModelLocker::updateModel happened: install the new weights before the next wave
+      if (ver != have) {   // ModelLocker::updateModel happened: install the new weights before the next wave is enqueued
         runner.setWeights(*locker_->weights(), ver);
         have = ver;
       }
-      if (!runner.step(sink)) break;
+      const bool ok = runner.hostWalk() ? runner.step(host_sink) : runner.stepDevice(dev_sink);
+      ++waves_;
+      if (!ok) break;
     }
   }
+
+  int64_t waves() const { return waves_.load(); }
+  int concurrentGames() const { return std::max(1, cfg_.concurrent_games); }
 
  private:
   std::shared_ptr<ModelLocker> locker_;
   std::shared_ptr<ValuePrioritizedReplay> replay_;
   const RecursiveSolvingParams cfg_;
   const int seed_;
+  std::atomic<int64_t> waves_{0};
 };
 
 std::shared_ptr<ThreadLoop> create_cfr_thread(std::shared_ptr<ModelLocker> locker, std::shared_ptr<ValuePrioritizedReplay> replay,
@@ -105,6 +121,7 @@ float compute_exploitability_fp(RecursiveSolvingParams params) {
 // checkpoint's value net, then the exploitability of the assembled full-tree strategy.
 float compute_exploitability_with_net(RecursiveSolvingParams params, const std::string& model_path) {
   py::gil_scoped_release nogil;
+  params.net_mode = liars_dice::env_int("CFRB_EVAL_NET_MODE", CFRB_NET_FP32);   // the reference evaluates a checkpoint with an fp32 forward
   auto model = torch::jit::load(model_path, torch::kCPU);
   RecursiveEvaluator ev(params, eval_device(), 8192);
   ev.setWeights(flat_weights_of(model));
@@ -118,6 +135,7 @@ float compute_exploitability_with_net(RecursiveSolvingParams params, const std::
 // of the net against full-depth solves, with the beliefs defined by the net strategy and by the full-tree strategy.
 std::tuple<float, float, float> compute_stats_with_net(RecursiveSolvingParams params, const std::string& model_path) {
   py::gil_scoped_release nogil;
+  params.net_mode = liars_dice::env_int("CFRB_EVAL_NET_MODE", CFRB_NET_FP32);   // the reference evaluates a checkpoint with an fp32 forward
   PhaseTimer pt;
   auto model = torch::jit::load(model_path, torch::kCPU);
   model.eval();
@@ -248,6 +266,8 @@ PYBIND11_MODULE(rela, m) {
            py::arg("beta"), py::arg("prefetch"), py::arg("use_priority"), py::arg("compressed_values"))
       .def("size", &ValuePrioritizedReplay::size)
       .def("num_add", &ValuePrioritizedReplay::numAdd)
+      .def("storage_device", &ValuePrioritizedReplay::storageDevice,
+           "rebel_b200 extension: CUDA ordinal the rows live on (-1 host memory: no CUDA device, -2 nothing stored yet)")
       .def("sample", &ValuePrioritizedReplay::sample)
       .def("pop_until", &ValuePrioritizedReplay::popUntil)
       .def("load", &ValuePrioritizedReplay::load)
@@ -280,11 +300,14 @@ PYBIND11_MODULE(rela, m) {
       // rebel_b200 extensions (defaults from CFRB_* environment variables, see params.h)
       .def_readwrite("concurrent_games", &RecursiveSolvingParams::concurrent_games)
       .def_readwrite("net_mode", &RecursiveSolvingParams::net_mode)
-      .def_readwrite("state_dtype", &RecursiveSolvingParams::state_dtype);
+      .def_readwrite("state_dtype", &RecursiveSolvingParams::state_dtype)
+      .def_readwrite("host_walk", &RecursiveSolvingParams::host_walk);
 
   py::class_<DataThreadLoop, ThreadLoop, std::shared_ptr<DataThreadLoop>>(m, "DataThreadLoop")
       .def(py::init<std::shared_ptr<ModelLocker>, std::shared_ptr<ValuePrioritizedReplay>, const RecursiveSolvingParams&, int>(),
-           py::arg("model_locker"), py::arg("replay"), py::arg("params"), py::arg("thread_id"));
+           py::arg("model_locker"), py::arg("replay"), py::arg("params"), py::arg("thread_id"))
+      .def_property_readonly("waves", &DataThreadLoop::waves, "rebel_b200 extension: waves of concurrent_games subgames completed")
+      .def_property_readonly("concurrent_games", &DataThreadLoop::concurrentGames);
 
   py::class_<Context>(m, "Context")
       .def(py::init<>())

@@ -4,23 +4,31 @@
 // update_priority, same blocking semantics (producers block while the ring of 1.25 x capacity rows is full, sampling
 // evicts the oldest rows down to `capacity`), same on-disk record format (rela/types.cc:87-111).
 //
-// Not a port: the reference stores one pair of heap-allocated torch tensors per example behind a vector of DataType; at
-// GPU generation rates (millions of rows per minute) that is an allocation storm.  Here rows live in two flat float
-// arrays (ring buffer), producers append whole waves with one memcpy per block, and a batch is gathered straight into
-// a (pinned, when it goes to a GPU) tensor.  Prefetch futures are unnecessary because sampling is a gather of `batch` rows;
-// the `prefetch` argument is accepted for API compatibility.
+// Not a port: the reference stores one pair of heap-allocated host tensors per example behind a vector of DataType and
+// stacks a batch on the host before moving it to the training device (rela/types.cc:19-41).  Here the rows are DEVICE
+// RESIDENT: two [ring][dim] fp32 matrices in HBM behind the C ABI (cfrb_rows_*, include/cfrb200.h).
+// Generator loops append a whole wave's examples with one device-to-device copy straight from the buffer their kernels wrote
+// (addRowsDevice), and sample() gathers the batch on the device into the tensors it returns, on the consumer's own CUDA
+// stream — an example never visits host memory between the kernel that produced it and the trainer's batch.  Only the
+// bookkeeping the reference keeps under its mutex stays on the host: head / size, priorities, eviction marks, the sampler RNG.
+// On a machine WITHOUT a CUDA device (the CPU test tier) the same class keeps the rows in host memory so that the ring /
+// blocking / priority logic can be tested; nothing is computed there.
 #pragma once
+#include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
 
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
+#include <functional>
 #include <mutex>
 #include <random>
 #include <stdexcept>
 #include <string>
 #include <tuple>
 #include <vector>
+
+#include "../../../include/cfrb200.h"
 
 namespace rela {
 
@@ -30,6 +38,79 @@ class ValueTransition {
   ValueTransition(const torch::Tensor& q, const torch::Tensor& v) : query(q), values(v) {}
   torch::Tensor query;
   torch::Tensor values;
+};
+
+// Where the rows of the ring live: HBM (cfrb_rows) when a CUDA device exists, host vectors otherwise.
+class RowStore {
+ public:
+  RowStore() = default;
+  RowStore(const RowStore&) = delete;
+  RowStore& operator=(const RowStore&) = delete;
+  ~RowStore() { if (dev_) cfrb_rows_destroy(dev_); }
+
+  bool created() const { return q_dim_ >= 0; }
+  bool onDevice() const { return dev_ != nullptr; }
+  int device() const { return dev_ ? cfrb_rows_device(dev_) : -1; }
+  int qDim() const { return q_dim_; }
+  int vDim() const { return v_dim_; }
+
+  void create(int64_t cap, int q_dim, int v_dim, int prefer_device) {
+    cap_ = cap; q_dim_ = q_dim; v_dim_ = v_dim;
+    const int ndev = cfrb_device_count();
+    if (ndev > 0) {
+      int d = prefer_device;
+      if (const char* e = std::getenv("CFRB_REPLAY_DEVICE")) d = std::atoi(e);
+      if (d < 0 || d >= ndev) d = 0;
+      if (cfrb_rows_create(d, cap, q_dim, v_dim, &dev_) < 0) throw std::runtime_error(std::string("cfrb_rows_create: ") + cfrb_last_error());
+    } else {
+      hq_.assign((size_t)cap * q_dim, 0.f);
+      hv_.assign((size_t)cap * v_dim, 0.f);
+    }
+  }
+  // kind 0: host pointers, 1: device pointers on src_device
+  void write(int64_t slot, int n, const float* q, const float* v, int kind, int src_device) {
+    if (dev_) {
+      if (cfrb_rows_write(dev_, slot, n, q, v, kind, src_device) < 0) throw std::runtime_error(std::string("cfrb_rows_write: ") + cfrb_last_error());
+      return;
+    }
+    if (kind != 0) throw std::runtime_error("RowStore: device rows offered to a host-memory store");
+    for (int i = 0; i < n; ++i) {
+      const int64_t j = (slot + i) % cap_;
+      std::copy(q + (size_t)i * q_dim_, q + (size_t)(i + 1) * q_dim_, hq_.begin() + (size_t)j * q_dim_);
+      std::copy(v + (size_t)i * v_dim_, v + (size_t)(i + 1) * v_dim_, hv_.begin() + (size_t)j * v_dim_);
+    }
+  }
+  void read(int64_t slot, int n, float* q, float* v) {
+    if (dev_) {
+      if (cfrb_rows_read(dev_, slot, n, q, v) < 0) throw std::runtime_error(std::string("cfrb_rows_read: ") + cfrb_last_error());
+      return;
+    }
+    for (int i = 0; i < n; ++i) {
+      const int64_t j = (slot + i) % cap_;
+      std::copy(hq_.begin() + (size_t)j * q_dim_, hq_.begin() + (size_t)(j + 1) * q_dim_, q + (size_t)i * q_dim_);
+      std::copy(hv_.begin() + (size_t)j * v_dim_, hv_.begin() + (size_t)(j + 1) * v_dim_, v + (size_t)i * v_dim_);
+    }
+  }
+  // out_device: -1 host, else CUDA ordinal of out_q / out_v
+  void gather(const std::vector<int>& ids, float* out_q, float* out_v, int out_device, void* stream) {
+    if (dev_) {
+      if (cfrb_rows_gather(dev_, ids.data(), (int)ids.size(), out_q, out_v, out_device, stream) < 0)
+        throw std::runtime_error(std::string("cfrb_rows_gather: ") + cfrb_last_error());
+      return;
+    }
+    if (out_device >= 0) throw std::runtime_error("RowStore: no CUDA device");
+    for (size_t i = 0; i < ids.size(); ++i) {
+      const int64_t j = ids[i];
+      std::copy(hq_.begin() + (size_t)j * q_dim_, hq_.begin() + (size_t)(j + 1) * q_dim_, out_q + i * q_dim_);
+      std::copy(hv_.begin() + (size_t)j * v_dim_, hv_.begin() + (size_t)(j + 1) * v_dim_, out_v + i * v_dim_);
+    }
+  }
+
+ private:
+  cfrb_rows* dev_ = nullptr;
+  std::vector<float> hq_, hv_;
+  int64_t cap_ = 0;
+  int q_dim_ = -1, v_dim_ = -1;
 };
 
 class ValuePrioritizedReplay {
@@ -44,42 +125,40 @@ class ValuePrioritizedReplay {
 
   int size() const { std::lock_guard<std::mutex> lk(m_); return size_; }
   int numAdd() const { return num_add_.load(); }
+  // rebel_b200 extension: CUDA ordinal the rows live on (-1: host memory, no CUDA device; -2: nothing stored yet)
+  int storageDevice() const { std::lock_guard<std::mutex> lk(m_); return store_.created() ? store_.device() : -2; }
 
-  // Native producer path: n rows of width q_dim / v_dim; priority may be null (= 1).  Blocks while the ring is full.
-  // Returns false if the buffer was closed (shutdown) while waiting.
-  bool addRows(const float* q, int q_dim, const float* v, int v_dim, int n, const float* priority) {
-    if (n <= 0) return true;
-    std::unique_lock<std::mutex> lk(m_);
-    ensureWidths(q_dim, v_dim);
-    if (n > ring_) throw std::runtime_error("ValuePrioritizedReplay: block larger than the buffer");
-    cv_space_.wait(lk, [&] { return size_ + n <= ring_ || closed_; });
-    if (closed_) return false;
-    double add = 0;
-    for (int i = 0; i < n; ++i) {
-      const int j = (head_ + size_ + i) % ring_;
-      std::copy(q + (size_t)i * q_dim_, q + (size_t)(i + 1) * q_dim_, queries_.begin() + (size_t)j * q_dim_);
-      std::copy(v + (size_t)i * v_dim_, v + (size_t)(i + 1) * v_dim_, values_.begin() + (size_t)j * v_dim_);
-      float w = priority ? priority[i] : 1.f;
-      if (use_priority_) w = std::pow(w, alpha_);
-      weights_[j] = w;
-      evicted_[j] = 0;
-      add += w;
-    }
-    size_ += n;
-    sum_ += add;
-    num_add_ += n;
-    return true;
+  // Producer paths.  n rows of width q_dim / v_dim; priority may be null (= 1).  Blocks while the ring is full
+  // (ConcurrentQueue::blockAppend, prioritized_replay.h:59-96); `cancelled` (optional) is polled whenever the buffer is woken
+  // (wake()) so that a terminating generator loop can leave — it returns false then, without closing the buffer for others.
+  bool addRows(const float* q, int q_dim, const float* v, int v_dim, int n, const float* priority,
+               const std::function<bool()>& cancelled = nullptr) {
+    return append(q, q_dim, v, v_dim, n, priority, /*kind=*/0, /*src_device=*/-1, cancelled);
   }
+  // The same for rows that already live in device memory (a generator's example buffer): one device-to-device copy.
+  bool addRowsDevice(const float* dev_q, int q_dim, const float* dev_v, int v_dim, int n, int src_device,
+                     const std::function<bool()>& cancelled = nullptr) {
+    return append(dev_q, q_dim, dev_v, v_dim, n, nullptr, /*kind=*/1, src_device, cancelled);
+  }
+  void wake() { cv_space_.notify_all(); }
 
   // add(batch, priority) of the reference: slices an [n, ...] transition into rows (prioritized_replay.h:254-261)
   void add(const ValueTransition& batch, const torch::Tensor& priority) {
-    auto q = batch.query.to(torch::kCPU, torch::kFloat32).contiguous();
-    auto v = batch.values.to(torch::kCPU, torch::kFloat32).contiguous();
     auto p = priority.to(torch::kCPU, torch::kFloat32).contiguous();
     const int n = (int)p.size(0);
+    auto q = batch.query, v = batch.values;
     if (q.dim() == 1) q = q.unsqueeze(0);
     if (v.dim() == 1) v = v.unsqueeze(0);
     if (q.size(0) != n || v.size(0) != n) throw std::runtime_error("ValuePrioritizedReplay.add: batch/priority size mismatch");
+    if (q.is_cuda() && v.is_cuda() && q.get_device() == v.get_device() && cfrb_device_count() > 0) {
+      // rows that are already on a GPU stay there
+      q = q.to(torch::kFloat32).contiguous(); v = v.to(torch::kFloat32).contiguous();
+      c10::cuda::getCurrentCUDAStream(q.get_device()).synchronize();
+      append(q.data_ptr<float>(), (int)q.size(1), v.data_ptr<float>(), (int)v.size(1), n, p.data_ptr<float>(), 1, (int)q.get_device(), nullptr);
+      return;
+    }
+    q = q.to(torch::kCPU, torch::kFloat32).contiguous();
+    v = v.to(torch::kCPU, torch::kFloat32).contiguous();
     addRows(q.data_ptr<float>(), (int)q.size(1), v.data_ptr<float>(), (int)v.size(1), n, p.data_ptr<float>());
   }
 
@@ -88,11 +167,8 @@ class ValuePrioritizedReplay {
       throw std::runtime_error("ValuePrioritizedReplay.sample: previous samples' priority has not been updated");
     std::unique_lock<std::mutex> lk(m_);
     if (size_ <= 0) throw std::runtime_error("ValuePrioritizedReplay.sample: buffer is empty");
-    const bool to_gpu = device != "cpu";
-    auto opts = torch::TensorOptions().dtype(torch::kFloat32).pinned_memory(to_gpu);
-    auto q = torch::empty({batchsize, q_dim_}, opts), v = torch::empty({batchsize, v_dim_}, opts);
     auto w = torch::zeros({batchsize}, torch::kFloat32);
-    float* qp = q.data_ptr<float>(); float* vp = v.data_ptr<float>(); float* wp = w.data_ptr<float>();
+    float* wp = w.data_ptr<float>();
     std::vector<int> ids(batchsize);
     const int size = size_;
     const double sum = sum_;
@@ -101,7 +177,6 @@ class ValuePrioritizedReplay {
       for (int i = 0; i < batchsize; ++i) {
         const int j = (head_ + dist(rng_)) % ring_;
         ids[i] = j; wp[i] = weights_[j]; evicted_[j] = 0;
-        gather(j, qp + (size_t)i * q_dim_, vp + (size_t)i * v_dim_);
       }
     } else {                // stratified proportional sampling (prioritized_replay.h:373-449)
       const float segment = (float)sum / batchsize;
@@ -113,23 +188,37 @@ class ValuePrioritizedReplay {
           id = (head_ + next) % ring_; wj = weights_[id]; acc += wj; ++next;
         }
         ids[i] = id; wp[i] = wj; evicted_[id] = 0;
-        gather(id, qp + (size_t)i * q_dim_, vp + (size_t)i * v_dim_);
+      }
+    }
+    // makeBatch (rela/types.cc:19-41): gather the rows into the batch tensors — on the device when the rows are there
+    const bool to_gpu = device != "cpu";
+    ValueTransition batch;
+    if (store_.onDevice() && to_gpu) {
+      const auto d = torch::Device(device);
+      const int di = d.has_index() ? d.index() : 0;
+      auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(torch::Device(torch::kCUDA, di));
+      batch.query = torch::empty({batchsize, store_.qDim()}, opts);
+      batch.values = torch::empty({batchsize, store_.vDim()}, opts);
+      store_.gather(ids, batch.query.data_ptr<float>(), batch.values.data_ptr<float>(), di, (void*)c10::cuda::getCurrentCUDAStream(di).stream());
+    } else {
+      auto opts = torch::TensorOptions().dtype(torch::kFloat32).pinned_memory(to_gpu && cfrb_device_count() > 0);
+      batch.query = torch::empty({batchsize, store_.qDim()}, opts);
+      batch.values = torch::empty({batchsize, store_.vDim()}, opts);
+      store_.gather(ids, batch.query.data_ptr<float>(), batch.values.data_ptr<float>(), -1, nullptr);
+      if (to_gpu) {
+        const auto d = torch::Device(device);
+        batch.query = batch.query.to(d, /*non_blocking=*/true);
+        batch.values = batch.values.to(d, /*non_blocking=*/true);
       }
     }
     if (size_ > capacity_) popLocked(size_ - capacity_);   // evict oldest down to capacity (prioritized_replay.h:474-477)
     lk.unlock();
+    sampled_ids_ = ids;
     if (use_priority_) {
-      sampled_ids_ = ids;
       w = torch::pow(size * (w / (float)sum), -beta_);
       w /= w.max();
     }
-    ValueTransition batch(q, v);
-    if (to_gpu) {
-      auto d = torch::Device(device);
-      batch.query = q.to(d, /*non_blocking=*/true);
-      batch.values = v.to(d, /*non_blocking=*/true);
-      w = w.to(d);
-    }
+    if (to_gpu) w = w.to(torch::Device(device));
     return std::make_tuple(batch, w);
   }
 
@@ -139,7 +228,7 @@ class ValuePrioritizedReplay {
     auto p = torch::pow(priority.to(torch::kCPU, torch::kFloat32), alpha_).contiguous();
     const float* pp = p.data_ptr<float>();
     std::lock_guard<std::mutex> lk(m_);
-    for (size_t i = 0; i < sampled_ids_.size(); ++i) {
+    for (size_t i = 0; i < sampled_ids_.size(); ++i) {   // ConcurrentQueue::update (prioritized_replay.h:132-150): evicted rows are skipped
       const int id = sampled_ids_[i];
       if (evicted_[id]) continue;
       sum_ += pp[i] - weights_[id];
@@ -158,11 +247,15 @@ class ValuePrioritizedReplay {
     std::lock_guard<std::mutex> lk(m_);
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) throw std::runtime_error("cannot open " + path);
-    for (int i = 0; i < size_; ++i) {
-      const int j = (head_ + i) % ring_;
-      std::fwrite(&q_dim_, sizeof(int), 1, f); std::fwrite(&v_dim_, sizeof(int), 1, f);
-      std::fwrite(&queries_[(size_t)j * q_dim_], sizeof(float), q_dim_, f);
-      std::fwrite(&values_[(size_t)j * v_dim_], sizeof(float), v_dim_, f);
+    if (size_ > 0) {
+      const int qd = store_.qDim(), vd = store_.vDim();
+      std::vector<float> q((size_t)size_ * qd), v((size_t)size_ * vd);
+      store_.read(head_, size_, q.data(), v.data());
+      for (int i = 0; i < size_; ++i) {
+        std::fwrite(&qd, sizeof(int), 1, f); std::fwrite(&vd, sizeof(int), 1, f);
+        std::fwrite(&q[(size_t)i * qd], sizeof(float), qd, f);
+        std::fwrite(&v[(size_t)i * vd], sizeof(float), vd, f);
+      }
     }
     std::fclose(f);
   }
@@ -170,7 +263,12 @@ class ValuePrioritizedReplay {
   void load(const std::string& path, float priority, int max_size, int stride) {
     FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("cannot open " + path);
-    std::vector<float> q, v;
+    std::vector<float> q, v, bq, bv, bp;
+    int qd = 0, vd = 0;
+    auto flush = [&]() {
+      if (!bp.empty()) addRows(bq.data(), qd, bv.data(), vd, (int)bp.size(), bp.data());
+      bq.clear(); bv.clear(); bp.clear();
+    };
     for (int added = 0, i = 0;; ++i) {
       if (max_size > 0 && added == max_size) break;
       int qs = 0, vs = 0;
@@ -178,9 +276,13 @@ class ValuePrioritizedReplay {
       q.resize(qs); v.resize(vs);
       if ((int)std::fread(q.data(), sizeof(float), qs, f) != qs || (int)std::fread(v.data(), sizeof(float), vs, f) != vs) break;
       if (stride > 1 && i % stride != 0) continue;
-      addRows(q.data(), qs, v.data(), vs, 1, &priority);
+      if (!bp.empty() && (qs != qd || vs != vd)) flush();
+      qd = qs; vd = vs;
+      bq.insert(bq.end(), q.begin(), q.end()); bv.insert(bv.end(), v.begin(), v.end()); bp.push_back(priority);
+      if ((int)bp.size() >= 4096) flush();     // one host-to-device copy per block, not per record
       ++added;
     }
+    flush();
     std::fclose(f);
   }
 
@@ -188,12 +290,10 @@ class ValuePrioritizedReplay {
   std::vector<torch::Tensor> extract() {
     std::lock_guard<std::mutex> lk(m_);
     const int n = size_;
-    auto q = torch::empty({n, std::max(q_dim_, 0)}), v = torch::empty({n, std::max(v_dim_, 0)}), w = torch::empty({n});
-    for (int i = 0; i < n; ++i) {
-      const int j = (head_ + i) % ring_;
-      gather(j, q.data_ptr<float>() + (size_t)i * q_dim_, v.data_ptr<float>() + (size_t)i * v_dim_);
-      w.data_ptr<float>()[i] = use_priority_ ? std::pow(weights_[j], 1.f / alpha_) : weights_[j];
-    }
+    const int qd = std::max(store_.qDim(), 0), vd = std::max(store_.vDim(), 0);
+    auto q = torch::empty({n, qd}), v = torch::empty({n, vd}), w = torch::empty({n});
+    if (n > 0) store_.read(head_, n, q.data_ptr<float>(), v.data_ptr<float>());
+    for (int i = 0; i < n; ++i) w.data_ptr<float>()[i] = std::pow(weights_[(head_ + i) % ring_], 1.f / alpha_);   // :341
     popLocked(n);
     return {q, v, w};
   }
@@ -203,25 +303,31 @@ class ValuePrioritizedReplay {
     add(ValueTransition(data[0], data[1]), data[2]);
   }
 
-  // Wake producers blocked in addRows for shutdown (not part of the reference surface; used by thread loops).
-  void close() {
-    { std::lock_guard<std::mutex> lk(m_); closed_ = true; }
-    cv_space_.notify_all();
-  }
-
  private:
-  void ensureWidths(int q_dim, int v_dim) {
-    if (q_dim_ < 0) {
-      q_dim_ = q_dim; v_dim_ = v_dim;
-      queries_.assign((size_t)ring_ * q_dim_, 0.f);
-      values_.assign((size_t)ring_ * v_dim_, 0.f);
-    } else if (q_dim != q_dim_ || v_dim != v_dim_) {
-      throw std::runtime_error("ValuePrioritizedReplay: row width changed");
+  bool append(const float* q, int q_dim, const float* v, int v_dim, int n, const float* priority, int kind, int src_device,
+              const std::function<bool()>& cancelled) {
+    if (n <= 0) return true;
+    std::unique_lock<std::mutex> lk(m_);
+    if (!store_.created()) store_.create(ring_, q_dim, v_dim, kind == 1 ? src_device : 0);
+    else if (q_dim != store_.qDim() || v_dim != store_.vDim()) throw std::runtime_error("ValuePrioritizedReplay: row width changed");
+    if (n > ring_) throw std::runtime_error("ValuePrioritizedReplay: block larger than the buffer");
+    cv_space_.wait(lk, [&] { return size_ + n <= ring_ || (cancelled && cancelled()); });
+    if (size_ + n > ring_) return false;   // cancelled while waiting
+    const int first = (head_ + size_) % ring_;
+    if (kind == 1 && !store_.onDevice()) throw std::runtime_error("ValuePrioritizedReplay: device rows without a CUDA device");
+    store_.write(first, n, q, v, kind, src_device);
+    double add = 0;
+    for (int i = 0; i < n; ++i) {
+      const int j = (first + i) % ring_;
+      float w = priority ? priority[i] : 1.f;
+      if (use_priority_) w = std::pow(w, alpha_);
+      weights_[j] = w;                       // evicted_[j] is NOT reset here (blockAppend never touches it, :59-96)
+      add += w;
     }
-  }
-  void gather(int j, float* q, float* v) const {
-    std::copy(queries_.begin() + (size_t)j * q_dim_, queries_.begin() + (size_t)(j + 1) * q_dim_, q);
-    std::copy(values_.begin() + (size_t)j * v_dim_, values_.begin() + (size_t)(j + 1) * v_dim_, v);
+    size_ += n;
+    sum_ += add;
+    num_add_ += n;
+    return true;
   }
   void popLocked(int n) {
     for (int i = 0; i < n; ++i) {
@@ -238,12 +344,11 @@ class ValuePrioritizedReplay {
   const bool use_priority_;
   mutable std::mutex m_;
   std::condition_variable cv_space_;
-  int q_dim_ = -1, v_dim_ = -1;
-  std::vector<float> queries_, values_, weights_;
+  RowStore store_;
+  std::vector<float> weights_;
   std::vector<char> evicted_;
   int head_ = 0, size_ = 0;
   double sum_ = 0;
-  bool closed_ = false;
   std::atomic<int> num_add_{0};
   std::vector<int> sampled_ids_;
   std::mt19937 rng_;

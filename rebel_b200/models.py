@@ -66,4 +66,9 @@ def flatten_state_dict(state_dict):
     missing = [k for k in FLAT_ORDER if k not in state_dict]
     if missing:
         raise ValueError(f"state_dict is not a 2-layer LayerNorm Net2 (missing {missing})")
+    extra = [k for k in state_dict if k not in FLAT_ORDER]
+    if extra:   # e.g. Net2's default n_layers=3 adds body.8 / body.9: never evaluate a truncated network
+        raise ValueError(f"state_dict has parameters the accelerated Net2(n_hidden=256, n_layers=2, use_layer_norm=True) does not: {extra}")
+    if tuple(state_dict["body.4.weight"].shape) != (256, 256):
+        raise ValueError(f"n_hidden must be 256, got body.4.weight {tuple(state_dict['body.4.weight'].shape)}")
     return np.concatenate([state_dict[k].detach().to(torch.float32).cpu().numpy().ravel() for k in FLAT_ORDER])
