@@ -197,6 +197,12 @@ int cfrb_exploitability(cfrb_handle* h, const double* full_strategy, double* out
 /* Counters for bench.py: kernels launched by this handle since creation, and leaf rows of the wave. */
 int64_t cfrb_kernel_launches(const cfrb_handle* h);
 int64_t cfrb_wave_leaf_rows(const cfrb_handle* h);
+/* Timing marks (benchmarks): record CUDA event `slot` (0..7) on `cuda_stream` (NULL = the handle's stream); device time
+ * between two recorded marks (waits for the second). */
+int cfrb_mark(cfrb_handle* h, int32_t slot, void* cuda_stream);
+int cfrb_mark_elapsed_ms(cfrb_handle* h, int32_t a, int32_t b, float* ms);
+/* Overwrite a scratch buffer of `bytes` on the stream (pass more than the 126 MB of L2 to evict it between timed steps). */
+int cfrb_l2_flush(cfrb_handle* h, size_t bytes, void* cuda_stream);
 /* Device time in ms of the most recent cfrb_run, and of its value-net kernels only (CUDA events on
  * the launching stream; valid after cfrb_sync). */
 int cfrb_last_run_ms(cfrb_handle* h, float* total_ms, float* net_ms);
@@ -218,6 +224,12 @@ int cfrb_selfplay_wave(cfrb_handle* h, float* dev_ex_q, float* dev_ex_v, int32_t
 int cfrb_selfplay_wait_examples(cfrb_handle* h);
 /* Game states (public state and beliefs [n][2][H]) copied to the host; any pointer may be NULL.  Synchronises.  Returns n_games. */
 int cfrb_selfplay_state(cfrb_handle* h, int32_t* last_bid, int32_t* player, double* beliefs);
+/* Test aid: the division-free quotient of the regret-matching step (reciprocal of the node's sum + two fused multiply-add
+ * corrections, csrc/cfr_d2v2.cuh) against IEEE division on blocks x 256 x 4096 pseudo-random operand pairs. */
+int cfrb_debug_div_check(cfrb_handle* h, uint64_t seed, int32_t blocks, uint64_t* mismatches);
+/* Roots (last_bid, player_id) of the subgames of the current wave — also of a wave built on the device by cfrb_selfplay_wave
+ * (synchronises then).  Writes min(n, cap) entries, returns n. */
+int cfrb_wave_roots(cfrb_handle* h, int32_t* last_bid, int32_t* player_id, int32_t cap);
 /* Block until the work enqueued on `cuda_stream` (NULL = the handle's stream) has finished. */
 int cfrb_stream_wait(cfrb_handle* h, void* cuda_stream);
 

@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE — round-2 fixtures generated from the REFERENCE itself (oracle/_ref), build container only:
+
+    make -C oracle ref && python oracle/make_golden_r2.py [datagen] [config5] [band]
+
+  datagen_stats.npz   P5: the statistic cfvpy/selfplay.py:158-169 logs — per last action (and "initial")
+                      the example count, the sum of the targets and the sum of the per-example MSE of the seed-0 Net2 — over
+                      >= 50 k training examples of the reference's RlRunner loops (recursive_solving.cc:160-182) with the seed-0
+                      Net2 as value net, for TWO disjoint seed sets per shape (their difference is the band the GPU must meet).
+  config5_net.npz     BASELINE config 5 with the value net: recursive_eval's sampled recursive strategies (seeds 0..R-1,
+                      recursive_eval.cc:117-191,343-369) with the seed-0 Net2 evaluated in fp32 by ATen, 1x4f, 1024 iterations:
+                      exploitability at powers of two.
+  net_band.npz        derived tolerance of the tensor-core value nets: root value means after 1024 iterations when the
+                      REFERENCE's own net outputs are multiplied by 1 + sigma N(0,1), sigma = the measured relative output
+                      noise of the tcgen05 kernels (5.4e-4 fp32-GELU, 7.7e-4 packed-half GELU), 8 noise seeds per root.
+"""
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.oracle import Oracle, game_dims  # noqa: E402
+from oracle.make_golden import recursive_eval_reference, weights  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def last_action_stats(q, v, A, net=None):
+    """selfplay.py:158-169: bucket = index of the one-hot last bid in the query (A = "initial": all zeros)."""
+    onehot = q[:, 2:2 + A]
+    aid = np.where(onehot.sum(1) > 0, onehot.argmax(1), A)
+    cnt = np.bincount(aid, minlength=A + 1).astype(np.int64)
+    vsum = np.zeros(A + 1); vsq = np.zeros(A + 1); lsum = np.zeros(A + 1)
+    np.add.at(vsum, aid, v.astype(np.float64).sum(1))
+    np.add.at(vsq, aid, (v.astype(np.float64) ** 2).sum(1))
+    if net is not None:
+        import torch
+        with torch.no_grad():
+            pred = net(torch.from_numpy(q)).numpy()
+        np.add.at(lsum, aid, ((v - pred).astype(np.float64) ** 2).mean(1))
+    return cnt, vsum, vsq, lsum
+
+
+def datagen(R, threads=8):
+    from rebel_b200.models import make_selfplay_net
+    out = {}
+    for (D, F, games_per_thread) in [(1, 4, 1500), (1, 6, 1300)]:
+        A, H, Q = game_dims(D, F)
+        w = weights(D, F)
+        net = make_selfplay_net(D, F, seed=0)
+        for name, seed0 in (("a", 0), ("b", 5000)):
+            res = [None] * threads
+            t0 = time.time()
+
+            def work(i):
+                res[i] = R.rl_runner(D, F, seed0 + i, n_games=games_per_thread, num_iters=1024, net_w=w, cap=games_per_thread * 16)
+            th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+            [t.start() for t in th]; [t.join() for t in th]
+            q = np.concatenate([r[0] for r in res]); v = np.concatenate([r[1] for r in res])
+            cnt, vsum, vsq, lsum = last_action_stats(q, v, A, net)
+            out[f"count_{name}_{D}x{F}"] = cnt; out[f"val_sum_{name}_{D}x{F}"] = vsum
+            out[f"val_sq_{name}_{D}x{F}"] = vsq; out[f"loss_sum_{name}_{D}x{F}"] = lsum
+            print(f"datagen {D}x{F} set {name}: {len(q)} examples in {time.time() - t0:.0f} s", flush=True)
+        out[f"cfg_{D}x{F}"] = np.array([1024, 2, threads, games_per_thread])
+    np.savez_compressed(os.path.join(OUT, "datagen_stats.npz"), **out)
+
+
+def config5(R):
+    D, F, iters, reps = 1, 4, 1024, 64
+    t0 = time.time()
+    r = recursive_eval_reference(R, D, F, iters, reps, net_w=weights(D, F))
+    out = {"cfg": np.array([D, F, iters, reps]), "checkpoints": r["checkpoints"], "exploitability": r["exploitability"]}
+    r0 = recursive_eval_reference(R, D, F, iters, reps)
+    out["exploitability_zero_net"] = r0["exploitability"]
+    np.savez_compressed(os.path.join(OUT, "config5_net.npz"), **out)
+    print("config5", r["checkpoints"], r["exploitability"].mean(1), r0["exploitability"].mean(1), f"{time.time() - t0:.0f} s", flush=True)
+
+
+def band(R):
+    out = {"sigmas": np.array([5.4e-4, 7.7e-4]), "seeds": np.arange(8)}
+    for (D, F) in [(1, 4), (1, 6), (2, 3)]:
+        A, H, Q = game_dims(D, F)
+        w = weights(D, F)
+        g = np.load(os.path.join(OUT, f"cfr_net_{D}x{F}.npz"))
+        for i, (lb, pl) in enumerate(g["roots"]):
+            b = g[f"beliefs{i}"]
+            for si, sigma in enumerate(out["sigmas"]):
+                mus = []
+                for seed in out["seeds"]:
+                    R.set_net_noise(sigma, 1 + int(seed))
+                    mus.append(R.cfr_solve(D, F, b, [1024], int(lb), int(pl), num_iters=1024, net_w=w, want=("avg",))["root_means"][0])
+                R.set_net_noise(0.0, 0)
+                mus = np.stack(mus)
+                out[f"mu_pert{si}_{D}x{F}_{i}"] = mus
+                d = np.abs(mus - g[f"mu1024_nofma{i}"])
+                print(f"band {D}x{F} root{i} sigma={sigma:g}: mean|dmu| {d.mean():.2e} (per seed max {d.mean((1, 2)).max():.2e}), max {d.max():.2e}", flush=True)
+    np.savez_compressed(os.path.join(OUT, "net_band.npz"), **out)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["band", "config5", "datagen"]
+    R = Oracle("ref_nofma")      # deterministic build: band + config 5
+    RF = Oracle("ref_fast")      # -O3 build for the statistical fixture (>= 100 k examples per shape)
+    for k in what:
+        {"datagen": datagen, "config5": config5, "band": band}[k](RF if k == "datagen" else R)

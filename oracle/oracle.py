@@ -64,6 +64,7 @@ class Oracle:
         f.restype = C.c_double
         if kind != "port":
             self._f("bench_datagen").restype = C.c_int64
+            self._f("bench_datagen_windows").restype = C.c_int64
             self._f("last_error").restype = C.c_char_p
 
     def _f(self, name):
@@ -178,6 +179,14 @@ class Oracle:
         assert rc == 0
         return out
 
+    def set_net_noise(self, rel, seed=0):
+        """Reference builds only: relative gaussian noise on the Net2 outputs of the following cfr_solve calls (this thread)."""
+        assert self.kind != "port"
+        f = self.lib.ref_set_net_noise
+        f.argtypes = [C.c_double, C.c_uint64]
+        f.restype = None
+        f(float(rel), int(seed))
+
     def rl_runner(self, D, F, seed, n_games, num_iters=1024, max_depth=2, linear_update=True,
                   random_action_prob=0.25, sample_leaf=True, net_w=None, hidden=256, cap=4096, use_cfr=True):
         A, H, Q = game_dims(D, F)
@@ -257,3 +266,18 @@ class Oracle:
         if n < 0:
             raise RuntimeError(self._f("last_error")().decode())
         return n, el.value
+
+    def bench_datagen_windows(self, D, F, script_path, threads, warmup_s, n_windows, window_s, seed0=0, num_iters=1024, max_depth=2,
+                              random_action_prob=0.25, sample_leaf=True):
+        """One continuous run of `threads` RlRunner loops; returns (examples per window [n], seconds per window [n])."""
+        assert self.kind != "port"
+        counts = np.zeros(n_windows, np.int64)
+        secs = np.zeros(n_windows, np.float64)
+        f = self._f("bench_datagen_windows")
+        f.argtypes = [C.c_int] * 4 + [C.c_float, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,
+                      C.POINTER(C.c_int64), _dp]
+        n = f(D, F, num_iters, max_depth, random_action_prob, int(sample_leaf), script_path.encode(), threads, seed0,
+              float(warmup_s), n_windows, float(window_s), counts.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(secs, _dp))
+        if n < 0:
+            raise RuntimeError(self._f("last_error")().decode())
+        return counts, secs

@@ -53,6 +53,8 @@ using namespace liars_dice;
 namespace {
 
 thread_local std::string g_err;
+thread_local double g_noise_rel = 0;       // ref_set_net_noise: relative gaussian noise on the Net2 outputs of ref_cfr_solve
+thread_local uint64_t g_noise_seed = 0;
 
 SubgameSolvingParams make_params(int num_iters, int max_depth, int linear_update, int dcfr,
                                  double dcfr_alpha, double dcfr_beta, double dcfr_gamma) {
@@ -89,8 +91,16 @@ class FlatNet2 : public IValueNet {
     torch::NoGradGuard ng;
     auto x = torch::gelu(torch::layer_norm(torch::linear(q, w1, b1), {hidden_}, g1, be1, 1e-5));
     x = torch::gelu(torch::layer_norm(torch::linear(x, w2, b2), {hidden_}, g2, be2, 1e-5));
-    return torch::linear(x, w3, b3);
+    auto y = torch::linear(x, w3, b3);
+    if (noise_rel > 0) {   // parity-band experiments (SURVEY appendix B "pert"): outputs * (1 + rel * N(0,1)), seeded
+      float* p = y.data_ptr<float>();
+      std::normal_distribution<double> n01(0.0, 1.0);
+      for (int64_t i = 0; i < y.numel(); ++i) p[i] = (float)(p[i] * (1.0 + noise_rel * n01(noise_gen)));
+    }
+    return y;
   }
+  double noise_rel = 0;
+  std::mt19937_64 noise_gen{0};
   void add_training_example(const torch::Tensor q, const torch::Tensor v) override {
     std::lock_guard<std::mutex> lk(m_);
     const float* qp = q.data_ptr<float>();
@@ -169,6 +179,9 @@ extern "C" {
 
 const char* ref_last_error() { return g_err.c_str(); }
 
+// Parity-band experiments: the next ref_cfr_solve calls of this thread multiply every value-net output by 1 + rel * N(0,1).
+void ref_set_net_noise(double rel, uint64_t seed) { g_noise_rel = rel; g_noise_seed = seed; }
+
 // tree.h:51-70.  out rows: last_bid, player_id, children_begin, children_end, parent, depth.
 int ref_unroll_tree(int D, int F, int last_bid, int player_id, int max_depth, int32_t* out,
                     int cap_nodes) {
@@ -231,7 +244,10 @@ int ref_cfr_solve(int D, int F, int last_bid, int player_id, const double* belie
     for (auto& n : tree) has_pleaf |= (!n.num_children() && !game.is_terminal(n.state));
     std::shared_ptr<IValueNet> net;
     if (net_w) {
-      net = std::make_shared<FlatNet2>(net_w, 2 + A + 2 * H, hidden, H);
+      auto n2 = std::make_shared<FlatNet2>(net_w, 2 + A + 2 * H, hidden, H);
+      n2->noise_rel = g_noise_rel;
+      n2->noise_gen.seed(g_noise_seed);
+      net = n2;
     } else if (has_pleaf) {
       net = create_zero_net(H, false);
     }
@@ -586,6 +602,54 @@ int64_t ref_bench_datagen(int D, int F, int num_iters, int max_depth, float rand
     stop = true;
     for (auto& th : pool) th.join();
     return n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// The same loops timed in consecutive windows of one continuous run (the bench's --impl reference arm: one window = one
+// "step"): after `warmup_s` the example counter is sampled every `window_s` seconds; counts_out[i] = examples added during
+// window i.  Returns the total number of examples of the timed windows.
+int64_t ref_bench_datagen_windows(int D, int F, int num_iters, int max_depth, float random_action_prob, int sample_leaf,
+                                  const char* script_path, int threads, int seed0, double warmup_s, int n_windows,
+                                  double window_s, int64_t* counts_out, double* seconds_out) {
+  try {
+    torch::set_num_threads(1);
+    RecursiveSolvingParams cfg;
+    cfg.num_dice = D;
+    cfg.num_faces = F;
+    cfg.random_action_prob = random_action_prob;
+    cfg.sample_leaf = sample_leaf != 0;
+    cfg.subgame_params = make_params(num_iters, max_depth, 1, 0, 0, 0, 0);
+    std::vector<std::shared_ptr<CountingScriptNet>> nets;
+    for (int t = 0; t < threads; ++t) nets.push_back(std::make_shared<CountingScriptNet>(script_path));
+    std::atomic<bool> stop{false};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+      pool.emplace_back([&, t]() {
+        at::set_num_threads(1);
+        RlRunner runner(cfg, nets[t], seed0 + t);
+        while (!stop.load()) runner.step();
+      });
+    }
+    auto total = [&]() { int64_t n = 0; for (auto& net : nets) n += net->n_examples.load(); return n; };
+    std::this_thread::sleep_for(std::chrono::duration<double>(warmup_s));
+    int64_t prev = total(), sum = 0;
+    auto t_prev = std::chrono::steady_clock::now();
+    for (int i = 0; i < n_windows; ++i) {
+      std::this_thread::sleep_until(t_prev + std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double>(window_s)));
+      const auto now = std::chrono::steady_clock::now();
+      const int64_t cur = total();
+      if (counts_out) counts_out[i] = cur - prev;
+      if (seconds_out) seconds_out[i] = std::chrono::duration<double>(now - t_prev).count();
+      sum += cur - prev;
+      prev = cur;
+      t_prev = now;
+    }
+    stop = true;
+    for (auto& th : pool) th.join();
+    return sum;
   } catch (const std::exception& e) {
     g_err = e.what();
     return -1;

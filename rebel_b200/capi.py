@@ -75,6 +75,25 @@ def lib():
     L.cfrb_wave_leaf_rows.argtypes = [vp]
     L.cfrb_wave_leaf_rows.restype = C.c_int64
     L.cfrb_last_run_ms.argtypes = [vp, _fp, _fp]
+    L.cfrb_selfplay_create.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint32), C.c_float, C.c_int32]
+    L.cfrb_selfplay_wave.argtypes = [vp, vp, vp, C.c_int32, vp]
+    L.cfrb_selfplay_wait_examples.argtypes = [vp]
+    L.cfrb_selfplay_state.argtypes = [vp, _ip, _ip, _dp]
+    L.cfrb_stream_wait.argtypes = [vp, vp]
+    L.cfrb_debug_div_check.argtypes = [vp, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
+    L.cfrb_wave_roots.argtypes = [vp, _ip, _ip, C.c_int32]
+    L.cfrb_mark.argtypes = [vp, C.c_int32, vp]
+    L.cfrb_mark_elapsed_ms.argtypes = [vp, C.c_int32, C.c_int32, _fp]
+    L.cfrb_l2_flush.argtypes = [vp, C.c_size_t, vp]
+    L.cfrb_dev_alloc.argtypes = [C.c_int32, C.c_size_t, C.POINTER(vp)]
+    L.cfrb_dev_free.argtypes = [C.c_int32, vp]
+    L.cfrb_dev_to_host.argtypes = [C.c_int32, vp, vp, C.c_size_t]
+    L.cfrb_rows_create.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.cfrb_rows_destroy.argtypes = [vp]
+    L.cfrb_rows_device.argtypes = [vp]
+    L.cfrb_rows_write.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, C.c_int32, C.c_int32]
+    L.cfrb_rows_read.argtypes = [vp, C.c_int64, C.c_int32, _fp, _fp]
+    L.cfrb_rows_gather.argtypes = [vp, _ip, C.c_int32, vp, vp, C.c_int32, vp]
     _lib = L
     return L
 
@@ -225,6 +244,63 @@ class WaveSolver:
     @property
     def leaf_rows(self):
         return lib().cfrb_wave_leaf_rows(self._h)
+
+    # ---- device-resident self-play (cfrb_selfplay_*)
+    def selfplay_create(self, seeds, random_action_prob=0.25, sample_leaf=True):
+        s = np.ascontiguousarray(seeds, np.uint32)
+        _check(lib().cfrb_selfplay_create(self._h, s.size, s.ctypes.data_as(C.POINTER(C.c_uint32)), random_action_prob, int(sample_leaf)))
+        self.n = s.size
+        self._sp_bufs = None
+
+    def selfplay_wave(self, start_next=True, keep_examples=False, stream=None):
+        """Finish the pending wave and (optionally) start the next one, asynchronously.  keep_examples: the finished wave's
+        examples go to a device buffer owned by this object; examples() then copies them to the host."""
+        q = v = None
+        if keep_examples:
+            if self._sp_bufs is None:
+                a, b = C.c_void_p(), C.c_void_p()
+                _check(lib().cfrb_dev_alloc(self.cfg.device, self.n * 2 * self.Q * 4, C.byref(a)))
+                _check(lib().cfrb_dev_alloc(self.cfg.device, self.n * 2 * self.H * 4, C.byref(b)))
+                self._sp_bufs = (a, b)
+            q, v = self._sp_bufs
+        return _check(lib().cfrb_selfplay_wave(self._h, q, v, int(start_next), C.c_void_p(stream) if stream else None))
+
+    def selfplay_examples(self):
+        lib().cfrb_selfplay_wait_examples(self._h)
+        q = np.zeros((self.n, 2, self.Q), np.float32)
+        v = np.zeros((self.n, 2, self.H), np.float32)
+        _check(lib().cfrb_dev_to_host(self.cfg.device, q.ctypes.data_as(C.c_void_p), self._sp_bufs[0], q.nbytes))
+        _check(lib().cfrb_dev_to_host(self.cfg.device, v.ctypes.data_as(C.c_void_p), self._sp_bufs[1], v.nbytes))
+        return q, v
+
+    def selfplay_state(self):
+        lb = np.zeros(self.n, np.int32); pl = np.zeros(self.n, np.int32); b = np.zeros((self.n, 2, self.H), np.float64)
+        _check(lib().cfrb_selfplay_state(self._h, _p(lb, _ip), _p(pl, _ip), _p(b, _dp)))
+        return lb, pl, b
+
+    def div_check(self, seed, blocks):
+        bad = C.c_uint64(0)
+        _check(lib().cfrb_debug_div_check(self._h, seed, blocks, C.byref(bad)))
+        return bad.value
+
+    def wave_roots(self):
+        lb = np.zeros(self.n, np.int32); pl = np.zeros(self.n, np.int32)
+        n = _check(lib().cfrb_wave_roots(self._h, _p(lb, _ip), _p(pl, _ip), self.n))
+        return lb[:n], pl[:n]
+
+    def wait_examples(self):
+        _check(lib().cfrb_selfplay_wait_examples(self._h))
+
+    def mark(self, slot, stream=None):
+        _check(lib().cfrb_mark(self._h, slot, C.c_void_p(stream) if stream else None))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float(0)
+        _check(lib().cfrb_mark_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def l2_flush(self, nbytes=256 << 20, stream=None):
+        _check(lib().cfrb_l2_flush(self._h, nbytes, C.c_void_p(stream) if stream else None))
 
     def last_run_ms(self):
         a, b = C.c_float(0), C.c_float(0)

@@ -6,6 +6,7 @@
 #include "cfr_kernels.cuh"
 #include "br_kernel.cuh"
 #include "selfplay_kernels.cuh"
+#include "cfr_d2v2.cuh"
 
 namespace cfrb {
 
@@ -110,12 +111,61 @@ void rows_launch_gather(const float* src, int width, const int* ids, int n, floa
   rows_gather_kernel<<<blocks, 256, 0, st>>>(src, width, ids, n, out);
 }
 
+template <typename real>
+cudaError_t cfr_configure_d2v2(int smem_bytes) {
+  cudaError_t e = cudaSuccess;
+#define CFRB_CFG(HC)                                                                                                      \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cfr_iter_d2v2_kernel<real, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  CFRB_CFG(0) CFRB_CFG(4) CFRB_CFG(5) CFRB_CFG(6) CFRB_CFG(9) CFRB_CFG(16)
+#undef CFRB_CFG
+  return e;
+}
+template <typename real>
+int cfr_d2v2_smem_bytes(int Nmax, int H, int Hout, int Lmax, int Tmax, int n1max, int stride) {
+  return D2v2Layout((int)sizeof(real), Nmax, H, Hout, Lmax, Tmax, n1max, stride).bytes;
+}
+template <typename real>
+void cfr_launch_iter_d2v2(const CfrDev<real>& p, int blocks, size_t smem, cudaStream_t st, int iter, int do_b, int do_f, int n1max) {
+#define CFRB_CALL(HC) launch_pdl(cfr_iter_d2v2_kernel<real, HC>, blocks, 32, smem, st, p, iter, do_b, do_f, n1max)
+  CFRB_DISPATCH_H(p.H, CFRB_CALL)
+#undef CFRB_CALL
+}
+
+// div_by_rcp against IEEE division on pseudo-random operands: quotient mantissas spread over [1, 2), including operands whose
+// quotient lies within a few ulp of a power of two and denominators with all-ones / all-zeros low mantissa bits.
+__global__ void div_check_kernel(unsigned long long seed, unsigned long long* mismatches) {
+  unsigned long long s = seed + (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+  auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  unsigned long long bad = 0;
+  for (int i = 0; i < 4096; ++i) {
+    const unsigned long long a = next(), c = next(), m = next();
+    double b = __longlong_as_double((long long)(0x3FF0000000000000ull | (c >> 12)));           // [1, 2)
+    double x = __longlong_as_double((long long)(0x3FF0000000000000ull | (a >> 12)));
+    const int kind = (int)(m & 7);
+    if (kind == 1) b = __longlong_as_double((long long)(0x3FFFFFFFFFFFFF00ull | (c & 0xFF)));     // denominator just below 2
+    if (kind == 2) b = __longlong_as_double((long long)(0x3FF0000000000000ull | (c & 0xFF)));     // just above 1
+    if (kind == 3) x = b * (1.0 + (double)((long long)(a & 0xF) - 8) * 2.220446049250313e-16);      // quotient within a few ulp of 1
+    if (kind == 4) x = x * 1e-80;                                                                   // the smoothing epsilon's scale
+    if (kind == 5) b = b * (double)(1 + (c & 15));                                                  // sums of up to a dozen regrets
+    const double y = 1.0 / b;
+    const double q = div_by_rcp(x, b, y);
+    if (__double_as_longlong(q) != __double_as_longlong(x / b)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+void div_check_launch(unsigned long long seed, int blocks, unsigned long long* mismatches, cudaStream_t st) {
+  div_check_kernel<<<blocks, 256, 0, st>>>(seed, mismatches);
+}
+
 #define CFRB_INSTANTIATE(real)                                                                                             \
   template cudaError_t cfr_configure<real>(int, int);                                                                      \
   template void cfr_launch_init<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int);                      \
   template void cfr_launch_iter<real>(const CfrDev<real>&, int, int, int, size_t, cudaStream_t, int, int, int, int);             \
   template cudaError_t cfr_configure_d2<real>(int);                                                                        \
   template void cfr_launch_iter_d2<real>(const CfrDev<real>&, int, int, size_t, cudaStream_t, int, int, int, int);                \
+  template cudaError_t cfr_configure_d2v2<real>(int);                                                                      \
+  template int cfr_d2v2_smem_bytes<real>(int, int, int, int, int, int, int);                                                \
+  template void cfr_launch_iter_d2v2<real>(const CfrDev<real>&, int, size_t, cudaStream_t, int, int, int, int);             \
   template void sp_launch_begin<real>(const SpDev&, real*, cudaStream_t);                                                  \
   template void sp_launch_finish<real>(const SpDev&, const real*, const real*, float*, float*, cudaStream_t);
 CFRB_INSTANTIATE(float)

@@ -37,6 +37,7 @@ struct CfrDev {
   real* scaler;                   // [rows] sum of opponent reach at the pseudo-leaf
   real* scratch; size_t scratch_stride;   // global scratch (CTA groups), reals per subgame
   int nh_max, tmp_reals;                  // scratch layout: bufA[nh_max] | bufB[nh_max] | tmp[tmp_reals] | lsum[2*Lmax]
+  int lmax, tmax;                         // largest pseudo-leaf / terminal count over the templates (cfr_iter_d2v2_kernel's layout)
   // params
   int linear, dcfr; real dcfr_alpha, dcfr_beta, dcfr_gamma;
   int use_net;
@@ -87,6 +88,15 @@ template <typename real> void sp_launch_begin(const SpDev& p, real* wave_beliefs
 template <typename real> void sp_launch_finish(const SpDev& p, const real* mu, const real* snap, float* ex_q, float* ex_v, cudaStream_t st);
 // rows [ids[i]] of a [*, width] fp32 matrix -> out[i]  (replay sampling)
 void rows_launch_gather(const float* src, int width, const int* ids, int n, float* out, cudaStream_t st);
+
+// Generation-2 depth <= 2 kernel (cfr_d2v2.cuh): one warp per CTA, inputs staged by cp.async.bulk.
+template <typename real> cudaError_t cfr_configure_d2v2(int smem_bytes);
+template <typename real> int cfr_d2v2_smem_bytes(int Nmax, int H, int Hout, int Lmax, int Tmax, int n1max, int stride);
+template <typename real> void cfr_launch_iter_d2v2(const CfrDev<real>& p, int blocks, size_t smem, cudaStream_t st, int iter, int do_b, int do_f,
+                                                   int n1max);
+// Development check of div_by_rcp (cfr_d2v2.cuh): n pseudo-random (x, b) pairs per call, returns the number of quotients that
+// differ from x / b in *mismatches (device pointer).
+void div_check_launch(unsigned long long seed, int blocks, unsigned long long* mismatches, cudaStream_t st);
 
 // Launchers implemented in cfr_kernels.cu (explicitly instantiated for float and double).  `group` is 32 (one warp per
 // subgame, shared-memory scratch) or 256 (one CTA per subgame, global scratch).

@@ -17,7 +17,7 @@
 #include "cfr_tree.h"
 #include "leaf_mlp_simt.cuh"
 #include "leaf_mlp_tc.cuh"
-#include "leaf_mlp_tc2.cuh"
+#include "leaf_mlp_tc3.cuh"
 
 namespace {
 inline bool is_tc(int net_mode) { return net_mode == CFRB_NET_TC_F16 || net_mode == CFRB_NET_TC_F16X2; }
@@ -78,6 +78,8 @@ struct cfrb_handle {
   int max_levels = 0;
   int d2_groups_per_cta = 8;
   int d2_scratch_per_group = 0;
+  bool d2v2 = false;       // cfr_iter_d2v2_kernel (CFR solver, depth <= 2): one warp per CTA, inputs staged by cp.async.bulk
+  int d2v2_smem = 0, n1max = 0;
   int table_stride = 0;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
@@ -109,7 +111,7 @@ struct cfrb_handle {
   DevBuf<int> d_sg_tmpl, d_sg_player, d_sg_row_off, d_sg_act, d_steps;
   DevBuf<float> d_X, d_out, d_dbg;
   long long* dbg_trace = nullptr;   // set only inside cfrb_debug_net_trace
-  bool tc2 = false;                 // value net runs the two-tiles-in-flight kernel
+  bool tc_gen1 = false;             // CFRB_TC_GEN=1: the round-1 one-tile kernel (leaf_mlp_tc.cuh) instead of leaf_mlp_tc3.cuh
   DevBuf<__half> d_Xh;
   WaveState<float> sf;
   WaveState<double> sd;
@@ -137,6 +139,8 @@ struct cfrb_handle {
     cudaEvent_t ev_examples = nullptr;    // recorded behind the example / advance kernels of the last finished wave
     bool ev_recorded = false;
   } sp;
+  cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // cfrb_mark: timing events
+  void* flush_buf = nullptr; size_t flush_bytes = 0;                                                 // cfrb_l2_flush
   bool rows_on_device = false;   // the wave was built on the device: its row count / roots exist only there
   bool mirror_stale = false;     // ... and the host mirror (h_tmpl, h_beliefs, rows) has not been pulled yet
 };
@@ -159,7 +163,10 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   const size_t rows_cap = (size_t)K * std::max(h->Lmax, 1);
   CK(s.beliefs.alloc((size_t)K * 2 * g.H)); CK(s.mu.alloc((size_t)K * 2 * g.H));
   CK(s.R.alloc(tab)); CK(s.Sg.alloc(tab)); CK(s.S.alloc(tab)); CK(s.Snap.alloc(tab));
-  CK(s.vterm.alloc((size_t)K * std::max(h->Tmax, 1) * g.H)); CK(s.scaler.alloc(rows_cap));
+  const int vterm_stride = round_up(std::max(h->Tmax, 1) * g.H, 4);     // 16-byte aligned rows for the bulk copies
+  CK(s.vterm.alloc((size_t)K * vterm_stride + 8)); CK(s.scaler.alloc(rows_cap + 8));
+  CK(cudaMemset(s.vterm.p, 0, ((size_t)K * vterm_stride + 8) * sizeof(real)));
+  CK(cudaMemset(s.scaler.p, 0, (rows_cap + 8) * sizeof(real)));
   CK(cudaMemset(s.Snap.p, 0, tab * sizeof(real)));
   const size_t per_group_bytes = (size_t)h->scratch_per_group * sizeof(real);
   if (per_group_bytes * 2 <= (size_t)max_optin) {
@@ -181,6 +188,10 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
       h->d2_groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(4, cta_budget / d2_bytes));
       if (const char* e = std::getenv("CFRB_D2_GROUPS")) h->d2_groups_per_cta = std::max(1, std::min(h->d2_groups_per_cta, std::atoi(e)));
       CK(cfrb::cfr_configure_d2<real>((int)(d2_bytes * h->d2_groups_per_cta)));
+      const char* gen = std::getenv("CFRB_D2_GEN");
+      h->d2v2_smem = cfrb::cfr_d2v2_smem_bytes<real>(h->Nmax, g.H, h->Hout, std::max(h->Lmax, 1), std::max(h->Tmax, 1), h->n1max, h->table_stride);
+      h->d2v2 = h->cfg.solver == CFRB_SOLVER_CFR && !(gen && *gen == '1') && h->d2v2_smem <= max_optin;
+      if (h->d2v2) CK(cfrb::cfr_configure_d2v2<real>(h->d2v2_smem));
     }
   } else {
     h->group = 256;
@@ -195,7 +206,8 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   d.wave_n = h->d_wave.p; d.sg_tmpl = h->d_sg_tmpl.p; d.sg_player = h->d_sg_player.p; d.sg_row_off = h->d_sg_row_off.p;
   d.sg_act_iter = h->d_sg_act.p; d.beliefs = s.beliefs.p; d.mu = s.mu.p; d.steps = h->d_steps.p;
   d.R = s.R.p; d.Sg = s.Sg.p; d.S = s.S.p; d.Snap = s.Snap.p; d.table_stride = h->table_stride;
-  d.vterm = s.vterm.p; d.vterm_stride = std::max(h->Tmax, 1) * g.H;
+  d.vterm = s.vterm.p; d.vterm_stride = vterm_stride;
+  d.lmax = std::max(h->Lmax, 1); d.tmax = std::max(h->Tmax, 1);
   d.X = h->cfg.net_mode == CFRB_NET_FP32 ? h->d_X.p : nullptr;
   d.Xh = is_tc(h->cfg.net_mode) ? h->d_Xh.p : nullptr;
   d.net_out = h->d_out.p; d.scaler = s.scaler.p;
@@ -223,7 +235,9 @@ template <typename real>
 static int launch_iter_t(cfrb_handle* h, cudaStream_t st, int iter, int do_b, int do_f) {
   auto& s = state_of<real>(h);
   const int nsg = h->capturing ? h->cfg.max_subgames : h->n;   // surplus groups return at once (k >= *wave_n)
-  if (h->d2) {
+  if (h->d2 && h->d2v2) {
+    cfrb::cfr_launch_iter_d2v2<real>(s.dev, nsg, (size_t)h->d2v2_smem, st, iter, do_b, do_f, h->n1max);
+  } else if (h->d2) {
     const int blocks = (nsg + h->d2_groups_per_cta - 1) / h->d2_groups_per_cta;
     const size_t smem = (size_t)h->d2_scratch_per_group * sizeof(real) * h->d2_groups_per_cta;
     cfrb::cfr_launch_iter_d2<real>(s.dev, blocks, 32 * h->d2_groups_per_cta, smem, st, iter, do_b, do_f, h->d2_scratch_per_group);
@@ -471,6 +485,8 @@ int cfrb_destroy(cfrb_handle* h) {
   h->sp.last_bid.release(); h->sp.player.release(); h->sp.mt_idx.release(); h->sp.beliefs.release(); h->sp.mt.release();
   h->sp.seeds.release();
   if (h->sp.ev_examples) cudaEventDestroy(h->sp.ev_examples);
+  for (auto e : h->marks) if (e) cudaEventDestroy(e);
+  if (h->flush_buf) cudaFree(h->flush_buf);
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   for (auto e : h->net_ev) cudaEventDestroy(e);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -545,8 +561,9 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   // ---- sizes
   const int K = cfg->max_subgames;
   h->Qpad = round_up(g.Q + 1, 16);   // one spare column carries the constant 1 that feeds bias 1 through the tensor cores
-  h->Hout = g.H;
-  h->table_stride = std::max(1, (h->Nmax - 1) * g.H);
+  h->Hout = round_up(g.H, 4);                                     // value-net output rows padded to 16 bytes
+  h->table_stride = round_up(std::max(1, (h->Nmax - 1) * g.H), 4);   // every subgame's tables start 16-byte aligned (bulk copies)
+  h->n1max = g.A;
   h->scratch_per_group = cfrb::cfr_scratch_reals(h->Nmax, g.H, h->Lmax, h->Tmax);
   int max_optin = 0;
   CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
@@ -571,16 +588,15 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
     CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
     CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
     CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
-    {   // two-tiles-in-flight variant (leaf_mlp_tc2.cuh) when its activation ring fits next to the weights
-      const cfrb::tc::Tc2Layout T2(h->Qpad);
-      // Opt-in (CFRB_TC2=1): bit-identical, but measured SLOWER on B200 (188 vs 166 us per 540 672 rows) — with the A operand in
-      // shared memory the SS MMAs fetch 96 B/clk of operands, which starves the epilogue's own shared-memory traffic.
-      const char* on2 = std::getenv("CFRB_TC2");
-      h->tc2 = T2.smem_bytes <= max_optin && on2 && *on2 == '1';
-      if (h->tc2) {
-        CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2.smem_bytes));
-        CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2.smem_bytes));
-      }
+    {
+      const char* gen = std::getenv("CFRB_TC_GEN");
+      h->tc_gen1 = gen && *gen == '1';
+      const cfrb::tc::Tc3Layout T3(h->Qpad);
+      if (T3.smem_bytes > max_optin) return fail(CFRB_EINVAL, "tensor-core value net does not fit shared memory for this game shape");
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
     }
   }
   CK(cudaFuncSetAttribute(cfrb::leaf_mlp_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -660,21 +676,36 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
     __half* hw1 = reinterpret_cast<__half*>(blob.data() + L.off_w1);
     __half* hw2 = reinterpret_cast<__half*>(blob.data() + L.off_w2);
     __half* hw3 = reinterpret_cast<__half*>(blob.data() + L.off_w3);
-    for (int j = 0; j < hid; ++j) for (int k = 0; k < Q; ++k) hw1[cfrb::tc::umma_kmajor_offset_halves(j, k, hid)] = __float2half_rn(w1[(size_t)j * Q + k]);
-    for (int j = 0; j < hid; ++j) hw1[cfrb::tc::umma_kmajor_offset_halves(j, Q, hid)] = __float2half_rn(b1[j]);   // bias 1 x constant-1 column
+    // Generation 3 (leaf_mlp_tc3.cuh): LayerNorm without the mean.  Subtracting from every column of W (and from the bias) its
+    // mean over the 256 output features makes the features of y = W x + b sum to zero for every x, which is all the mean
+    // subtraction of LayerNorm does; the epilogue then only needs sum y^2.  Done in double, before the fp16 rounding.
+    const bool gen1 = h->tc_gen1;
+    std::vector<double> m1(Q + 1, 0.0), m2(hid + 1, 0.0);
+    if (!gen1) {
+      for (int k = 0; k < Q; ++k) { for (int j = 0; j < hid; ++j) m1[k] += w1[(size_t)j * Q + k]; m1[k] /= hid; }
+      for (int j = 0; j < hid; ++j) m1[Q] += b1[j];
+      m1[Q] /= hid;
+      for (int k = 0; k < hid; ++k) { for (int j = 0; j < hid; ++j) m2[k] += w2[(size_t)j * hid + k]; m2[k] /= hid; }
+      for (int j = 0; j < hid; ++j) m2[hid] += b2[j];
+      m2[hid] /= hid;
+    }
+    for (int j = 0; j < hid; ++j) for (int k = 0; k < Q; ++k) hw1[cfrb::tc::umma_kmajor_offset_halves(j, k, hid)] = __float2half_rn((float)(w1[(size_t)j * Q + k] - m1[k]));
+    for (int j = 0; j < hid; ++j) hw1[cfrb::tc::umma_kmajor_offset_halves(j, Q, hid)] = __float2half_rn((float)(b1[j] - m1[Q]));   // bias 1 x constant-1 column
     __half* hones = reinterpret_cast<__half*>(blob.data() + L.off_ones);
     __half* hb2 = reinterpret_cast<__half*>(blob.data() + L.off_bias2);
     for (int r = 0; r < cfrb::tc::kTileM; ++r) hones[cfrb::tc::umma_kmajor_offset_halves(r, 0, cfrb::tc::kTileM)] = __float2half_rn(1.f);
-    for (int j = 0; j < hid; ++j) hb2[cfrb::tc::umma_kmajor_offset_halves(j, 0, hid)] = __float2half_rn(b2[j]);
-    for (int j = 0; j < hid; ++j) for (int k = 0; k < hid; ++k) hw2[cfrb::tc::umma_kmajor_offset_halves(j, k, hid)] = __float2half_rn(w2[(size_t)j * hid + k]);
+    for (int j = 0; j < hid; ++j) hb2[cfrb::tc::umma_kmajor_offset_halves(j, 0, hid)] = __float2half_rn((float)(b2[j] - m2[hid]));
+    for (int j = 0; j < hid; ++j) for (int k = 0; k < hid; ++k) hw2[cfrb::tc::umma_kmajor_offset_halves(j, k, hid)] = __float2half_rn((float)(w2[(size_t)j * hid + k] - m2[k]));
     for (int j = 0; j < H; ++j) for (int k = 0; k < hid; ++k) hw3[cfrb::tc::umma_kmajor_offset_halves(j, k, cfrb::tc::kNout)] = __float2half_rn(w3[(size_t)j * hid + k]);
     float* ln1 = reinterpret_cast<float*>(blob.data() + L.off_ln1);
     float* ln2 = reinterpret_cast<float*>(blob.data() + L.off_ln2);
+    // generation 3 with the packed-half GELU evaluates the activation from y / 2: gamma / 2 and beta / 2 are stored
+    const float lnscale = (!gen1 && h->cfg.net_mode == CFRB_NET_TC_F16X2) ? 0.5f : 1.f;
     for (int j = 0; j < hid; ++j) {
       // per feature pair (j even): {gamma_j, gamma_j+1, beta_j, beta_j+1} — the packed operands of the epilogue's fma.f32x2
       const int o = (j >> 1) * 4 + (j & 1);
-      ln1[o] = g1[j]; ln1[o + 2] = be1[j];
-      ln2[o] = g2[j]; ln2[o + 2] = be2[j];
+      ln1[o] = lnscale * g1[j]; ln1[o + 2] = lnscale * be1[j];
+      ln2[o] = lnscale * g2[j]; ln2[o + 2] = lnscale * be2[j];
     }
     std::copy(b3, b3 + H, reinterpret_cast<float*>(blob.data() + L.off_b3));
     if (!h->d_blob.p) CK(h->d_blob.alloc(L.blob_bytes));
@@ -776,23 +807,26 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
     const int grid = (h->capturing || h->rows_on_device) ? h->num_sms : std::min(tiles, h->num_sms);   // surplus CTAs return at once
     const bool x2 = h->cfg.net_mode == CFRB_NET_TC_F16X2;
     a.trace = h->dbg_trace;
-    if (dbg1 || dbg2 || a.trace) {
-      if (x2) cfrb::tc::leaf_mlp_tc_kernel<true, true><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
-      else cfrb::tc::leaf_mlp_tc_kernel<true, false><<<grid, cfrb::tc::kThreads, L.smem_bytes, st>>>(a);
-    } else if (h->tc2) {
-      const cfrb::tc::Tc2Layout T2(h->Qpad);
-      if (x2) cfrb::tc::leaf_mlp_tc2_kernel<true><<<grid, cfrb::tc::kThreads, T2.smem_bytes, st>>>(a);
-      else cfrb::tc::leaf_mlp_tc2_kernel<false><<<grid, cfrb::tc::kThreads, T2.smem_bytes, st>>>(a);
-    } else {
-      // programmatic dependent launch: the kernel stages its weights while the CFR kernel before it drains (leaf_mlp_tc.cuh)
-      cudaLaunchConfig_t lc{};
-      lc.gridDim = dim3(grid); lc.blockDim = dim3(cfrb::tc::kThreads); lc.dynamicSmemBytes = L.smem_bytes; lc.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      lc.attrs = at; lc.numAttrs = 1;
-      if (x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<false, true>, a));
+    const cfrb::tc::Tc3Layout T3(h->Qpad);
+    const bool dbg = dbg1 || dbg2 || a.trace;
+    // programmatic dependent launch: the kernel fetches its weights while the CFR kernel before it drains
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(cfrb::tc::kThreads); lc.stream = st;
+    lc.dynamicSmemBytes = h->tc_gen1 ? L.smem_bytes : T3.smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = dbg ? 0 : 1;
+    if (h->tc_gen1) {
+      if (dbg && x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<true, true>, a));
+      else if (dbg) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<true, false>, a));
+      else if (x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<false, true>, a));
       else CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<false, false>, a));
+    } else {
+      if (dbg && x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<true, true>, a));
+      else if (dbg) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<true, false>, a));
+      else if (x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<false, true>, a));
+      else CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<false, false>, a));
     }
   } else {
     // a wave built on the device: worst-case grid, CTAs beyond the device-side row count return at once
@@ -1099,7 +1133,46 @@ int cfrb_exploitability(cfrb_handle* h, const double* full_strategy, double* out
 }
 
 int64_t cfrb_kernel_launches(const cfrb_handle* h) { return h ? h->launches : 0; }
-int64_t cfrb_wave_leaf_rows(const cfrb_handle* h) { return h ? h->rows : 0; }
+int64_t cfrb_wave_leaf_rows(const cfrb_handle* h) {
+  if (!h) return 0;
+  if (h->rows_on_device && h->mirror_stale) {   // a wave built on the device: the count lives there
+    int wave[2] = {0, 0};
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(wave, h->d_wave.p, sizeof(wave), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return wave[1];
+  }
+  return h->rows;
+}
+
+// Timing marks: CUDA events recorded on the launching stream (NULL = the handle's stream); elapsed device time between two.
+int cfrb_mark(cfrb_handle* h, int32_t slot, void* cuda_stream) {
+  if (!h || slot < 0 || slot >= 8) return fail(CFRB_EINVAL, "cfrb_mark: slot must be in [0, 8)");
+  CK(cudaSetDevice(h->cfg.device));
+  if (!h->marks[slot]) CK(cudaEventCreate(&h->marks[slot]));
+  CK(cudaEventRecord(h->marks[slot], cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream));
+  return CFRB_OK;
+}
+int cfrb_mark_elapsed_ms(cfrb_handle* h, int32_t a, int32_t b, float* ms) {
+  if (!h || !ms || a < 0 || a >= 8 || b < 0 || b >= 8 || !h->marks[a] || !h->marks[b]) return fail(CFRB_EINVAL, "cfrb_mark_elapsed_ms: bad marks");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->marks[b]));
+  CK(cudaEventElapsedTime(ms, h->marks[a], h->marks[b]));
+  return CFRB_OK;
+}
+// Evict the L2 cache: overwrite a scratch buffer of `bytes` (> 126 MB) on the stream, for benchmarks' timed loops.
+int cfrb_l2_flush(cfrb_handle* h, size_t bytes, void* cuda_stream) {
+  if (!h || bytes == 0) return fail(CFRB_EINVAL, "cfrb_l2_flush: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->flush_bytes < bytes) {
+    if (h->flush_buf) cudaFree(h->flush_buf);
+    h->flush_buf = nullptr; h->flush_bytes = 0;
+    CK(cudaMalloc(&h->flush_buf, bytes));
+    h->flush_bytes = bytes;
+  }
+  CK(cudaMemsetAsync(h->flush_buf, 1, bytes, cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream));
+  return CFRB_OK;
+}
 
 int cfrb_last_run_ms(cfrb_handle* h, float* total_ms, float* net_ms) {
   if (!h) return fail(CFRB_EINVAL, "null handle");
@@ -1200,6 +1273,36 @@ int cfrb_selfplay_state(cfrb_handle* h, int32_t* last_bid, int32_t* player, doub
   if (player) CK(cudaMemcpy(player, h->sp.player.p, K * sizeof(int), cudaMemcpyDeviceToHost));
   if (beliefs) CK(cudaMemcpy(beliefs, h->sp.beliefs.p, (size_t)K * 2 * h->g.H * sizeof(double), cudaMemcpyDeviceToHost));
   return K;
+}
+
+// Roots of the current wave (inspection; pulls the descriptors of a device-built wave).  Returns the number of subgames.
+int cfrb_wave_roots(cfrb_handle* h, int32_t* last_bid, int32_t* player_id, int32_t cap) {
+  if (!h) return fail(CFRB_EINVAL, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  { int rc = sync_mirror(h); if (rc) return rc; }
+  for (int k = 0; k < h->n && k < cap; ++k) {
+    if (last_bid) last_bid[k] = h->h_last_bid[k];
+    if (player_id) player_id[k] = h->h_player[k];
+  }
+  return h->n;
+}
+
+// Development / test aid: div_by_rcp (reciprocal + two fused-multiply-add corrections, cfr_d2v2.cuh) against IEEE division on
+// `blocks` x 256 x 4096 pseudo-random operand pairs; *mismatches receives the number of differing quotients.
+int cfrb_debug_div_check(cfrb_handle* h, uint64_t seed, int32_t blocks, uint64_t* mismatches) {
+  if (!h || !mismatches || blocks < 1) return fail(CFRB_EINVAL, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(unsigned long long)));
+  CK(cudaMemset(d, 0, sizeof(unsigned long long)));
+  cfrb::div_check_launch(seed, blocks, d, h->own_stream);
+  cudaError_t e = cudaStreamSynchronize(h->own_stream);
+  unsigned long long out = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&out, d, sizeof(out), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(e);
+  *mismatches = out;
+  return CFRB_OK;
 }
 
 int cfrb_stream_wait(cfrb_handle* h, void* cuda_stream) {

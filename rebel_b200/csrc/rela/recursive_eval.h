@@ -36,6 +36,7 @@ struct RecursiveEvalResult {
   std::vector<std::array<double, 2>> exploitability;
   int num_nodes = 0;
   int64_t subgames_solved = 0;
+  int64_t subgame_iters = 0;   // CFR iterations the reference would run for these subgames: the sum of their act_iterations
   double gpu_seconds = 0;   // host wall time spent inside cfrb_begin_wave / cfrb_run / cfrb_fetch_compact
 };
 
@@ -243,6 +244,7 @@ class RecursiveEvaluator {
           const Pending& P = cur[off + i];
           lb[i] = full_[P.root].last_bid; pl[i] = full_[P.root].player_id; ai[i] = act[P.repeat][P.root];
           max_act = std::max(max_act, full_mode ? sp.num_iters : ai[i]);
+          res.subgame_iters += full_mode ? sp.num_iters : ai[i];
           std::copy(P.beliefs.begin(), P.beliefs.end(), bel.begin() + (size_t)i * 2 * H_);
         }
         const auto t0 = std::chrono::steady_clock::now();

@@ -229,7 +229,7 @@ py::dict recursive_eval_sampled(const RecursiveSolvingParams& cfg, int device, i
   }
   py::dict d;
   d["summed_strategy"] = ss; d["summed_reach"] = sr; d["final_strategy"] = fs;
-  d["checkpoints"] = r.checkpoints; d["exploitability"] = ex; d["subgames_solved"] = r.subgames_solved;
+  d["checkpoints"] = r.checkpoints; d["exploitability"] = ex; d["subgames_solved"] = r.subgames_solved; d["subgame_iters"] = r.subgame_iters;
   d["gpu_seconds"] = r.gpu_seconds;
   return d;
 }

@@ -451,28 +451,37 @@ def test_full_size_properties_1x6f(rb, port, net_weights, net_name):
     S.close()
 
 
-@pytest.mark.parametrize("K", [1, 3, 149, 700])
-def test_two_tile_value_net_kernel_is_bit_identical(rb, net_weights, K):
-    """leaf_mlp_tc2_kernel (CFRB_TC2=1, two tiles in flight, A operand through a shared-memory ring) produces exactly the bits
-    of the default one-tile kernel, for wave sizes that give the CTAs single / odd / even numbers of tiles."""
-    import os
-    D, F = 1, 6
-    H = F ** D
-    rng = np.random.RandomState(K)
-    b = rng.rand(K, 2, H); b /= b.sum(-1, keepdims=True)
-    outs = []
-    for flag in ("0", "1"):
-        os.environ["CFRB_TC2"] = flag
-        try:
-            S = rb.WaveSolver(D, F, K, net_mode=rb.NET_TC_F16X2)
-        finally:
-            os.environ.pop("CFRB_TC2", None)
-        S.set_weights(net_weights(D, F))
-        S.begin(np.full(K, -1, np.int32), np.zeros(K, np.int32), b)
-        S.run(3)
-        outs.append((S.leaf_io()[1], S.fetch(("root_means",))["root_means"]))
+@pytest.mark.parametrize("net_name", ["tc_f16x2", "tc_f16"])
+@pytest.mark.parametrize("D,F", [(1, 6), (2, 3)])
+def test_value_net_rows_do_not_depend_on_their_tile(rb, port, net_weights, D, F, net_name):
+    """The two-tiles-in-flight tcgen05 kernel (leaf_mlp_tc3.cuh) evaluates every query row on its own: the outputs of a subgame's
+    rows are bit-identical whether the wave has 1, 2, 3, 149 or 1300 subgames (CTAs with a single tile, an odd / even number of
+    tiles, first and second TMEM A-operand region, partial last tile), and match the fp32 oracle net within fp16 tolerance."""
+    A, H, Q = game_dims(D, F)
+    Kmax = 1300
+    rng = np.random.RandomState(5)
+    b = rng.rand(Kmax, 2, H); b /= b.sum(-1, keepdims=True)
+    lb = rng.randint(-1, A - 2, size=Kmax).astype(np.int32); lb[:4] = -1
+    pl = rng.randint(0, 2, size=Kmax).astype(np.int32)
+    w = net_weights(D, F)
+    mode = getattr(rb, "NET_" + net_name.upper())
+    ref = None
+    for K in (Kmax, 1, 2, 3, 149):
+        S = rb.WaveSolver(D, F, K, net_mode=mode)
+        S.set_weights(w)
+        S.begin(lb[:K], pl[:K], b[:K])
+        S.run(2)
+        q, o, sc = S.leaf_io()
+        mu = S.fetch(("root_means",))["root_means"]
         S.close()
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        if ref is None:
+            ref = (q, o, mu)
+            want = port.net2_forward(w, Q, 256, H, q)
+            err = np.abs(o - want)
+            assert err.max() < 4e-3 * max(1.0, np.abs(want).max()) and err.mean() < 4e-4, (err.max(), err.mean())
+        else:
+            n = len(q)
+            assert np.array_equal(q, ref[0][:n]) and np.array_equal(o, ref[1][:n]) and np.array_equal(mu, ref[2][:K]), K
 
 
 def test_snapshot_matches_strategy_at_act_iteration(rb, port):
@@ -494,6 +503,39 @@ def test_snapshot_matches_strategy_at_act_iteration(rb, port):
         for k in np.nonzero(act == a)[0]:
             assert np.array_equal(snap[k], last[k]), (k, a)
     S.close()
+
+
+def test_snapshot_of_act_iteration_zero_needs_no_run(rb, port):
+    """act_iteration == 0 (probability 1/136 per subgame in the sampled recursive evaluation at 32 iterations; always possible
+    in RlRunner): the sampling strategy is the CFR constructor's uniform one and must be in the snapshot even when cfrb_run
+    is called with 0 iterations (or not at all) — on a fresh handle and after a previous wave left other data there."""
+    D, F = 1, 6
+    A, H, Q = game_dims(D, F)
+    S = rb.WaveSolver(D, F, 8, net_mode=rb.NET_ZERO)
+    lb = np.array([-1, 3, 0], np.int32); pl = np.array([0, 1, 1], np.int32)
+    b = np.stack([port.synthetic_beliefs(H, 70 + i) for i in range(3)])
+    for rnd in range(2):
+        if rnd == 1:      # leave a non-uniform snapshot of another wave behind first
+            S.begin(lb, pl, b, np.array([4, 4, 4], np.int32))
+            S.run(6)
+        S.begin(lb, pl, b, np.array([0, 0, 0], np.int32))
+        S.run(0)
+        snap = S.fetch(("snapshot",))["snapshot"]
+        S.begin(lb, pl, b, None)
+        init = S.fetch(("last",))["last"]                   # the constructor's uniform strategy
+        assert np.array_equal(snap, init) and snap.max() > 0, rnd
+    S.close()
+
+
+def test_fast_division_is_correctly_rounded(rb):
+    """cfr_iter_d2v2_kernel obtains sigma = max(R, eps) / sum from the reciprocal of the sum (one true division per (node, hand))
+    and two fused multiply-add correction steps instead of one IEEE division per action.  The quotients must be the correctly
+    rounded ones — the bits `/` gives — or the solver would leave the reference's trajectory: 4.3e9 pseudo-random operand pairs
+    (uniform mantissas, denominators next to 1 and 2, quotients within a few ulp of 1, the 1e-80 scale, small-integer multiples)."""
+    S = rb.WaveSolver(1, 4, 1, net_mode=rb.NET_ZERO)
+    bad = sum(S.div_check(seed, 1024) for seed in (1, 2, 3, 4))
+    S.close()
+    assert bad == 0, bad
 
 
 def test_edge_cases_and_errors(rb, port):

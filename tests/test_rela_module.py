@@ -292,3 +292,106 @@ def test_drop_in_datagen_flow(rela):
     while not ctx.terminated() and time.time() - t0 < 30:
         time.sleep(0.05)
     assert ctx.terminated() and ctx.error() == ""
+
+
+def test_model_locker_rejects_deeper_net2(rela):
+    """A Net2 with n_layers=3 (the reference Net2's own default) contains all ten keys of the 2-layer net plus more: it must be
+    rejected, never truncated (ModelLocker, flatten_state_dict)."""
+    from rebel_b200.models import Net2, flatten_state_dict
+    deep = Net2(num_faces=4, num_dice=1, n_hidden=256, n_layers=3, use_layer_norm=True)
+    with pytest.raises(RuntimeError, match="unexpected parameter"):
+        rela.ModelLocker([torch.jit.script(deep)], "cuda:0")
+    with pytest.raises(ValueError):
+        flatten_state_dict(deep.state_dict())
+    narrow = Net2(num_faces=4, num_dice=1, n_hidden=128, n_layers=2, use_layer_norm=True)
+    with pytest.raises(RuntimeError, match="256"):
+        rela.ModelLocker([torch.jit.script(narrow)], "cuda:0")
+
+
+def test_terminating_a_loop_keeps_the_shared_replay_open(rela):
+    """DataThreadLoop::terminate wakes a producer blocked on the full ring but must not close the buffer for other users
+    (the reference's buffer stays usable after Context.terminate)."""
+    r = rela.ValuePrioritizedReplay(8, 0, 1.0, 1.0, 0, False, False)
+    ctx = rela.Context()
+    ctx.terminate()
+    q = torch.zeros(4, 3)
+    r.push([q, q.clone(), torch.ones(4)])
+    assert r.size() == 4 and r.num_add() == 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,F", [(1, 4), (1, 6), (2, 3)])
+@pytest.mark.parametrize("sample_leaf,use_cfr", [(True, True), (False, True), (True, False)])
+def test_device_walk_equals_host_walk(rela, D, F, sample_leaf, use_cfr):
+    """The self-play walk on the device (mt19937 streams, libstdc++ distributions, fp64 belief updates in kernels) emits the
+    same example stream, bit for bit, as the per-game host walk that uses std::mt19937 itself — 96 concurrent games, 12 waves,
+    zero net and fp32 net."""
+    from rebel_b200.models import flatten_state_dict, make_selfplay_net
+    w = torch.from_numpy(flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict()))
+    for net_mode, weights in ((0, None), (1, w)):
+        out = []
+        for host_walk in (1, 0):
+            cfg = make_cfg(rela, D, F, sample_leaf=sample_leaf, concurrent_games=96, net_mode=net_mode, state_dtype=0, host_walk=host_walk,
+                           subgame_params=dict(num_iters=16, max_depth=2, linear_update=True, use_cfr=use_cfr))
+            out.append(rela.run_selfplay_waves(cfg, 0, 11, 12, weights))
+        (qh, vh), (qd, vd) = out
+        assert qh.shape == qd.shape == (12 * 2 * 96, game_dims(D, F)[2])
+        assert torch.equal(qh, qd) and torch.equal(vh, vd), (net_mode, int((qh != qd).sum()), int((vh != vd).sum()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,F", [(1, 4), (2, 3)])
+def test_every_game_of_a_wave_replays_a_reference_runner(rela, port, D, F):
+    """Game g of a loop seeded with s consumes the generator seed s + 10^6 g in the reference's draw order: its example stream
+    equals RlRunner(seed = s + 10^6 g) — checked against the oracle port (itself pinned bit-exact to the compiled reference's
+    RlRunner) for several games of one device-side wave loop, zero net."""
+    K, waves, iters, s = 8, 10, 24, 5
+    cfg = make_cfg(rela, D, F, sample_leaf=True, concurrent_games=K, net_mode=0, state_dtype=0,
+                   subgame_params=dict(num_iters=iters, max_depth=2, linear_update=True, use_cfr=True))
+    q, v = rela.run_selfplay_waves(cfg, 0, s, waves)
+    q = q.numpy().reshape(waves, K, 2, -1); v = v.numpy().reshape(waves, K, 2, -1)
+    for g in (0, 3, 7):
+        rq, rv = port.rl_runner(D, F, s + 1000000 * g, n_games=waves, num_iters=iters, cap=4 * waves * 2 * 8)
+        n = waves * 2
+        assert len(rq) >= n
+        assert np.array_equal(q[:, g].reshape(n, -1), rq[:n]) and np.array_equal(v[:, g].reshape(n, -1), rv[:n]), g
+
+
+@pytest.mark.gpu
+def test_replay_rows_live_on_the_device(rela, tmp_path):
+    """with a CUDA device the rows of the ring are in HBM; batches are gathered on the device into the tensors
+    sample() returns; host round trips only for save / extract / cpu batches.  Same ring semantics as on the host."""
+    Q, H = 27, 6
+    r = rela.ValuePrioritizedReplay(capacity=100, seed=1, alpha=1.0, beta=0.4, prefetch=3, use_priority=False, compressed_values=False)
+    assert r.storage_device() == -2
+    q = torch.arange(120 * Q, dtype=torch.float32).reshape(120, Q)
+    v = torch.arange(120 * H, dtype=torch.float32).reshape(120, H)
+    r.push([q, v, torch.ones(120)])
+    assert r.storage_device() >= 0 and r.size() == 120
+    for dev in ("cuda:0", "cpu"):
+        batch, w = r.sample(64, dev)
+        assert batch.query.device.type == ("cuda" if dev != "cpu" else "cpu")
+        rows = (batch.query[:, 0] / Q).long().cpu()
+        assert torch.equal(batch.query.cpu(), q[rows]) and torch.equal(batch.values.cpu(), v[rows])
+    assert r.size() == 100                                               # sampling evicted down to capacity
+    r.push([q[:25].cuda(), v[:25].cuda(), torch.ones(25)])               # CUDA tensors are appended device to device; the ring wraps
+    assert r.size() == 125
+    path = str(tmp_path / "dump.bin")
+    r.save(path)
+    r2 = rela.ValuePrioritizedReplay(1000, 2, 1.0, 0.4, 0, False, False)
+    r2.load(path, 1.0, -1, 1)
+    ex = r2.extract()
+    want_q = torch.cat([q[20:120], q[:25]]); want_v = torch.cat([v[20:120], v[:25]])
+    assert torch.equal(ex[0], want_q) and torch.equal(ex[1], want_v)
+    # many batches on the consumer's stream without synchronising in between, while a producer keeps overwriting the ring
+    r3 = rela.ValuePrioritizedReplay(64, 3, 1.0, 0.4, 0, False, False)
+    r3.push([q[:64], v[:64], torch.ones(64)])
+    got = []
+    for i in range(40):
+        b, _ = r3.sample(32, "cuda:0")
+        got.append(b)
+        r3.push([q[i:i + 8], v[i:i + 8], torch.ones(8)])
+    torch.cuda.synchronize()
+    for b in got:
+        rows = (b.query[:, 0] / Q).long().cpu()
+        assert torch.equal(b.query.cpu(), q[rows]) and torch.equal(b.values.cpu(), v[rows])
