@@ -623,35 +623,46 @@ def run_datagen(args):
     # ================= end to end through the reference-facing `rela` module with host buffers (`e2e`) =================
     ref_model = [torch.jit.script(make_selfplay_net(D, F, seed=0))]
     locker = rela.ModelLocker(ref_model, f"cuda:{local}")
-    replay = rela.ValuePrioritizedReplay(capacity=max(1 << 18, 16 * K), seed=10001 + rank, alpha=1.0, beta=1.0, prefetch=0, use_priority=False,
+    replay = rela.ValuePrioritizedReplay(capacity=max(1 << 18, 16 * K * world), seed=10001 + rank, alpha=1.0, beta=1.0, prefetch=0, use_priority=False,
                                          compressed_values=False)
+    if world > 1:
+        # one process per GPU: the library's own NCCL communicators (cfrb_comm_*): update_model = ncclBroadcast from rank 0, every
+        # wave's examples -> rank 0's device-resident replay by grouped send / recv from the generators' device buffers
+        ids = [rela.comm_unique_id(), rela.comm_unique_id()] if rank == 0 else [None, None]
+        dist.broadcast_object_list(ids, src=0)
+        comm_w = rela.Comm(ids[0], rank, world, local)
+        comm_x = rela.Comm(ids[1], rank, world, local)
+        locker.set_comm(comm_w, 0)
+        rela.set_example_comm(comm_x, 0)
+    loop = rela.create_cfr_thread(locker, replay, rela_cfg(rela, args, K, mode), rank * 1000)
     ctx = rela.Context()
-    ctx.push_env_thread(rela.create_cfr_thread(locker, replay, rela_cfg(rela, args, K, mode), rank * 1000))
+    ctx.push_env_thread(loop)
     ctx.start()
+    rows_per_wave = 2 * K * world if rank == 0 else 0          # rows a wave adds to THIS rank's replay (all ranks' rows land on rank 0)
 
-    def wait_adds(target, limit=300.0):
+    def wait_waves(target, limit=300.0):
         t0 = time.perf_counter()
-        while replay.num_add() < target:
+        while loop.waves < target:
             if ctx.error() or time.perf_counter() - t0 > limit:
                 raise RuntimeError(f"generator loop stalled: {ctx.error()}")
             time.sleep(0.0005)
-    wait_adds(2 * K * 3)                            # eager run, graph capture, replay
+    wait_waves(3)                                   # eager run, graph capture, replay
     barrier()
-    n0 = replay.num_add()
-    wait_adds(n0 + 1)                               # start at a wave boundary
-    n0 = replay.num_add()
+    w0 = loop.waves
+    wait_waves(w0 + 1)                              # start at a wave boundary
+    w0 = loop.waves
     t0 = time.perf_counter()
     for i in range(steps):
-        locker.update_model(net)                    # trainer -> generators: fresh weights from HOST memory (installed before the next wave)
-        wait_adds(n0 + 2 * K * (i + 1))
-        batch, _ = replay.sample(2 * K, "cpu" if world == 1 else f"cuda:{local}")   # the step's examples back to HOST memory
-        if world > 1:                               # generators -> rank 0's trainer: NCCL gather of the device-resident batch, then the host read
-            blk = torch.cat([batch.query, batch.values], 1)
-            out = [torch.empty_like(blk) for _ in range(world)] if rank == 0 else None
-            dist.gather(blk, out, dst=0)
-            blk = blk.cpu()
+        locker.update_model(net)                    # trainer -> generators: fresh weights from HOST memory (N > 1: + ncclBroadcast), installed before the next wave
+        wait_waves(w0 + i + 1)
+        if rank == 0:
+            batch, _ = replay.sample(rows_per_wave, "cpu")     # the step's examples (of all ranks) back to HOST memory
     t1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
     ctx.terminate()
+    if world > 1:
+        rela.set_example_comm(None, 0)
     while not ctx.terminated():
         time.sleep(0.01)
     barrier()
@@ -659,7 +670,7 @@ def run_datagen(args):
     e2e_value = world * K * iters * steps / (ms_e2e * 1e-3)
     Qp = (Q + 1 + 15) // 16 * 16
     h2d = 256 * Qp * 2 + 256 * 256 * 2 + 16 * 256 * 2 + 128 * 16 * 2 + 256 * 16 * 2 + 2 * 256 * 8 + 64 if is_tc else nflat * 4
-    d2h = 2 * K * (Q + H) * 4
+    d2h = 2 * K * world * (Q + H) * 4               # rank 0 reads every rank's rows
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -708,8 +719,9 @@ def run_datagen(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / steps,
                 "api": "rela.ModelLocker.update_model (weights from host memory) + rela.create_cfr_thread / Context (generator loop) + "
-                       "rela.ValuePrioritizedReplay.sample(2K, 'cpu') (the step's examples to host memory)" + ("; NCCL gather of the batch to rank 0" if world > 1 else ""),
-                "timing": "wall clock between wave boundaries observed through replay.num_add(), device idle-synchronised before and after, max over ranks"},
+                       "rela.ValuePrioritizedReplay.sample(rows of the step, 'cpu') (the step's examples to host memory)" +
+                       ("; N > 1: weights by ncclBroadcast, every rank's examples to rank 0's device-resident replay by ncclSend/Recv (cfrb_comm_*)" if world > 1 else ""),
+                "timing": "wall clock between wave boundaries of the generator loop, device idle-synchronised before and after, max over ranks"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
@@ -757,6 +769,11 @@ def run_config5(args):
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
+    comm = None
+    if dist:
+        ids = [rela.comm_unique_id()] if rank == 0 else [None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = rela.Comm(ids[0], rank, world, local)
     seed0 = rank * per_rank
     for i in range(max(1, min(args.warmup, 2))):
         rela.recursive_eval_sampled(cfg, local, min(per_step, 8), seed0, per_step, args.subgames, wt)
@@ -769,8 +786,8 @@ def run_config5(args):
         s_, r_ = r["summed_strategy"].to(dev), r["summed_reach"].to(dev)
         acc_s = s_ if acc_s is None else acc_s + s_
         acc_r = r_ if acc_r is None else acc_r + r_
-    if dist:                                        # the reference sums in strategy_id order on one thread; here ranks are reduced by NCCL
-        dist.reduce(acc_s, dst=0); dist.reduce(acc_r, dst=0)
+    if dist:                                        # the reference sums in strategy_id order on one thread; here ranks are reduced by NCCL (cfrb_comm_reduce_sum)
+        comm.reduce_sum(acc_s.contiguous(), 0); comm.reduce_sum(acc_r.contiguous(), 0)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     barrier()

@@ -255,6 +255,28 @@ int cfrb_dev_alloc(int32_t device, size_t bytes, void** out);
 int cfrb_dev_free(int32_t device, void* p);
 int cfrb_dev_to_host(int32_t device, void* dst, const void* src, size_t bytes);
 
+/* ---- One process per GPU: the two hand-overs the reference performs through shared host memory inside ONE process become NCCL
+ * collectives over NVLink, issued by this library on device buffers (no torch.distributed, no host bounce):
+ *   ModelLocker::updateModel (rela/model_locker.h:69-79)         -> cfrb_comm_broadcast_weights
+ *   PrioritizedReplay::add   (rela/prioritized_replay.h:247-261) -> cfrb_comm_gather_rows into the trainer rank's device rows
+ *   recursive_eval's float32 accumulation (recursive_eval.cc:343-363) -> cfrb_comm_reduce_sum
+ * The 128-byte id is created on one rank (cfrb_comm_unique_id) and handed to the others by the launcher (e.g. through the
+ * torchrun store); every function is a collective: all ranks of the communicator call it, in the same order. */
+typedef struct cfrb_comm cfrb_comm;
+int cfrb_comm_unique_id(uint8_t* out128);
+int cfrb_comm_create(const uint8_t* id128, int32_t rank, int32_t world, int32_t device, cfrb_comm** out);
+int cfrb_comm_destroy(cfrb_comm* c);
+int cfrb_comm_rank(const cfrb_comm* c);
+int cfrb_comm_world(const cfrb_comm* c);
+/* flat fp32 weights (cfrb_set_weights layout): read from the root's host buffer, written to every other rank's host buffer. */
+int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_t root);
+/* every rank contributes n rows from DEVICE buffers dev_q [n][q_dim], dev_v [n][v_dim]; on the root they arrive in rank order in
+ * the DEVICE buffers recv_q [world * n][q_dim], recv_v [world * n][v_dim] (ignored elsewhere). */
+int cfrb_comm_gather_rows(cfrb_comm* c, const float* dev_q, const float* dev_v, int32_t n, int32_t q_dim, int32_t v_dim, float* recv_q,
+                          float* recv_v, int32_t root);
+/* in-place float32 sum over the ranks of a DEVICE buffer, result on the root. */
+int cfrb_comm_reduce_sum(cfrb_comm* c, float* dev_buf, size_t n, int32_t root);
+
 #ifdef __cplusplus
 }
 #endif

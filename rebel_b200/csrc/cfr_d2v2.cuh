@@ -24,18 +24,6 @@
 
 namespace cfrb {
 
-// Correctly rounded x / b given y = RN(1 / b) (a true division): q0 = x y is within 2 ulp; the first residual step makes it
-// faithful, the second one correctly rounded (Markstein's theorem; exhaustively cross-checked against `/` by
-// tests/test_gpu_parity.py::test_fast_division_is_correctly_rounded).  Operands here are regrets in [1e-80, ~1e3] and their sums.
-__device__ __forceinline__ double div_by_rcp(double x, double b, double y) {
-  double q = x * y;
-  double r = fma(-q, b, x);
-  q = fma(r, y, q);
-  r = fma(-q, b, x);
-  return fma(r, y, q);
-}
-__device__ __forceinline__ float div_by_rcp(float x, float b, float y) { (void)y; return x / b; }
-
 __device__ __forceinline__ uint32_t d2v2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void d2v2_bulk(void* smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d2v2_smem_u32(smem_dst)),
@@ -71,14 +59,17 @@ struct D2v2Layout {
   }
 };
 
-template <typename real, int HC>
-__global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int n1max) {
+// GT = threads per subgame (= per CTA): 32, 64 or 128.  More threads shorten every phase of the one subgame the CTA owns (its
+// staged tables are shared), at the price of idle lanes in the short phases.
+template <typename real, int HC, int GT>
+__global__ void __launch_bounds__(GT, 8) cfr_iter_d2v2_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int n1max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   asm volatile("griddepcontrol.launch_dependents;");
   const int lane = threadIdx.x;
   const int k = blockIdx.x;
   if (k >= *p.wave_n) return;
-  constexpr int G = 32;
+  constexpr int G = GT;
+  auto group_sync = [] { if (GT == 32) __syncwarp(); else __syncthreads(); };
   constexpr int kAl = 16 / (int)sizeof(real);          // elements per 16 bytes
   const int H = HC > 0 ? HC : p.H;
   const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
@@ -114,6 +105,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  group_sync();
   // the previous kernels' outputs (value-net rows; tables written by the previous CFR launch) are read from here on
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (lane == 0) {
@@ -145,7 +137,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
     while (!done)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
   }
-  __syncwarp();
+  group_sync();
   const real* rsv = rs - ra;                           // rsv[e * H + h] for the staged edges
   const real* ssv = ss - ra;
 
@@ -165,7 +157,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
         val[term[z] * H + h] = vt_s[it];
       }
     }
-    __syncwarp();
+    group_sync();
     // ---- bottom-up (update_regrets :538-575): level-1 node values, then the root
     if (lv.n2e > lv.n1e) {
       for (int it = lane; it < n1 * H; it += G) {
@@ -178,7 +170,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
         else        { for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h]; }
         val[n * H + h] = v;
       }
-      __syncwarp();
+      group_sync();
       if (!mine0) {   // new regrets of the level-1 actions, kept in the child's slot
         for (int it = lane; it < (lv.n2e - lv.n1e) * H; it += G) {
           const int c = lv.n1e + it / H, h = it % H;
@@ -192,7 +184,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
       else       { for (int n = 1; n <= n1; ++n) v += val[n * H + h]; }
       val[h] = v;
     }
-    __syncwarp();
+    group_sync();
     if (mine0) {
       for (int it = lane; it < n1 * H; it += G) {
         const int n = 1 + it / H, h = it % H;
@@ -217,7 +209,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
         strat = rpow(ns / (ns + 1), p.dcfr_gamma);
       }
     }
-    __syncwarp();
+    group_sync();
     // ---- regret matching (:619-634): per acting (node, hand) the sum of max(R, 1e-80) and its reciprocal
     real* rcp = rs;                                      // the staged regrets are dead: reuse the region, indexed like val's parents
     const real* bt = bel + trav * H;
@@ -236,7 +228,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
       val[n * H + h] = sum;
       rcp[n * H + h] = (real)1 / sum;
     }
-    __syncwarp();
+    group_sync();
     // ---- new strategy, regret discount and sum-strategy update (:639-661) on the traverser's level; the child's slot receives
     // belief * new strategy = the traverser's reach under the new strategy (:636-638), which the forward half reuses
     for (int it = lane; it < (ce - cb) * H; it += G) {
@@ -251,7 +243,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
       val[c * H + h] = rn * sg;
     }
     if (lane == 0) p.steps[2 * k + trav] = s + 1;
-    __syncwarp();
+    group_sync();
   }
   // ---- sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
   if (p.sg_act_iter[k] == iter) {
@@ -271,7 +263,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
     const real* b1 = bel + (1 - rp) * H;
     for (int it = lane; it < (lv.n2e - lv.n1e) * H; it += G) val[lv.n1e * H + it] = b1[it % H] * sgs[n1 * H + it];
   }
-  __syncwarp();
+  group_sync();
   // Reach rows: the root player's reach at a level-2 node is its parent's level-1 slot, the other player's is the node's own
   // slot; at a level-1 node the root player's is the node's slot, the other player's is its root belief.
   real* hist = reinterpret_cast<real*>(io + Lo.io_hist);
@@ -294,7 +286,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
       qpar[i * H + h] = __float2half_rn(f);
     }
   }
-  __syncwarp();
+  group_sync();
   // ---- pseudo-leaves: the other player's sums, the scaler (sum of the opponent's reach, :264-268) and its fp16 columns
   for (int r = lane; r < t.L; r += G) {
     const int n = pleaf[r];
@@ -310,7 +302,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
       qown[r * H + h] = __float2half_rn(f);
     }
   }
-  __syncwarp();
+  group_sync();
   // ---- query rows (write_query_to :104-123), fp16 tile in UMMA K-major core-matrix order, one 16-byte store per (row, 8
   // columns): constant columns from the per-template table, flags, and the two belief blocks from the fp16 values above
   const int leaf_player = rp ^ ((t.levels - 1) & 1);
@@ -376,7 +368,7 @@ __global__ void __launch_bounds__(32, 16) cfr_iter_d2v2_kernel(CfrDev<real> p, i
     for (int m = 0; m < kMaxBins; ++m) hist[z * (kMaxBins + 1) + m] = cnt[m];
     hist[z * (kMaxBins + 1) + kMaxBins] = tot;
   }
-  __syncwarp();
+  group_sync();
   for (int it = lane; it < t.T * H; it += G) {
     const int z = it / H, h = it % H;
     const int pbid = term[t.T + z];

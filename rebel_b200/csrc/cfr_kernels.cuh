@@ -63,6 +63,19 @@ __device__ __forceinline__ float query_value(const CfrDev<real>& p, int q, int l
   return q == 2 + A + 2 * H ? 1.f : 0.f;
 }
 
+// Correctly rounded x / b given y = RN(1 / b) (a true division): q0 = x y is within 2 ulp; the first residual step makes it
+// faithful, the second one correctly rounded (Markstein) — the same bits as `/` at a tenth of the instructions of an fp64
+// division; cross-checked against `/` on 4.3e9 operand pairs by tests/test_gpu_parity.py::test_fast_division_is_correctly_rounded.
+// Operands here are regrets in [1e-80, ~1e3] and their sums over at most A actions.
+__device__ __forceinline__ double div_by_rcp(double x, double b, double y) {
+  double q = x * y;
+  double r = fma(-q, b, x);
+  q = fma(r, y, q);
+  r = fma(-q, b, x);
+  return fma(r, y, q);
+}
+__device__ __forceinline__ float div_by_rcp(float x, float b, float y) { (void)y; return x / b; }
+
 // Forward half of iteration `iter`: reach, query rows + scalers for pseudo-leaves, payoffs for terminals.
 template <typename real, int G, int HC>
 __device__ void cfr_forward(const CfrDev<real>& p, int k, int trav, real* reach0, real* reach1, int have, real* lsum, real* hist, int lane) {
@@ -471,46 +484,70 @@ __global__ void __launch_bounds__(512) cfr_iter_kernel(CfrDev<real> p, int iter,
 struct D2Levels {
   int n1b, n1e, n2e;   // level 1 = [n1b, n1e), level 2 = [n1e, n2e) (empty when the template has two levels)
 };
-__device__ __forceinline__ D2Levels d2_levels(const int* __restrict__ level_begin, const TemplateDev& t) {
+// One tree template, packed into bytes (every depth-2 template has at most 255 nodes) so that a warp copies the whole thing into
+// shared memory with a single coalesced round trip at kernel entry; every parent / child / leaf-list lookup of the phases is
+// then a shared-memory byte load instead of a dependent global load (the "shared-memory staging of the tree's child-index
+// arrays").  Layout (cfrb_api.cu builds it): 16-byte header {N, L, T, levels, n1e, n2e, -, -, qconst_off:int32, -}, then
+// parent[N] child_begin[N] nchild[N] last_bid+1[N] pleaf[L] term[3][T] matches[H*F].
+struct D2Tmpl {
+  int N, L, T, levels, qconst_off;
+  const unsigned char *parent, *child_begin, *nchild, *bid1, *pleaf, *term, *matches;
+};
+__device__ __forceinline__ D2Tmpl d2_tmpl_view(const unsigned char* b, int HF) {
+  D2Tmpl t;
+  t.N = b[0]; t.L = b[1]; t.T = b[2]; t.levels = b[3];
+  t.qconst_off = *reinterpret_cast<const int*>(b + 8);
+  t.parent = b + 16; t.child_begin = t.parent + t.N; t.nchild = t.child_begin + t.N; t.bid1 = t.nchild + t.N;
+  t.pleaf = t.bid1 + t.N; t.term = t.pleaf + t.L; t.matches = t.term + 3 * t.T;
+  (void)HF;
+  return t;
+}
+__device__ __forceinline__ D2Levels d2_levels(const int* __restrict__ level_begin, const TemplateDev& t) {   // from the int arrays (cfr_d2v2.cuh)
   D2Levels L;
   L.n1b = level_begin[t.level_off + 1];
   L.n1e = t.levels >= 2 ? level_begin[t.level_off + 2] : L.n1b;
   L.n2e = t.levels >= 3 ? level_begin[t.level_off + 3] : L.n1e;
   return L;
 }
+__device__ __forceinline__ D2Levels d2_levels(const unsigned char* b) {
+  D2Levels L;
+  L.n1b = 1; L.n1e = b[4]; L.n2e = b[5];
+  return L;
+}
 // Row [H] of reach probabilities of `player` at node n (level 1 or 2) in the d2 scratch.
-template <typename real>
-__device__ __forceinline__ const real* d2_reach_row(const real* slot, const real* bel, const int* __restrict__ parent, int n, int n1e,
+template <typename real, typename PT>
+__device__ __forceinline__ const real* d2_reach_row(const real* slot, const real* bel, const PT* parent, int n, int n1e,
                                                     int player, int rp, int H) {
   if (n < n1e) return player == rp ? slot + n * H : bel + player * H;           // level 1
   return player == rp ? slot + parent[n] * H : slot + n * H;                    // level 2
 }
 
 template <typename real, int HC>
-__device__ void cfr_backward_d2(const CfrDev<real>& p, int k, int trav, real* val, const real* bel, int lane) {
+__device__ void cfr_backward_d2(const CfrDev<real>& p, const D2Tmpl& t, const D2Levels& lv, int k, int trav, real* val, const real* bel, real* rcp, int lane) {
   constexpr int G = 32;
-  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int H = HC > 0 ? HC : p.H;
   const int rp = p.sg_player[k];
   real* R = p.R + (size_t)k * p.table_stride;
   real* Sg = p.Sg + (size_t)k * p.table_stride;
   real* S = p.S + (size_t)k * p.table_stride;
-  const int* __restrict__ parent = p.parent + t.node_off;
-  const int* __restrict__ nchild = p.nchild + t.node_off;
-  const int* __restrict__ child_begin = p.child_begin + t.node_off;
+  const unsigned char* parent = t.parent; const unsigned char* nchild = t.nchild; const unsigned char* child_begin = t.child_begin;
   const int row0 = p.sg_row_off[k];
-  const D2Levels lv = d2_levels(p.level_begin, t);
   const bool mine0 = rp == trav;          // traverser acts at the root (else at level 1)
   // leaf values = (float)(net(query) * scaler) (subgame_solving.cc:266-282); terminals from the forward half
+  // Table / value-net reads go through the read-only path (ld.global.nc): none of these locations is read again after this
+  // launch writes it, and without possible aliasing against the stores the unrolled loops keep several loads in flight per lane
+  // instead of one dependent L2 / HBM round trip per iteration (the ncu profile of round 1: 7 warps per issue on long_scoreboard).
+#pragma unroll 4
   for (int it = lane; it < t.L * H; it += G) {
     const int r = it / H, h = it % H;
-    const int n = p.pleaf_node[t.pleaf_off + r];
-    val[n * H + h] = p.use_net ? (real)(float)((real)p.net_out[(size_t)(row0 + r) * p.Hout + h] * p.scaler[row0 + r]) : (real)0;
+    const int n = t.pleaf[r];
+    val[n * H + h] = p.use_net ? (real)(float)((real)__ldg(p.net_out + (size_t)(row0 + r) * p.Hout + h) * __ldg(p.scaler + row0 + r)) : (real)0;
   }
   const real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
+#pragma unroll 4
   for (int it = lane; it < t.T * H; it += G) {
     const int z = it / H, h = it % H;
-    val[p.term_node[t.term_off + z] * H + h] = vt[z * H + h];
+    val[t.term[z] * H + h] = __ldg(vt + z * H + h);
   }
   __syncwarp();
   // ---- bottom-up (update_regrets :538-575): level-1 node values, then the root
@@ -521,21 +558,22 @@ __device__ void cfr_backward_d2(const CfrDev<real>& p, int k, int trav, real* va
       if (!nc) continue;
       const int c0 = child_begin[n];
       real v = 0;
-      if (!mine0) { for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h] * Sg[(c0 + j - 1) * H + h]; }
+      if (!mine0) { for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h] * __ldg(Sg + (c0 + j - 1) * H + h); }
       else        { for (int j = 0; j < nc; ++j) v += val[(c0 + j) * H + h]; }
       val[n * H + h] = v;
     }
     __syncwarp();
     if (!mine0) {   // new regrets of the level-1 actions, kept in the child's slot
+#pragma unroll 4
       for (int it = lane; it < (lv.n2e - lv.n1e) * H; it += G) {
         const int c = lv.n1e + it / H, h = it % H;
-        val[c * H + h] = (R[(c - 1) * H + h] + val[c * H + h]) - val[parent[c] * H + h];
+        val[c * H + h] = (__ldg(R + (c - 1) * H + h) + val[c * H + h]) - val[parent[c] * H + h];
       }
     }
   }
   for (int h = lane; h < H; h += G) {
     real v = 0;
-    if (mine0) { for (int n = lv.n1b; n < lv.n1e; ++n) v += val[n * H + h] * Sg[(n - 1) * H + h]; }
+    if (mine0) { for (int n = lv.n1b; n < lv.n1e; ++n) v += val[n * H + h] * __ldg(Sg + (n - 1) * H + h); }
     else       { for (int n = lv.n1b; n < lv.n1e; ++n) v += val[n * H + h]; }
     val[h] = v;
   }
@@ -543,7 +581,7 @@ __device__ void cfr_backward_d2(const CfrDev<real>& p, int k, int trav, real* va
   if (mine0) {
     for (int it = lane; it < (lv.n1e - lv.n1b) * H; it += G) {
       const int n = lv.n1b + it / H, h = it % H;
-      val[n * H + h] = (R[(n - 1) * H + h] + val[n * H + h]) - val[h];
+      val[n * H + h] = (__ldg(R + (n - 1) * H + h) + val[n * H + h]) - val[h];
     }
   }
   // ---- root value running mean (:579-590) and discounts (:592-617)
@@ -582,17 +620,20 @@ __device__ void cfr_backward_d2(const CfrDev<real>& p, int k, int trav, real* va
       sum += Eps<real>::kLiteral ? (r > Eps<real>::v ? r : Eps<real>::v) : rmax0(r);   // max(R, 1e-80) (:626-629)
     }
     val[n * H + h] = sum;
+    rcp[n * H + h] = (real)1 / sum;      // one true division per (node, hand); the per-action quotients below are derived from it
   }
   __syncwarp();
+#pragma unroll 4
   for (int it = lane; it < (ce - cb) * H; it += G) {
     const int c = cb + it / H, h = it % H;
     const int e = (c - 1) * H + h, par = parent[c];
+    const real s_old = __ldg(S + e);
     const real r = val[c * H + h], sum = val[par * H + h], rn = bt[h];
-    const real sg = Eps<real>::kLiteral ? (r > Eps<real>::v ? r : Eps<real>::v) / sum
+    const real sg = Eps<real>::kLiteral ? div_by_rcp(r > Eps<real>::v ? r : Eps<real>::v, sum, rcp[par * H + h])
                                         : (sum > 0 ? rmax0(r) / sum : (real)1 / nchild[par]);
     Sg[e] = sg;
     R[e] = r * (r > 0 ? pos : neg);
-    S[e] = S[e] * strat + rn * sg;
+    S[e] = s_old * strat + rn * sg;
     val[c * H + h] = rn * sg;
   }
   if (lane == 0) p.steps[2 * k + trav] = s + 1;
@@ -603,29 +644,25 @@ __device__ void cfr_backward_d2(const CfrDev<real>& p, int k, int trav, real* va
 // cfr_backward_d2.  The best-response flags (1 / 0) replace the children's values in place, then give way to the discounted
 // sums, and finally to belief x new average strategy = the reach the forward half needs (same `have` protocol as CFR).
 template <typename real, int HC>
-__device__ void fp_backward_d2(const CfrDev<real>& p, int k, int trav, real* val, const real* bel, int lane) {
+__device__ void fp_backward_d2(const CfrDev<real>& p, const D2Tmpl& t, const D2Levels& lv, int k, int trav, real* val, const real* bel, int lane) {
   constexpr int G = 32;
-  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int H = HC > 0 ? HC : p.H;
   const int rp = p.sg_player[k];
   real* Last = p.R + (size_t)k * p.table_stride;
   real* Avg = p.Sg + (size_t)k * p.table_stride;
   real* S = p.S + (size_t)k * p.table_stride;
-  const int* __restrict__ parent = p.parent + t.node_off;
-  const int* __restrict__ nchild = p.nchild + t.node_off;
-  const int* __restrict__ child_begin = p.child_begin + t.node_off;
+  const unsigned char* parent = t.parent; const unsigned char* nchild = t.nchild; const unsigned char* child_begin = t.child_begin;
   const int row0 = p.sg_row_off[k];
-  const D2Levels lv = d2_levels(p.level_begin, t);
   const bool mine0 = rp == trav;
   for (int it = lane; it < t.L * H; it += G) {
     const int r = it / H, h = it % H;
-    const int n = p.pleaf_node[t.pleaf_off + r];
+    const int n = t.pleaf[r];
     val[n * H + h] = p.use_net ? (real)(float)((real)p.net_out[(size_t)(row0 + r) * p.Hout + h] * p.scaler[row0 + r]) : (real)0;
   }
   const real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
   for (int it = lane; it < t.T * H; it += G) {
     const int z = it / H, h = it % H;
-    val[p.term_node[t.term_off + z] * H + h] = vt[z * H + h];
+    val[t.term[z] * H + h] = vt[z * H + h];
   }
   __syncwarp();
   // ---- bottom-up best response (BRSolver::compute_br :316-358): level 1, then the root
@@ -719,53 +756,103 @@ __device__ void fp_backward_d2(const CfrDev<real>& p, int k, int trav, real* val
 // have: level whose slots already hold the reach of the player acting above it (0: level-1 slots = reach_P0 valid,
 // 1: level-2 slots = reach_P1 valid, -1: neither).
 template <typename real, int HC>
-__device__ void cfr_forward_d2(const CfrDev<real>& p, int k, int trav, real* slot, const real* bel, int have, real* lsum, real* hist,
-                               int lane) {
+__device__ void cfr_forward_d2(const CfrDev<real>& p, const D2Tmpl& t, const D2Levels& lv, int k, int trav, real* slot, const real* bel, int have,
+                               real* aux, real* hist, int lane) {
   constexpr int G = 32;
-  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int H = HC > 0 ? HC : p.H;
   const int rp = p.sg_player[k];
   const real* Sg = p.Sg + (size_t)k * p.table_stride;     // not __restrict__/const-cached: written earlier in this launch
-  const int* __restrict__ parent = p.parent + t.node_off;
-  const D2Levels lv = d2_levels(p.level_begin, t);
+  const unsigned char* parent = t.parent;
   // ---- reach under Sg (compute_reach_probabilities, subgame_solving.cc:54-78): belief * strategy of the acting level
   if (have != 0) {
     const real* b0 = bel + rp * H;
+#pragma unroll 4
     for (int it = lane; it < (lv.n1e - lv.n1b) * H; it += G) {
       const int n = lv.n1b + it / H, h = it % H;
-      slot[n * H + h] = b0[h] * Sg[(n - 1) * H + h];
+      slot[n * H + h] = b0[h] * __ldg(Sg + (n - 1) * H + h);      // a level this launch did not write (see `have`)
     }
   }
   if (have != 1) {
     const real* b1 = bel + (1 - rp) * H;
+#pragma unroll 4
     for (int it = lane; it < (lv.n2e - lv.n1e) * H; it += G) {
       const int c = lv.n1e + it / H, h = it % H;
-      slot[c * H + h] = b1[h] * Sg[(c - 1) * H + h];
+      slot[c * H + h] = b1[h] * __ldg(Sg + (c - 1) * H + h);
     }
   }
   __syncwarp();
-  // ---- pseudo-leaves: normalisation sums + scaler (subgame_solving.cc:257-265)
+  // ---- pseudo-leaves (subgame_solving.cc:257-265, write_query_to :104-123).  All pseudo-leaves of a depth-2 tree sit on level 2:
+  // the root player's reach there is its parent's level-1 slot — the same row for every leaf under one level-1 node — so it is
+  // summed / normalised once per level-1 node; the other player's reach is the leaf's own slot.  The normalised beliefs are kept
+  // as fp16 (the precision of the query tiles) and the 16-byte chunks are assembled from them.
   const int row0 = p.sg_row_off[k];
-  for (int r = lane; r < t.L; r += G) {
-    const int n = p.pleaf_node[t.pleaf_off + r];
-    const real* r0 = d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H);
-    const real* r1 = d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H);
-    real s0 = 0, s1 = 0, e0 = 0, e1 = 0;
-    for (int h = 0; h < H; ++h) {
-      s0 += r0[h]; s1 += r1[h];                                              // vector_sum (:264)
-      e0 += r0[h] + Eps<real>::v; e1 += r1[h] + Eps<real>::v;               // normalize_probabilities_safe
+  const int n1 = lv.n1e - lv.n1b;
+  real* par_sum = aux;
+  real* par_inv = aux + p.n1max;
+  __half* qpar = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(aux) + ((2 * p.n1max * (int)sizeof(real) + 15) & ~15));
+  __half* qown = qpar + p.n1max * H;
+  const int opp = 1 - trav;
+  const bool have_l2 = lv.n2e > lv.n1e;
+  if (have_l2) {
+    for (int i = lane; i < n1; i += G) {
+      const real* r = slot + (1 + i) * H;
+      real s0 = 0, e0 = 0;
+      for (int h = 0; h < H; ++h) { s0 += r[h]; e0 += r[h] + Eps<real>::v; }                  // vector_sum (:264) / normalize_probabilities_safe
+      const real inv = (real)1 / e0;
+      par_sum[i] = s0; par_inv[i] = inv;
+      for (int h = 0; h < H; ++h) {
+        float f;
+        if (Eps<real>::kLiteral) f = (float)((r[h] + Eps<real>::v) * inv);                    // util.h:68-78
+        else f = isfinite(inv) ? (float)(r[h] * inv) : 1.f / H;
+        qpar[i * H + h] = __float2half_rn(f);
+      }
     }
-    lsum[2 * r] = (real)1 / e0; lsum[2 * r + 1] = (real)1 / e1;
-    p.scaler[row0 + r] = trav == 0 ? s1 : s0;
+    __syncwarp();
+    for (int r = lane; r < t.L; r += G) {
+      const int n = t.pleaf[r];
+      const real* ro = slot + n * H;
+      real s1 = 0, e1 = 0;
+      for (int h = 0; h < H; ++h) { s1 += ro[h]; e1 += ro[h] + Eps<real>::v; }
+      const real inv = (real)1 / e1;
+      p.scaler[row0 + r] = (opp == rp) ? par_sum[parent[n] - 1] : s1;                         // sum of the opponent's reach (:264-268)
+      for (int h = 0; h < H; ++h) {
+        float f;
+        if (Eps<real>::kLiteral) f = (float)((ro[h] + Eps<real>::v) * inv);
+        else f = isfinite(inv) ? (float)(ro[h] * inv) : 1.f / H;
+        qown[r * H + h] = __float2half_rn(f);
+      }
+    }
+  } else {
+    // two-level template (max_depth 1, or a root whose only children are leaves): the pseudo-leaves are level-1 nodes; the root
+    // player's reach is the node's slot, the other player's its root belief
+    for (int r = lane; r < t.L; r += G) {
+      const int n = t.pleaf[r];
+      const real* r0 = d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H);
+      const real* r1 = d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H);
+      real s0 = 0, s1 = 0, e0 = 0, e1 = 0;
+      for (int h = 0; h < H; ++h) { s0 += r0[h]; s1 += r1[h]; e0 += r0[h] + Eps<real>::v; e1 += r1[h] + Eps<real>::v; }
+      const real i0 = (real)1 / e0, i1 = (real)1 / e1;
+      p.scaler[row0 + r] = trav == 0 ? s1 : s0;
+      // qpar <- the root player's columns, qown <- the other player's, like on level 2 (one qpar row per leaf here)
+      const real* rr = rp == 0 ? r0 : r1; const real* ro = rp == 0 ? r1 : r0;
+      const real ir = rp == 0 ? i0 : i1, io_ = rp == 0 ? i1 : i0;
+      for (int h = 0; h < H; ++h) {
+        float fr, fo;
+        if (Eps<real>::kLiteral) { fr = (float)((rr[h] + Eps<real>::v) * ir); fo = (float)((ro[h] + Eps<real>::v) * io_); }
+        else { fr = isfinite(ir) ? (float)(rr[h] * ir) : 1.f / H; fo = isfinite(io_) ? (float)(ro[h] * io_) : 1.f / H; }
+        qpar[r * H + h] = __float2half_rn(fr);
+        qown[r * H + h] = __float2half_rn(fo);
+      }
+    }
   }
   __syncwarp();
-  // ---- query rows (write_query_to :104-123); all pseudo-leaves sit on the last level
+  // ---- query rows; all pseudo-leaves sit on the last level
   const int leaf_player = rp ^ ((t.levels - 1) & 1);
   const int Qp = p.Qpad;
   if (p.Xh != nullptr) {
     // fp16 tile in UMMA K-major core-matrix order, one 16-byte store per (row, 8 columns).  The constant columns (one-hot of
-    // the leaf's last bid, the 1 at column Q, zero padding) come from the per-template table qconst; only the acting player /
-    // traverser flags and the 2H belief columns are computed.
+    // the leaf's last bid, the 1 at column Q, zero padding) come from the per-template table qconst, the acting player /
+    // traverser flags are set here, the 2H belief columns are copied from the fp16 rows above.
     const int kc = Qp >> 3;
     const int qb0 = 2 + p.A, qb1 = qb0 + H, qb2 = qb1 + H;      // belief columns [qb0, qb1) player 0, [qb1, qb2) player 1
     const __half* __restrict__ qconst = p.qconst + t.qconst_off;
@@ -776,42 +863,39 @@ __device__ void cfr_forward_d2(const CfrDev<real>& p, int k, int trav, real* slo
       const int q0 = k8 * 8;
       if (q0 == 0) { c.h[0] = __float2half_rn((float)leaf_player); c.h[1] = __float2half_rn((float)trav); }
       if (q0 + 8 > qb0 && q0 < qb2) {
-        const int n = p.pleaf_node[t.pleaf_off + r];
-        const real* r0 = d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H);
-        const real* r1 = d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H);
-        const real s0 = lsum[2 * r], s1 = lsum[2 * r + 1];
+        const __half* rootp = have_l2 ? qpar + (parent[t.pleaf[r]] - 1) * H : qpar + r * H;   // player rp
+        const __half* other = qown + r * H;                                                                      // player 1 - rp
+        const __half* p0 = rp == 0 ? rootp : other;
+        const __half* p1 = rp == 0 ? other : rootp;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int q = q0 + j;
-          if (q >= qb0 && q < qb2) {
-            const bool first = q < qb1;
-            const real x = first ? r0[q - qb0] : r1[q - qb1];
-            const real sc = first ? s0 : s1;
-            float f;
-            if (Eps<real>::kLiteral) f = (float)((x + Eps<real>::v) * sc);              // util.h:68-78 (sc = 1 / sum)
-            else f = isfinite(sc) ? (float)(x * sc) : 1.f / H;
-            c.h[j] = __float2half_rn(f);
-          }
+          if (q >= qb0 && q < qb1) c.h[j] = p0[q - qb0];
+          else if (q >= qb1 && q < qb2) c.h[j] = p1[q - qb1];
         }
       }
       const int Rr = row0 + r, rr = Rr & 127;
       *reinterpret_cast<int4*>(p.Xh + (size_t)(Rr >> 7) * 128 * Qp + k8 * 1024 + (rr >> 3) * 64 + (rr & 7) * 8) = c.v;
     }
   } else if (p.X != nullptr) {
+    // fp32 parity net: the same columns in fp32 from the reach rows themselves
     for (int it = lane; it < t.L * Qp; it += G) {
       const int r = it / Qp, q = it % Qp;
-      const int n = p.pleaf_node[t.pleaf_off + r];
-      p.X[(size_t)(row0 + r) * Qp + q] =
-          query_value(p, q, leaf_player, trav, p.last_bid[t.node_off + n], d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H),
-                      d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H), lsum[2 * r], lsum[2 * r + 1]);
+      const int n = t.pleaf[r];
+      const real* r0 = d2_reach_row(slot, bel, parent, n, lv.n1e, 0, rp, H);
+      const real* r1 = d2_reach_row(slot, bel, parent, n, lv.n1e, 1, rp, H);
+      real e0 = 0, e1 = 0;
+      for (int h = 0; h < H; ++h) { e0 += r0[h] + Eps<real>::v; e1 += r1[h] + Eps<real>::v; }
+      p.X[(size_t)(row0 + r) * Qp + q] = query_value(p, q, leaf_player, trav, (int)t.bid1[n] - 1, r0, r1, (real)1 / e0, (real)1 / e1);
     }
   }
   // ---- terminals (compute_expected_terminal_values :80-98; win probability :765-789), as in cfr_forward
   constexpr int kMaxBins = 9;
   real* __restrict__ vt = p.vterm + (size_t)k * p.vterm_stride;
+  __syncwarp();      // hist shares the aux region with the fp16 belief columns the query rows were assembled from
   for (int z = lane; z < t.T; z += G) {
-    const int n = p.term_node[t.term_off + z];
-    const int face = p.term_node[t.term_off + t.T + z] % p.F;
+    const int n = t.term[z];
+    const int face = t.term[t.T + z] % p.F;
     const real* ro = d2_reach_row(slot, bel, parent, n, lv.n1e, 1 - trav, rp, H);
     real cnt[kMaxBins];
 #pragma unroll
@@ -819,7 +903,7 @@ __device__ void cfr_forward_d2(const CfrDev<real>& p, int k, int trav, real* slo
     real tot = 0;
     for (int g = 0; g < H; ++g) {
       const real r = ro[g];
-      const int mg = (int)p.matches[g * p.F + face];
+      const int mg = (int)t.matches[g * p.F + face];
       tot += r;
 #pragma unroll
       for (int m = 0; m < kMaxBins; ++m) cnt[m] += (m == mg) ? r : (real)0;
@@ -833,10 +917,10 @@ __device__ void cfr_forward_d2(const CfrDev<real>& p, int k, int trav, real* slo
   __syncwarp();
   for (int it = lane; it < t.T * H; it += G) {
     const int z = it / H, h = it % H;
-    const int pbid = p.term_node[t.term_off + t.T + z];
-    const int ndepth = p.term_node[t.term_off + 2 * t.T + z];
+    const int pbid = t.term[t.T + z];
+    const int ndepth = t.term[2 * t.T + z];
     const int quantity = 1 + pbid / p.F, face = pbid % p.F;
-    int left = quantity - (int)p.matches[h * p.F + face];
+    int left = quantity - (int)t.matches[h * p.F + face];
     left = left < 0 ? 0 : (left > kMaxBins - 1 ? kMaxBins - 1 : left);
     const real win = hist[z * (kMaxBins + 1) + left], tot = hist[z * (kMaxBins + 1) + kMaxBins];
     const real v = (real)(float)win * 2 - tot;
@@ -845,11 +929,10 @@ __device__ void cfr_forward_d2(const CfrDev<real>& p, int k, int trav, real* slo
   }
 }
 
-// Scratch of a d2 group (reals): slot[nh_max] | bel[2*H] | hist[tmp_reals] | lsum[2*Lmax]
+// Scratch of a d2 group (reals): slot[nh_max] | bel[2*H] | hist[tmp_reals] | aux (cfr_aux_bytes_d2)
 template <typename real, int HC>
 __global__ void __launch_bounds__(128, 8) cfr_iter_d2_kernel(CfrDev<real> p, int iter, int do_b, int do_f, int scratch_per_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  real* smem = reinterpret_cast<real*>(smem_raw);
   // Programmatic dependent launch: the value-net kernel that follows may be scheduled as soon as every CTA of this grid has
   // started (its weight-staging prologue then overlaps this grid's tail) ...
   asm volatile("griddepcontrol.launch_dependents;");
@@ -857,11 +940,22 @@ __global__ void __launch_bounds__(128, 8) cfr_iter_d2_kernel(CfrDev<real> p, int
   const int gid = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int k = blockIdx.x * groups_per_cta + gid;
   if (k >= *p.wave_n) return;
-  const TemplateDev t = p.tmpl[p.sg_tmpl[k]];
   const int H = HC > 0 ? HC : p.H;
-  real* slot = smem + (size_t)gid * scratch_per_group;
-  real* bel = slot + p.nh_max; real* hist = bel + 2 * H; real* lsum = hist + p.tmp_reals;
+  // per-group shared memory: [ template bytes (p.tpk_stride) | slot[nh_max] | bel[2*H] | aux ] ; the terminal histogram of the
+  // forward half aliases aux (the fp16 belief columns are dead once the query rows are written)
+  unsigned char* gbase = smem_raw + (size_t)gid * ((size_t)scratch_per_group * sizeof(real) + p.tpk_stride);
+  unsigned char* tb_s = gbase;
+  real* slot = reinterpret_cast<real*>(gbase + p.tpk_stride);
+  real* bel = slot + p.nh_max; real* aux = bel + 2 * H; real* hist = aux;
+  {   // the subgame's template: one coalesced 16-byte-per-lane copy
+    const int4* src = reinterpret_cast<const int4*>(p.tpk + (size_t)p.sg_tmpl[k] * p.tpk_stride);
+    int4* dst = reinterpret_cast<int4*>(tb_s);
+    for (int i = lane; i < p.tpk_stride / 16; i += 32) dst[i] = __ldg(src + i);
+  }
   for (int i = lane; i < 2 * H; i += 32) bel[i] = p.beliefs[(size_t)k * 2 * H + i];
+  __syncwarp();
+  const D2Tmpl t = d2_tmpl_view(tb_s, H * p.F);
+  const D2Levels lv = d2_levels(tb_s);
   {
     // The wave's tables (3 x K x 4.3 KB at 1x6f) do not fit in L2 next to the query tiles, so every launch streams them from
     // HBM.  Ask for this subgame's lines now: the requests overlap the leaf-value phase instead of stalling the phases
@@ -871,7 +965,6 @@ __global__ void __launch_bounds__(128, 8) cfr_iter_d2_kernel(CfrDev<real> p, int
     const char* sg = reinterpret_cast<const char*>(p.Sg) + off;
     for (int i = lane; i < lines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(sg + ((size_t)i << 7)));
     if (do_b) {   // regrets and sum strategy: only the edges below the previous traverser's level are touched
-      const D2Levels lv = d2_levels(p.level_begin, t);
       const bool root_acts = p.sg_player[k] == ((iter - 1) & 1);
       const int e0 = (root_acts ? lv.n1b : lv.n1e) - 1, e1 = (root_acts ? lv.n1e : lv.n2e) - 1;
       const size_t b0 = (size_t)e0 * H * sizeof(real) & ~(size_t)127, b1 = (size_t)e1 * H * sizeof(real);
@@ -890,8 +983,8 @@ __global__ void __launch_bounds__(128, 8) cfr_iter_d2_kernel(CfrDev<real> p, int
   const int tb = (iter - 1) & 1;
   const int rp = p.sg_player[k];
   if (do_b) {
-    if (p.fp) fp_backward_d2<real, HC>(p, k, tb, slot, bel, lane);
-    else cfr_backward_d2<real, HC>(p, k, tb, slot, bel, lane);
+    if (p.fp) fp_backward_d2<real, HC>(p, t, lv, k, tb, slot, bel, lane);
+    else cfr_backward_d2<real, HC>(p, t, lv, k, tb, slot, bel, aux, lane);
   }
   // sampling-strategy snapshot for RlRunner (recursive_solving.cc:168-174): state after `iter` iterations
   if (p.sg_act_iter[k] == iter) {
@@ -899,7 +992,7 @@ __global__ void __launch_bounds__(128, 8) cfr_iter_d2_kernel(CfrDev<real> p, int
     real* __restrict__ Sn = p.Snap + (size_t)k * p.table_stride;
     for (int i = lane; i < (t.N - 1) * H; i += 32) Sn[i] = Sg[i];
   }
-  if (do_f) cfr_forward_d2<real, HC>(p, k, iter & 1, slot, bel, do_b ? (tb == rp ? 0 : 1) : -1, lsum, hist, lane);
+  if (do_f) cfr_forward_d2<real, HC>(p, t, lv, k, iter & 1, slot, bel, do_b ? (tb == rp ? 0 : 1) : -1, aux, hist, lane);
 }
 
 // Wave initialisation == CFR constructor (subgame_solving.cc:509-524): uniform last strategy, zero regrets,

@@ -21,6 +21,7 @@ struct CfrDev {
   const int* parent; const int* child_begin; const int* nchild; const int* last_bid;
   const int* level_begin; const int* pleaf_node; const int* term_node;
   const unsigned char* matches;   // [H][F] num_matches(hand, face), liars_dice.h:83-91
+  const unsigned char* tpk; int tpk_stride;   // packed byte templates (cfr_iter_d2_kernel): template i at tpk + i * tpk_stride
   const __half* qconst;           // per template [L][Qpad] fp16: constant part of the query rows (one-hot last bid, 1 at column Q)
   // wave
   const int* wave_n;              // [1] number of live subgames
@@ -37,7 +38,7 @@ struct CfrDev {
   real* scaler;                   // [rows] sum of opponent reach at the pseudo-leaf
   real* scratch; size_t scratch_stride;   // global scratch (CTA groups), reals per subgame
   int nh_max, tmp_reals;                  // scratch layout: bufA[nh_max] | bufB[nh_max] | tmp[tmp_reals] | lsum[2*Lmax]
-  int lmax, tmax;                         // largest pseudo-leaf / terminal count over the templates (cfr_iter_d2v2_kernel's layout)
+  int lmax, tmax, n1max;                  // largest pseudo-leaf / terminal / level-1 node count over the templates (depth <= 2 kernels' layouts)
   // params
   int linear, dcfr; real dcfr_alpha, dcfr_beta, dcfr_gamma;
   int use_net;
@@ -49,8 +50,20 @@ struct CfrDev {
 __host__ __device__ inline int cfr_tmp_reals(int N, int H, int L, int T) { (void)N; (void)H; (void)L; return 10 * (T > 0 ? T : 1); }
 __host__ __device__ inline int cfr_scratch_reals(int N, int H, int L, int T) { return 2 * N * H + cfr_tmp_reals(N, H, L, T) + 2 * (L > 0 ? L : 1); }
 
-// Depth <= 2 kernel (cfr_iter_d2_kernel): slot[N*H] | bel[2*H] | hist[10*T] | lsum[2*L]
-__host__ __device__ inline int cfr_scratch_reals_d2(int N, int H, int L, int T) { return N * H + 2 * H + cfr_tmp_reals(N, H, L, T) + 2 * (L > 0 ? L : 1); }
+// Depth <= 2 kernel (cfr_iter_d2_kernel): slot[N*H] | bel[2*H] | aux.  aux (bytes) serves the backward half as
+// rcp[(n1max + 1) * H] reals (reciprocals of the regret-matching sums) and the forward half first as par_sum[n1max] | par_inv[n1max]
+// reals followed by the fp16 belief columns qpar[n1max * H] | qown[L * H], then as the terminal histogram hist[10 * T] reals.
+__host__ __device__ inline int cfr_aux_bytes_d2(int sz, int H, int L, int T, int n1max) {
+  const int fwd = ((2 * n1max * sz + 15) & ~15) + (((n1max + (L > 0 ? L : 1)) * H * 2 + 15) & ~15);
+  const int bwd = (n1max + 1) * H * sz;
+  const int hist = 10 * (T > 0 ? T : 1) * sz;
+  int m = fwd > bwd ? fwd : bwd;
+  m = m > hist ? m : hist;
+  return (m + 15) & ~15;
+}
+__host__ __device__ inline int cfr_scratch_reals_d2(int sz, int N, int H, int L, int T, int n1max) {
+  return N * H + 2 * H + (cfr_aux_bytes_d2(sz, H, L, T, n1max) + sz - 1) / sz;
+}
 
 // Full-tree best response (br_kernel.cuh).  Arrays describe ONE full-depth tree rooted at the initial state.
 struct BrDev {
@@ -92,8 +105,8 @@ void rows_launch_gather(const float* src, int width, const int* ids, int n, floa
 // Generation-2 depth <= 2 kernel (cfr_d2v2.cuh): one warp per CTA, inputs staged by cp.async.bulk.
 template <typename real> cudaError_t cfr_configure_d2v2(int smem_bytes);
 template <typename real> int cfr_d2v2_smem_bytes(int Nmax, int H, int Hout, int Lmax, int Tmax, int n1max, int stride);
-template <typename real> void cfr_launch_iter_d2v2(const CfrDev<real>& p, int blocks, size_t smem, cudaStream_t st, int iter, int do_b, int do_f,
-                                                   int n1max);
+template <typename real> void cfr_launch_iter_d2v2(const CfrDev<real>& p, int blocks, int threads, size_t smem, cudaStream_t st, int iter,
+                                                   int do_b, int do_f, int n1max);
 // Development check of div_by_rcp (cfr_d2v2.cuh): n pseudo-random (x, b) pairs per call, returns the number of quotients that
 // differ from x / b in *mismatches (device pointer).
 void div_check_launch(unsigned long long seed, int blocks, unsigned long long* mismatches, cudaStream_t st);

@@ -79,7 +79,7 @@ struct cfrb_handle {
   int d2_groups_per_cta = 8;
   int d2_scratch_per_group = 0;
   bool d2v2 = false;       // cfr_iter_d2v2_kernel (CFR solver, depth <= 2): one warp per CTA, inputs staged by cp.async.bulk
-  int d2v2_smem = 0, n1max = 0;
+  int d2v2_smem = 0, n1max = 0, d2v2_threads = 32;
   int table_stride = 0;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr;
@@ -106,6 +106,8 @@ struct cfrb_handle {
     size_t scratch_stride = 0;
   } br;
   DevBuf<__half> d_qconst;
+  DevBuf<unsigned char> d_tpk;   // byte-packed templates for the depth <= 2 kernel
+  int tpk_stride = 0;
   // device: wave (untyped part)
   DevBuf<int> d_wave;      // [0] = n, [1] = rows
   DevBuf<int> d_sg_tmpl, d_sg_player, d_sg_row_off, d_sg_act, d_steps;
@@ -118,6 +120,12 @@ struct cfrb_handle {
   // device: weights
   DevBuf<float> d_w;
   DevBuf<uint8_t> d_blob;
+  // weight upload without stalling the generator pipeline: two pinned staging buffers, stream-ordered copies on own_stream
+  uint8_t* w_stage[2] = {nullptr, nullptr};
+  size_t w_stage_bytes = 0;
+  cudaEvent_t w_ev[2] = {nullptr, nullptr};
+  int w_slot = 0;
+  cudaEvent_t w_last = nullptr;      // completion of the most recent upload (waited for by runs on other streams)
   cfrb::NetDev net{};
   bool have_weights = false;
   uint64_t weights_version = 0;
@@ -178,20 +186,22 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
     const int smem_bytes = (int)(per_group_bytes * h->groups_per_cta);
     CK(cfrb::cfr_configure<real>(32, smem_bytes));
     const char* no_d2 = std::getenv("CFRB_NO_D2");
-    if (h->max_levels <= 3 && !(no_d2 && *no_d2 == '1')) {
+    if (h->max_levels <= 3 && h->tpk_stride > 0 && !(no_d2 && *no_d2 == '1')) {
       // 32 warps per SM (register file: 64 registers x 32 warps) as 8 CTAs of 4 warps: small CTAs even out the last round
       // (8192 subgames on 4736 warp slots = 1.73 rounds); each CTA has 1 KB of shared memory reserved by the runtime
       h->d2 = true;
-      h->d2_scratch_per_group = cfrb::cfr_scratch_reals_d2(h->Nmax, h->g.H, h->Lmax, h->Tmax);
-      const size_t d2_bytes = (size_t)h->d2_scratch_per_group * sizeof(real);
+      h->d2_scratch_per_group = cfrb::cfr_scratch_reals_d2((int)sizeof(real), h->Nmax, h->g.H, h->Lmax, h->Tmax, h->n1max);
+      const size_t d2_bytes = (size_t)h->d2_scratch_per_group * sizeof(real) + h->tpk_stride;
       const size_t cta_budget = ((size_t)228 * 1024 - 8 * 1024) / 8;
       h->d2_groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(4, cta_budget / d2_bytes));
       if (const char* e = std::getenv("CFRB_D2_GROUPS")) h->d2_groups_per_cta = std::max(1, std::min(h->d2_groups_per_cta, std::atoi(e)));
       CK(cfrb::cfr_configure_d2<real>((int)(d2_bytes * h->d2_groups_per_cta)));
       const char* gen = std::getenv("CFRB_D2_GEN");
       h->d2v2_smem = cfrb::cfr_d2v2_smem_bytes<real>(h->Nmax, g.H, h->Hout, std::max(h->Lmax, 1), std::max(h->Tmax, 1), h->n1max, h->table_stride);
-      h->d2v2 = h->cfg.solver == CFRB_SOLVER_CFR && !(gen && *gen == '1') && h->d2v2_smem <= max_optin;
+      // generation 2 (cfr_d2v2.cuh) is opt-in (CFRB_D2_GEN=2): measured slower than the 32-warps-per-SM kernel
+      h->d2v2 = h->cfg.solver == CFRB_SOLVER_CFR && h->cfg.max_depth == 2 && gen && *gen == '2' && h->d2v2_smem <= max_optin;
       if (h->d2v2) CK(cfrb::cfr_configure_d2v2<real>(h->d2v2_smem));
+      if (const char* e = std::getenv("CFRB_D2V2_THREADS")) { const int v = std::atoi(e); if (v == 32 || v == 64 || v == 128) h->d2v2_threads = v; }
     }
   } else {
     h->group = 256;
@@ -203,11 +213,12 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
   d.tmpl = h->d_tmpl.p; d.parent = h->d_parent.p; d.child_begin = h->d_child_begin.p; d.nchild = h->d_nchild.p;
   d.last_bid = h->d_last_bid.p; d.level_begin = h->d_level_begin.p; d.pleaf_node = h->d_pleaf_node.p;
   d.term_node = h->d_term_node.p; d.matches = h->d_matches.p; d.qconst = h->d_qconst.p;
+  d.tpk = h->d_tpk.p; d.tpk_stride = h->tpk_stride;
   d.wave_n = h->d_wave.p; d.sg_tmpl = h->d_sg_tmpl.p; d.sg_player = h->d_sg_player.p; d.sg_row_off = h->d_sg_row_off.p;
   d.sg_act_iter = h->d_sg_act.p; d.beliefs = s.beliefs.p; d.mu = s.mu.p; d.steps = h->d_steps.p;
   d.R = s.R.p; d.Sg = s.Sg.p; d.S = s.S.p; d.Snap = s.Snap.p; d.table_stride = h->table_stride;
   d.vterm = s.vterm.p; d.vterm_stride = vterm_stride;
-  d.lmax = std::max(h->Lmax, 1); d.tmax = std::max(h->Tmax, 1);
+  d.lmax = std::max(h->Lmax, 1); d.tmax = std::max(h->Tmax, 1); d.n1max = h->n1max;
   d.X = h->cfg.net_mode == CFRB_NET_FP32 ? h->d_X.p : nullptr;
   d.Xh = is_tc(h->cfg.net_mode) ? h->d_Xh.p : nullptr;
   d.net_out = h->d_out.p; d.scaler = s.scaler.p;
@@ -236,10 +247,10 @@ static int launch_iter_t(cfrb_handle* h, cudaStream_t st, int iter, int do_b, in
   auto& s = state_of<real>(h);
   const int nsg = h->capturing ? h->cfg.max_subgames : h->n;   // surplus groups return at once (k >= *wave_n)
   if (h->d2 && h->d2v2) {
-    cfrb::cfr_launch_iter_d2v2<real>(s.dev, nsg, (size_t)h->d2v2_smem, st, iter, do_b, do_f, h->n1max);
+    cfrb::cfr_launch_iter_d2v2<real>(s.dev, nsg, h->d2v2_threads, (size_t)h->d2v2_smem, st, iter, do_b, do_f, h->n1max);
   } else if (h->d2) {
     const int blocks = (nsg + h->d2_groups_per_cta - 1) / h->d2_groups_per_cta;
-    const size_t smem = (size_t)h->d2_scratch_per_group * sizeof(real) * h->d2_groups_per_cta;
+    const size_t smem = ((size_t)h->d2_scratch_per_group * sizeof(real) + h->tpk_stride) * h->d2_groups_per_cta;
     cfrb::cfr_launch_iter_d2<real>(s.dev, blocks, 32 * h->d2_groups_per_cta, smem, st, iter, do_b, do_f, h->d2_scratch_per_group);
   } else {
     const int blocks = (nsg + h->groups_per_cta - 1) / h->groups_per_cta;
@@ -478,6 +489,7 @@ int cfrb_destroy(cfrb_handle* h) {
   h->d_tmpl.release(); h->d_parent.release(); h->d_child_begin.release(); h->d_nchild.release(); h->d_last_bid.release();
   h->br.parent.release(); h->br.child_begin.release(); h->br.nchild.release(); h->br.level_begin.release(); h->br.term_node.release();
   h->br.strategy.release(); h->br.scratch.release(); h->br.out.release();
+  h->d_tpk.release();
   h->d_level_begin.release(); h->d_pleaf_node.release(); h->d_term_node.release(); h->d_matches.release(); h->d_qconst.release();
   h->d_wave.release(); h->d_sg_tmpl.release(); h->d_sg_player.release(); h->d_sg_row_off.release(); h->d_sg_act.release();
   h->d_steps.release(); h->d_X.release(); h->d_out.release(); h->d_dbg.release(); h->d_Xh.release();
@@ -486,6 +498,7 @@ int cfrb_destroy(cfrb_handle* h) {
   h->sp.seeds.release();
   if (h->sp.ev_examples) cudaEventDestroy(h->sp.ev_examples);
   for (auto e : h->marks) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) { if (h->w_stage[i]) cudaFreeHost(h->w_stage[i]); if (h->w_ev[i]) cudaEventDestroy(h->w_ev[i]); }
   if (h->flush_buf) cudaFree(h->flush_buf);
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   for (auto e : h->net_ev) cudaEventDestroy(e);
@@ -549,11 +562,48 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
   for (int hd = 0; hd < g.H; ++hd)
     for (int f = 0; f < g.F; ++f) matches[(size_t)hd * g.F + f] = (unsigned char)g.num_matches(hd, f);
 
+  // byte-packed copies of the templates for cfr_iter_d2_kernel (one coalesced copy into shared memory per subgame and launch):
+  // header {N, L, T, levels, n1e, n2e, -, -, qconst_off:int32, -} | parent[N] child_begin[N] nchild[N] last_bid+1[N] pleaf[L]
+  // term[3][T] matches[H*F]; only built when every count fits a byte (all depth <= 2 trees of the supported games do)
+  std::vector<unsigned char> tpk;
+  if (h->max_levels <= 3 && h->Nmax <= 255 && g.A <= 254) {
+    size_t mx = 0;
+    for (const auto& t : h->tmpl) mx = std::max(mx, (size_t)16 + 4 * (size_t)t.N + t.L + 3 * (size_t)t.T + (size_t)g.H * g.F);
+    h->tpk_stride = round_up((int)mx, 16);
+    tpk.assign((size_t)h->tpk_stride * h->tmpl.size(), 0);
+    for (size_t i = 0; i < h->tmpl.size(); ++i) {
+      const auto& t = h->tmpl[i];
+      unsigned char* b = tpk.data() + i * h->tpk_stride;
+      b[0] = (unsigned char)t.N; b[1] = (unsigned char)t.L; b[2] = (unsigned char)t.T; b[3] = (unsigned char)t.levels;
+      b[4] = (unsigned char)(t.levels >= 2 ? t.level_begin[2] : t.level_begin[1]);
+      b[5] = (unsigned char)(t.levels >= 3 ? t.level_begin[3] : b[4]);
+      std::memcpy(b + 8, &td[i].qconst_off, sizeof(int));
+      unsigned char* q = b + 16;
+      for (int n = 0; n < t.N; ++n) q[n] = (unsigned char)(t.parent[n] < 0 ? 0 : t.parent[n]);
+      q += t.N;
+      for (int n = 0; n < t.N; ++n) q[n] = (unsigned char)t.child_begin[n];
+      q += t.N;
+      for (int n = 0; n < t.N; ++n) q[n] = (unsigned char)t.nchild[n];
+      q += t.N;
+      for (int n = 0; n < t.N; ++n) q[n] = (unsigned char)(t.last_bid[n] + 1);
+      q += t.N;
+      for (int r = 0; r < t.L; ++r) q[r] = (unsigned char)t.pleaf_node[r];
+      q += t.L;
+      for (int z = 0; z < t.T; ++z) {
+        q[z] = (unsigned char)t.term_node[z];
+        q[t.T + z] = (unsigned char)t.last_bid[t.parent[t.term_node[z]]];     // challenged bid (:287); a terminal is never the root
+        q[2 * t.T + z] = (unsigned char)t.depth[t.term_node[z]];
+      }
+      q += 3 * t.T;
+      std::memcpy(q, matches.data(), matches.size());
+    }
+  }
   auto up = [&](auto& buf, const auto& v) -> cudaError_t {
     cudaError_t e = buf.alloc(v.size());
     if (e != cudaSuccess) return e;
     return cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice);
   };
+  CK(up(h->d_tpk, tpk));
   CK(up(h->d_tmpl, td)); CK(up(h->d_parent, parent)); CK(up(h->d_child_begin, child_begin)); CK(up(h->d_nchild, nchild));
   CK(up(h->d_last_bid, last_bid)); CK(up(h->d_level_begin, level_begin)); CK(up(h->d_pleaf_node, pleaf_node));
   CK(up(h->d_term_node, term_node)); CK(up(h->d_matches, matches)); CK(up(h->d_qconst, qconst));
@@ -667,12 +717,29 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
   const float* w1 = flat; const float* b1 = w1 + (size_t)hid * Q; const float* g1 = b1 + hid; const float* be1 = g1 + hid;
   const float* w2 = be1 + hid; const float* b2 = w2 + (size_t)hid * hid; const float* g2 = b2 + hid; const float* be2 = g2 + hid;
   const float* w3 = be2 + hid; const float* b3 = w3 + (size_t)H * hid;
-  // ordered after work already enqueued on the handle's stream (ModelLocker::updateModel waits for in-flight forwards)
-  CK(cudaStreamSynchronize(h->own_stream));
+  // Stream-ordered upload: the packed weights are built in a pinned staging buffer and copied on the handle's stream, i.e.
+  // after the waves already enqueued there (ModelLocker::updateModel waits for in-flight forwards; here nothing waits — the
+  // generator's software pipeline keeps running) and before everything enqueued later.
+  const size_t total_fp32 = (size_t)Qp * hid + 3 * hid + (size_t)hid * hid + 3 * hid + (size_t)hid * h->Hout + h->Hout;
+  const size_t need = is_tc(h->cfg.net_mode) ? (size_t)cfrb::tc::BlobLayout(Qp).blob_bytes : total_fp32 * sizeof(float);
+  if (h->w_stage_bytes < need) {
+    CK(cudaStreamSynchronize(h->own_stream));
+    for (int i = 0; i < 2; ++i) {
+      if (h->w_stage[i]) cudaFreeHost(h->w_stage[i]);
+      h->w_stage[i] = nullptr;
+      CK(cudaMallocHost((void**)&h->w_stage[i], need));
+      if (!h->w_ev[i]) CK(cudaEventCreateWithFlags(&h->w_ev[i], cudaEventDisableTiming));
+    }
+    h->w_stage_bytes = need;
+  }
+  const int slot = h->w_slot;
+  h->w_slot ^= 1;
+  CK(cudaEventSynchronize(h->w_ev[slot]));        // the copy that last used this staging buffer (two uploads ago) is long done
+  std::memset(h->w_stage[slot], 0, need);
   if (is_tc(h->cfg.net_mode)) {
     // tensor-core blob: fp16 weights in UMMA K-major core-matrix order + fp32 {bias, gamma, beta} per feature
     const cfrb::tc::BlobLayout L(Qp);
-    std::vector<uint8_t> blob(L.blob_bytes, 0);
+    struct { uint8_t* p; uint8_t* data() { return p; } } blob{h->w_stage[slot]};
     __half* hw1 = reinterpret_cast<__half*>(blob.data() + L.off_w1);
     __half* hw2 = reinterpret_cast<__half*>(blob.data() + L.off_w2);
     __half* hw3 = reinterpret_cast<__half*>(blob.data() + L.off_w3);
@@ -709,11 +776,11 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
     }
     std::copy(b3, b3 + H, reinterpret_cast<float*>(blob.data() + L.off_b3));
     if (!h->d_blob.p) CK(h->d_blob.alloc(L.blob_bytes));
-    CK(cudaMemcpy(h->d_blob.p, blob.data(), L.blob_bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(h->d_blob.p, blob.data(), L.blob_bytes, cudaMemcpyHostToDevice, h->own_stream));
   } else {
     // transposed k-major fp32 weights for the SIMT kernel
     const size_t total = (size_t)Qp * hid + 3 * hid + (size_t)hid * hid + 3 * hid + (size_t)hid * h->Hout + h->Hout;
-    std::vector<float> pk(total, 0.f);
+    struct { float* p; float& operator[](size_t i) { return p[i]; } float* begin() { return p; } float* data() { return p; } } pk{reinterpret_cast<float*>(h->w_stage[slot])};
     size_t o = 0;
     const size_t o_w1 = o; for (int k = 0; k < Q; ++k) for (int j = 0; j < hid; ++j) pk[o_w1 + (size_t)k * hid + j] = w1[(size_t)j * Q + k];
     o += (size_t)Qp * hid;
@@ -729,13 +796,15 @@ int cfrb_set_weights(cfrb_handle* h, const float* flat, size_t n, uint64_t versi
     o += (size_t)hid * h->Hout;
     const size_t o_b3 = o; std::copy(b3, b3 + H, pk.begin() + o);
     if (!h->d_w.p) CK(h->d_w.alloc(total));
-    CK(cudaMemcpy(h->d_w.p, pk.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(h->d_w.p, pk.data(), total * sizeof(float), cudaMemcpyHostToDevice, h->own_stream));
     cfrb::NetDev& nd = h->net;
     nd.Qpad = Qp; nd.hidden = hid; nd.Hout = h->Hout;
     nd.w1t = h->d_w.p + o_w1; nd.b1 = h->d_w.p + o_b1; nd.g1 = h->d_w.p + o_g1; nd.be1 = h->d_w.p + o_be1;
     nd.w2t = h->d_w.p + o_w2; nd.b2 = h->d_w.p + o_b2; nd.g2 = h->d_w.p + o_g2; nd.be2 = h->d_w.p + o_be2;
     nd.w3t = h->d_w.p + o_w3; nd.b3 = h->d_w.p + o_b3;
   }
+  CK(cudaEventRecord(h->w_ev[slot], h->own_stream));
+  h->w_last = h->w_ev[slot];
   h->have_weights = true;
   h->weights_version = version;
   return CFRB_OK;
@@ -879,6 +948,7 @@ int cfrb_run(cfrb_handle* h, int32_t iters, void* cuda_stream) {
   if (h->n == 0 || iters == 0) return CFRB_OK;
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  if (st != h->own_stream && h->w_last) CK(cudaStreamWaitEvent(st, h->w_last, 0));   // weights are uploaded on the handle's own stream
   const int first = h->iters_done, last = first + iters;
   // Long runs are replayed from a CUDA graph: one host call instead of 2 * iters kernel launches, so a busy or slow host
   // thread cannot starve the GPU.  The graph bakes in the iteration indices and a wave-size-independent launch geometry; it
@@ -1485,6 +1555,124 @@ int cfrb_dev_free(int32_t device, void* p) {
 int cfrb_dev_to_host(int32_t device, void* dst, const void* src, size_t bytes) {
   CK(cudaSetDevice(device));
   CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return CFRB_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================================ NCCL (one process per GPU)
+// The reference is a single process: generator threads share the trainer's model replicas and its host-memory replay.  With
+// one process per GPU the two hand-overs become collectives over NVLink, issued from THIS library on device buffers:
+//   ModelLocker::updateModel (rela/model_locker.h:69-79)      -> ncclBroadcast of the flat weight buffer from the trainer's rank
+//   PrioritizedReplay::add   (rela/prioritized_replay.h:247-261) -> grouped ncclSend / ncclRecv of every rank's example rows
+//                                                                   into the trainer rank's device-resident replay rows
+//   recursive_eval's accumulation (recursive_eval.cc:343-363) -> ncclReduce(sum) of the float32 accumulators
+#include <nccl.h>
+
+struct cfrb_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+  cudaStream_t st = nullptr;
+  float* scratch = nullptr; size_t scratch_floats = 0;
+};
+
+#define NCK(call)                                                                                                       \
+  do {                                                                                                                  \
+    ncclResult_t r__ = (call);                                                                                          \
+    if (r__ != ncclSuccess) return fail(CFRB_ECUDA, std::string(#call) + ": " + ncclGetErrorString(r__));              \
+  } while (0)
+
+extern "C" {
+
+int cfrb_comm_unique_id(uint8_t* out128) {
+  if (!out128) return fail(CFRB_EINVAL, "null argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  NCK(ncclGetUniqueId(&id));
+  std::memcpy(out128, &id, 128);
+  return CFRB_OK;
+}
+
+int cfrb_comm_create(const uint8_t* id128, int32_t rank, int32_t world, int32_t device, cfrb_comm** out) {
+  if (!id128 || !out || world < 1 || rank < 0 || rank >= world) return fail(CFRB_EINVAL, "cfrb_comm_create: bad argument");
+  CK(cudaSetDevice(device));
+  auto* c = new cfrb_comm();
+  c->rank = rank; c->world = world; c->device = device;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclResult_t r = ncclCommInitRank(&c->comm, world, id, rank);
+  if (r != ncclSuccess) { delete c; return fail(CFRB_ECUDA, std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); }
+  cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { ncclCommDestroy(c->comm); delete c; return fail(CFRB_ECUDA, cudaGetErrorString(e)); }
+  *out = c;
+  return CFRB_OK;
+}
+
+int cfrb_comm_destroy(cfrb_comm* c) {
+  if (!c) return CFRB_OK;
+  cudaSetDevice(c->device);
+  if (c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->comm) ncclCommDestroy(c->comm);
+  delete c;
+  return CFRB_OK;
+}
+
+int cfrb_comm_rank(const cfrb_comm* c) { return c ? c->rank : -1; }
+int cfrb_comm_world(const cfrb_comm* c) { return c ? c->world : 0; }
+
+static int comm_scratch(cfrb_comm* c, size_t floats) {
+  if (c->scratch_floats >= floats) return CFRB_OK;
+  if (c->scratch) cudaFree(c->scratch);
+  c->scratch = nullptr; c->scratch_floats = 0;
+  CK(cudaMalloc((void**)&c->scratch, floats * sizeof(float)));
+  c->scratch_floats = floats;
+  return CFRB_OK;
+}
+
+int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_t root) {
+  if (!c || !flat_host || n == 0) return fail(CFRB_EINVAL, "cfrb_comm_broadcast_weights: bad argument");
+  CK(cudaSetDevice(c->device));
+  int rc = comm_scratch(c, n);
+  if (rc) return rc;
+  if (c->rank == root) CK(cudaMemcpyAsync(c->scratch, flat_host, n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  NCK(ncclBroadcast(c->scratch, c->scratch, n, ncclFloat, root, c->comm, c->st));
+  if (c->rank != root) CK(cudaMemcpyAsync(flat_host, c->scratch, n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return CFRB_OK;
+}
+
+int cfrb_comm_gather_rows(cfrb_comm* c, const float* dev_q, const float* dev_v, int32_t n, int32_t q_dim, int32_t v_dim, float* recv_q,
+                          float* recv_v, int32_t root) {
+  if (!c || !dev_q || !dev_v || n < 0 || q_dim < 1 || v_dim < 1) return fail(CFRB_EINVAL, "cfrb_comm_gather_rows: bad argument");
+  if (c->rank == root && (!recv_q || !recv_v)) return fail(CFRB_EINVAL, "cfrb_comm_gather_rows: the root needs receive buffers");
+  CK(cudaSetDevice(c->device));
+  const size_t nq = (size_t)n * q_dim, nv = (size_t)n * v_dim;
+  NCK(ncclGroupStart());
+  if (c->rank == root) {
+    for (int r = 0; r < c->world; ++r) {
+      if (r == root) continue;
+      NCK(ncclRecv(recv_q + (size_t)r * nq, nq, ncclFloat, r, c->comm, c->st));
+      NCK(ncclRecv(recv_v + (size_t)r * nv, nv, ncclFloat, r, c->comm, c->st));
+    }
+  } else {
+    NCK(ncclSend(dev_q, nq, ncclFloat, root, c->comm, c->st));
+    NCK(ncclSend(dev_v, nv, ncclFloat, root, c->comm, c->st));
+  }
+  NCK(ncclGroupEnd());
+  if (c->rank == root) {     // the root's own block: a device-to-device copy into its slot
+    CK(cudaMemcpyAsync(recv_q + (size_t)root * nq, dev_q, nq * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(recv_v + (size_t)root * nv, dev_v, nv * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
+  }
+  CK(cudaStreamSynchronize(c->st));
+  return CFRB_OK;
+}
+
+int cfrb_comm_reduce_sum(cfrb_comm* c, float* dev_buf, size_t n, int32_t root) {
+  if (!c || !dev_buf) return fail(CFRB_EINVAL, "cfrb_comm_reduce_sum: bad argument");
+  CK(cudaSetDevice(c->device));
+  NCK(ncclReduce(dev_buf, dev_buf, n, ncclFloat, ncclSum, root, c->comm, c->st));
+  CK(cudaStreamSynchronize(c->st));
   return CFRB_OK;
 }
 

@@ -12,7 +12,7 @@
 //     and every phase starts by pulling the accumulators into registers (64 per thread), which frees D at once; the issuer then
 //     runs the big MMA of the OTHER tile (layer 2 of X under E1(Y), layer 2 of Y under E2(X), ...) while this phase computes.
 //     Layer 3 (N = 16) of a tile is issued into D[0,16) right after the next phase has emptied D and is read by the four
-//     column-quarter-0 warps after their second sub-chunk; the next layer-1 MMA follows.  No accumulator is ever waited for
+//     column-quarter-0 warps after their first sub-chunk; the next layer-1 MMA follows.  No accumulator is ever waited for
 //     except at the very first tile and for a CTA's odd last tile.  (Generation 2 — leaf_mlp_tc2.cuh of round 1, removed —
 //     kept two accumulator regions and moved A through shared memory; its SS MMAs then competed with the epilogue for
 //     shared-memory bandwidth and it was slower.  Here A stays in TMEM.)
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc3_kernel(TcArgs a) {
           }
         }
         CFRB_TMEM_ST8(tmem_row + acol + part_id * (kColsPerThread / 2) + c * 8, pk);
-        if (c == 1 && out_here) {                                  // previous tile's layer 3 (16 K-steps of N = 16, ~1 800 cycles: the
+        if (c == 0 && out_here) {                                  // previous tile's layer 3 (16 K-steps of N = 16, ~1 800 cycles: the
                                                                    // A-operand fetch bounds a K-step, not N) has landed in D[0,16) by now
           int pj, pl;
           phase_of(k - 1, pj, pl);

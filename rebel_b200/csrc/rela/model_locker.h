@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -43,6 +44,8 @@ class ModelLocker {
     snapshot(py_model);
   }
 
+  // One process per GPU: `bcast` replaces the flat weights of every rank with the trainer rank's (ncclBroadcast, see Comm).
+  void setBroadcast(std::function<void(std::vector<float>&)> bcast) { bcast_ = std::move(bcast); }
   uint64_t version() const { return version_.load(); }
   std::shared_ptr<const std::vector<float>> weights() const {
     std::lock_guard<std::mutex> lk(m_);
@@ -92,6 +95,10 @@ class ModelLocker {
       const float* p = t.data_ptr<float>();
       flat->insert(flat->end(), p, p + t.numel());
     }
+    if (bcast_) {
+      py::gil_scoped_release nogil;
+      bcast_(*flat);
+    }
     {
       std::lock_guard<std::mutex> lk(m_);
       weights_ = flat;
@@ -103,6 +110,7 @@ class ModelLocker {
   mutable std::mutex m_;
   std::shared_ptr<const std::vector<float>> weights_;
   std::atomic<uint64_t> version_{0};
+  std::function<void(std::vector<float>&)> bcast_;
   int cpu_slot_ = -1;
 };
 

@@ -23,13 +23,62 @@ using liars_dice::SubgameSolvingParams;
 
 namespace {
 
+// One process per GPU (torchrun): NCCL communicator of libcfrb200 (cfrb_comm_*, include/cfrb200.h).  The reference has no
+// multi-process mode — its generator threads share the trainer's replay and model replicas inside one process — so this is the
+// B200 counterpart of those two shared objects: ModelLocker.update_model becomes a broadcast from the trainer's rank, and a
+// generator loop hands every wave's examples to the trainer rank's device-resident replay with grouped send / recv.
+class Comm {
+ public:
+  Comm(py::bytes id, int rank, int world, int device) : device_(device) {
+    const std::string s = id;
+    if (s.size() != 128) throw std::runtime_error("Comm: the NCCL unique id must be 128 bytes");
+    if (cfrb_comm_create(reinterpret_cast<const uint8_t*>(s.data()), rank, world, device, &c_) < 0)
+      throw std::runtime_error(std::string("cfrb_comm_create: ") + cfrb_last_error());
+  }
+  ~Comm() { if (c_) cfrb_comm_destroy(c_); }
+  Comm(const Comm&) = delete;
+  Comm& operator=(const Comm&) = delete;
+  int rank() const { return cfrb_comm_rank(c_); }
+  int world() const { return cfrb_comm_world(c_); }
+  int device() const { return device_; }
+  cfrb_comm* get() const { return c_; }
+  // flat fp32 weights (host tensor): the root's content replaces everybody else's
+  void broadcastWeights(torch::Tensor flat, int root) {
+    if (flat.is_cuda() || flat.scalar_type() != torch::kFloat32 || !flat.is_contiguous()) throw std::runtime_error("broadcast_weights: contiguous fp32 host tensor expected");
+    py::gil_scoped_release nogil;
+    if (cfrb_comm_broadcast_weights(c_, flat.data_ptr<float>(), (size_t)flat.numel(), root) < 0) throw std::runtime_error(cfrb_last_error());
+  }
+  // in-place sum of a float32 CUDA tensor over the ranks, result on the root (recursive_eval's accumulators)
+  void reduceSum(torch::Tensor t, int root) {
+    if (!t.is_cuda() || t.scalar_type() != torch::kFloat32 || !t.is_contiguous()) throw std::runtime_error("reduce_sum: contiguous fp32 CUDA tensor expected");
+    c10::cuda::getCurrentCUDAStream(t.get_device()).synchronize();
+    py::gil_scoped_release nogil;
+    if (cfrb_comm_reduce_sum(c_, t.data_ptr<float>(), (size_t)t.numel(), root) < 0) throw std::runtime_error(cfrb_last_error());
+  }
+
+ private:
+  cfrb_comm* c_ = nullptr;
+  int device_ = 0;
+};
+
+py::bytes comm_unique_id() {
+  uint8_t id[128];
+  if (cfrb_comm_unique_id(id) < 0) throw std::runtime_error(std::string("cfrb_comm_unique_id: ") + cfrb_last_error());
+  return py::bytes(reinterpret_cast<const char*>(id), 128);
+}
+
+// Communicator the generator loops created afterwards use to deliver their examples to rank `root`'s replay (None = local replay).
+std::shared_ptr<Comm> g_example_comm;
+int g_example_root = 0;
+void set_example_comm(std::shared_ptr<Comm> c, int root) { g_example_comm = std::move(c); g_example_root = root; }
+
 // DataThreadLoop::mainLoop of the reference plays games one after another (rela/data_loop.h:67-76); here each loop
 // iteration is one wave of `concurrent_games` subgames.  Pause / terminate are observed between waves.
 class DataThreadLoop : public ThreadLoop {
  public:
   DataThreadLoop(std::shared_ptr<ModelLocker> locker, std::shared_ptr<ValuePrioritizedReplay> replay,
                  const RecursiveSolvingParams& cfg, int seed)
-      : locker_(std::move(locker)), replay_(std::move(replay)), cfg_(cfg), seed_(seed) {
+      : locker_(std::move(locker)), replay_(std::move(replay)), cfg_(cfg), seed_(seed), comm_(g_example_comm), comm_root_(g_example_root) {
     // configuration errors surface here, on the Python thread that builds the loop, not inside the worker
     if (cfg_.num_dice < 1 || cfg_.num_faces < 1) throw std::runtime_error("create_cfr_thread: num_dice / num_faces not set");
     if (cfg_.subgame_params.max_depth < 1 || cfg_.subgame_params.num_iters < 1)
@@ -49,8 +98,21 @@ class DataThreadLoop : public ThreadLoop {
     uint64_t have = 0;
     const std::function<bool()> cancelled = [this] { return terminated(); };
     auto host_sink = [&](const float* q, int qd, const float* v, int vd, int n) { return replay_->addRows(q, qd, v, vd, n, nullptr, cancelled); };
+    float* recv_q = nullptr; float* recv_v = nullptr; int recv_rows = 0;
     auto dev_sink = [&](const float* q, int qd, const float* v, int vd, int n, int dev) {
-      return replay_->addRowsDevice(q, qd, v, vd, n, dev, cancelled);
+      if (!comm_) return replay_->addRowsDevice(q, qd, v, vd, n, dev, cancelled);
+      // one process per GPU: this wave's rows of every rank -> the trainer rank's replay, device to device over NVLink
+      const int world = comm_->world(), me = comm_->rank();
+      if (me == comm_root_ && recv_rows < world * n) {
+        if (recv_q) { cfrb_dev_free(dev, recv_q); cfrb_dev_free(dev, recv_v); }
+        if (cfrb_dev_alloc(dev, (size_t)world * n * qd * sizeof(float), (void**)&recv_q) < 0 ||
+            cfrb_dev_alloc(dev, (size_t)world * n * vd * sizeof(float), (void**)&recv_v) < 0)
+          throw std::runtime_error(cfrb_last_error());
+        recv_rows = world * n;
+      }
+      if (cfrb_comm_gather_rows(comm_->get(), q, v, n, qd, vd, recv_q, recv_v, comm_root_) < 0) throw std::runtime_error(cfrb_last_error());
+      if (me != comm_root_) return true;
+      return replay_->addRowsDevice(recv_q, qd, recv_v, vd, world * n, dev, cancelled);
     };
     while (!terminated()) {
       if (paused()) waitUntilResume();
@@ -74,6 +136,8 @@ class DataThreadLoop : public ThreadLoop {
   std::shared_ptr<ValuePrioritizedReplay> replay_;
   const RecursiveSolvingParams cfg_;
   const int seed_;
+  std::shared_ptr<Comm> comm_;
+  const int comm_root_;
   std::atomic<int64_t> waves_{0};
 };
 
@@ -319,9 +383,26 @@ PYBIND11_MODULE(rela, m) {
       .def("terminated", &Context::terminated)
       .def("error", &Context::error, "rebel_b200 extension: message of the last exception raised inside a generator loop");
 
+  py::class_<Comm, std::shared_ptr<Comm>>(m, "Comm", "rebel_b200 extension: NCCL communicator of libcfrb200 (one process per GPU)")
+      .def(py::init<py::bytes, int, int, int>(), py::arg("unique_id"), py::arg("rank"), py::arg("world"), py::arg("device"))
+      .def_property_readonly("rank", &Comm::rank)
+      .def_property_readonly("world", &Comm::world)
+      .def("broadcast_weights", &Comm::broadcastWeights, py::arg("flat"), py::arg("root") = 0)
+      .def("reduce_sum", &Comm::reduceSum, py::arg("tensor"), py::arg("root") = 0);
+  m.def("comm_unique_id", &comm_unique_id, "rebel_b200 extension: ncclGetUniqueId (call on one rank, hand the 128 bytes to the others)");
+  m.def("set_example_comm", &set_example_comm, py::arg("comm"), py::arg("root") = 0,
+        "rebel_b200 extension: generator loops created after this call deliver every wave's examples to rank `root`'s replay "
+        "(grouped ncclSend / ncclRecv from the device buffers); None restores the local replay.");
+
   py::class_<ModelLocker, std::shared_ptr<ModelLocker>>(m, "ModelLocker")
       .def(py::init<std::vector<py::object>, const std::string&>())
       .def("update_model", &ModelLocker::updateModel)
+      .def("set_comm", [](ModelLocker& l, std::shared_ptr<Comm> c, int root) {
+             l.setBroadcast(c ? std::function<void(std::vector<float>&)>([c, root](std::vector<float>& w) {
+               if (cfrb_comm_broadcast_weights(c->get(), w.data(), w.size(), root) < 0) throw std::runtime_error(cfrb_last_error());
+             }) : nullptr);
+           }, py::arg("comm"), py::arg("root") = 0,
+           "rebel_b200 extension: update_model becomes a collective — every rank calls it, rank `root`'s weights are broadcast (ncclBroadcast)")
       .def_property_readonly("version", &ModelLocker::version, "rebel_b200 extension: number of weight snapshots taken");
 
   m.def("compute_exploitability_fp", &compute_exploitability_fp, py::arg("params"));

@@ -12,11 +12,11 @@ S.begin(np.full(K, -1, np.int32), np.zeros(K, np.int32), b)
 for _ in range(3):
     S.reset(); S.run(256); S.sync()
 tot, _ = S.last_run_ms()
-print("gen", os.environ.get("CFRB_D2_GEN", "2"), "root wave: CFR us per iteration", tot / 256 * 1e3, flush=True)
+print("gen", os.environ.get("CFRB_D2_GEN", "1.5") + "/" + os.environ.get("CFRB_D2V2_THREADS", "32"), "root wave: CFR us per iteration", tot / 256 * 1e3, flush=True)
 S.selfplay_create(np.arange(K, dtype=np.uint32) * 1000000 + 7)
 for _ in range(8):
     S.selfplay_wave()
 S.sync()
 S.selfplay_wave(); S.sync()
 tot, _ = S.last_run_ms()
-print("gen", os.environ.get("CFRB_D2_GEN", "2"), "self-play wave: CFR us per iteration", tot / 1024 * 1e3, "rows", S.leaf_rows, flush=True)
+print("gen", os.environ.get("CFRB_D2_GEN", "1.5") + "/" + os.environ.get("CFRB_D2V2_THREADS", "32"), "self-play wave: CFR us per iteration", tot / 1024 * 1e3, "rows", S.leaf_rows, flush=True)

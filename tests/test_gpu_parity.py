@@ -315,13 +315,15 @@ def test_fictitious_play_bit_exact_vs_reference(rb, golden, port, net_weights, D
 @pytest.mark.parametrize("D,F", SHAPES)
 @pytest.mark.parametrize("net_name", ["fp32", "tc", "tcx2"])
 def test_long_horizon_within_reference_noise(rb, golden, net_weights, D, F, net_name):
-    """1024 iterations with the Net2 value net: root value means vs the reference.  The reference moves by mean 2.1e-4 /
-    max 2.8e-3 under a ONE-ulp fp32 perturbation of its net outputs ('pert'); that band, or 3x the
-    reference's own FMA/no-FMA self-noise when larger, is the acceptance criterion for the fp32 net.  The tensor-core nets
-    perturb the net outputs by ~5e-4..8e-4 relative (thousands of fp32 ulps, the reference's own `half_inference` regime) and the
-    response is chaotic — a change of the MMA accumulation order alone moves the 1x4f root values by 7e-4 — so their band
-    is 2e-3 mean / 1e-2 max on root values of order 0.1..1."""
+    """1024 iterations with the Net2 value net: root value means vs the reference.  fp32 net: the reference moves by mean
+    2.1e-4 / max 2.8e-3 under a ONE-ulp fp32 perturbation of its net outputs ('pert'); that band, or 3x the
+    reference's own FMA/no-FMA self-noise when larger, is the criterion.  Tensor-core nets: the band is DERIVED, not chosen —
+    the REFERENCE solver is run with its own net perturbed the way the tcgen05 kernels perturb it (weights rounded to fp16; on top
+    of that, independent relative noise on every output at the kernels' measured level, 5.4e-4 for fp32-GELU and 7.7e-4 for the
+    packed-half GELU, 8 seeds; tests/golden/net_band.npz from oracle/make_golden_r2.py), and the GPU must stay within 3x the
+    mean response of the reference to that perturbation (or 3x its self-noise, or the fp32 band, whichever is larger)."""
     g = golden(f"cfr_net_{D}x{F}.npz")
+    nb = golden("net_band.npz")
     n = len(g["roots"])
     S = rb.WaveSolver(D, F, n, net_mode=NETS(rb)[net_name])
     S.set_weights(net_weights(D, F))
@@ -332,9 +334,20 @@ def test_long_horizon_within_reference_noise(rb, golden, net_weights, D, F, net_
         a, b = g[f"mu1024_nofma{i}"], g[f"mu1024_fast{i}"]
         self_noise = np.abs(a - b).mean()
         d = np.abs(mu[i] - a)
-        _note(f"P4 {D}x{F}f net={net_name} root{i}: mean|dmu|={d.mean():.3e} max={d.max():.3e} ref-self-noise mean={self_noise:.3e}")
-        assert d.mean() <= max(7e-4 if net_name == "fp32" else 2e-3, 3 * self_noise), (D, F, i, d.mean(), self_noise)
-        assert d.max() <= 1e-2, (D, F, i, d.max())
+        band_mean, band_max = max(7e-4, 3 * self_noise), 1e-2
+        if net_name != "fp32":
+            si = 0 if net_name == "tc" else 1
+            pert = np.abs(nb[f"mu_pert{si}_{D}x{F}_{i}"] - a)                      # [seeds][2][H]
+            w16 = np.abs(nb[f"mu_w16_{D}x{F}_{i}"] - a)
+            response = max(pert.mean(), w16.mean())
+            band_mean = max(band_mean, 3 * response)
+            band_max = max(band_max, 3 * max(pert.max(), w16.max()))
+            _note(f"P4 {D}x{F}f net={net_name} root{i}: mean|dmu|={d.mean():.3e} max={d.max():.3e} | reference under the same perturbation: "
+                  f"fp16 weights {w16.mean():.3e}, + output noise {pert.mean():.3e} (max {pert.max():.3e}); self-noise {self_noise:.3e}; band {band_mean:.2e}")
+        else:
+            _note(f"P4 {D}x{F}f net={net_name} root{i}: mean|dmu|={d.mean():.3e} max={d.max():.3e} ref-self-noise mean={self_noise:.3e}")
+        assert d.mean() <= band_mean, (D, F, i, d.mean(), band_mean)
+        assert d.max() <= band_max, (D, F, i, d.max(), band_max)
     S.close()
 
 

@@ -395,3 +395,93 @@ def test_replay_rows_live_on_the_device(rela, tmp_path):
     for b in got:
         rows = (b.query[:, 0] / Q).long().cpu()
         assert torch.equal(b.query.cpu(), q[rows]) and torch.equal(b.values.cpu(), v[rows])
+
+
+def _last_action_stats(q, v, A, net):
+    """The statistic cfvpy/selfplay.py:158-169 logs: per last action (bucket A = "initial") example count, target sum, loss sum."""
+    onehot = q[:, 2:2 + A]
+    aid = np.where(onehot.sum(1) > 0, onehot.argmax(1), A)
+    cnt = np.bincount(aid, minlength=A + 1).astype(np.float64)
+    vsum = np.zeros(A + 1); lsum = np.zeros(A + 1)
+    np.add.at(vsum, aid, v.astype(np.float64).sum(1))
+    with torch.no_grad():
+        pred = net(torch.from_numpy(q)).numpy()
+    np.add.at(lsum, aid, ((v - pred).astype(np.float64) ** 2).mean(1))
+    return cnt, vsum, lsum
+
+
+def _chi2(a, b):
+    """Two-sample chi-square statistic of two count vectors (different totals)."""
+    na, nb = a.sum(), b.sum()
+    m = (a + b) > 0
+    return float((((a * np.sqrt(nb / na) - b * np.sqrt(na / nb)) ** 2)[m] / (a + b)[m]).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,F", [(1, 4), (1, 6)])
+def test_datagen_distribution_matches_reference(rela, golden, D, F):
+    """P5: the data-generation loop on the GPU (device walk, tcgen05 packed-half value net: the DEFAULT
+    product configuration, 1024 iterations, seed-0 Net2) against >= 50 k examples of the reference's RlRunner loops: the
+    per-last-action example counts (chi-square), mean targets and mean losses — the statistic selfplay.py:158-169 logs.  The
+    band is measured, not chosen: the same statistics between two disjoint seed sets of the REFERENCE (fixture
+    datagen_stats.npz, oracle/make_golden_r2.py).  Only complete games are counted on the GPU side (a wave loop stops mid-game)."""
+    from rebel_b200.models import flatten_state_dict, make_selfplay_net
+    from tests.test_gpu_parity import _note
+    A, H, Q = game_dims(D, F)
+    g = golden("datagen_stats.npz")
+    net = make_selfplay_net(D, F, seed=0)
+    w = torch.from_numpy(flatten_state_dict(net.state_dict()))
+    K, waves = 1024, 64
+    cfg = make_cfg(rela, D, F, concurrent_games=K, net_mode=3, state_dtype=0)
+    q, v = rela.run_selfplay_waves(cfg, 0, 123, waves, w)
+    q = q.numpy().reshape(waves, K, 2, Q); v = v.numpy().reshape(waves, K, 2, H)
+    starts = q[:, :, 0, 2:2 + A].sum(-1) == 0                      # [waves][K]: the subgame at the initial state = a game starts
+    last_start = waves - 1 - np.argmax(starts[::-1], axis=0)       # per slot: wave of its last game start
+    keep = np.arange(waves)[:, None] < last_start[None, :]         # everything before the (possibly unfinished) last game
+    qk, vk = q[keep].reshape(-1, Q), v[keep].reshape(-1, H)
+    assert len(qk) >= 50000
+    cnt, vsum, lsum = _last_action_stats(qk, vk, A, net)
+    ca, cb = g[f"count_a_{D}x{F}"].astype(np.float64), g[f"count_b_{D}x{F}"].astype(np.float64)
+    big = (ca >= 300) & (cb >= 300)
+    mean = lambda s, c: s[big] / (c[big] * H)
+    ma, mb, mg = mean(g[f"val_sum_a_{D}x{F}"], ca), mean(g[f"val_sum_b_{D}x{F}"], cb), mean(vsum, cnt)
+    la, lb_, lg = g[f"loss_sum_a_{D}x{F}"][big] / ca[big], g[f"loss_sum_b_{D}x{F}"][big] / cb[big], lsum[big] / cnt[big]
+    chi_ref, chi_gpu = _chi2(ca, cb), max(_chi2(cnt, ca), _chi2(cnt, cb))
+    dm_ref, dm_gpu = np.abs(ma - mb).max(), min(np.abs(mg - ma).max(), np.abs(mg - mb).max())
+    dl_ref, dl_gpu = (np.abs(la - lb_) / la).max(), min((np.abs(lg - la) / la).max(), (np.abs(lg - lb_) / lb_).max())
+    _note(f"P5 {D}x{F}f: {len(qk)} GPU examples vs {int(ca.sum())} + {int(cb.sum())} reference examples; chi2 of the last-action counts "
+          f"GPU-vs-ref {chi_gpu:.1f}, ref-vs-ref {chi_ref:.1f} ({A + 1} buckets); max |mean target diff| GPU {dm_gpu:.2e}, ref-vs-ref {dm_ref:.2e}; "
+          f"max relative loss diff GPU {dl_gpu:.2e}, ref-vs-ref {dl_ref:.2e}")
+    assert chi_gpu <= 3 * max(chi_ref, A + 1), (chi_gpu, chi_ref)
+    assert dm_gpu <= 3 * dm_ref + 1e-4, (dm_gpu, dm_ref)
+    assert dl_gpu <= 3 * dl_ref + 0.02, (dl_gpu, dl_ref)
+
+
+@pytest.mark.gpu
+def test_config5_with_the_value_net_vs_reference(rela, golden):
+    """BASELINE config 5 WITH the value net (round 1 pinned it with the zero net only): recursive_eval's 64 sampled recursive
+    strategies on 1x4f, 1024 iterations, seed-0 Net2.  Reference = compute_sampled_strategy_recursive_to_leaf with ATen fp32
+    (fixture config5_net.npz).  Zero net: bit-identical.  With the net the trajectories are chaotic, so the
+    exploitability of the averaged strategy is compared: the fp32 SIMT net must agree with the reference like the reference's
+    two builds agree with each other (3x their difference, at least 2e-3), the tensor-core nets within 1e-2 of it."""
+    from rebel_b200.models import flatten_state_dict, make_selfplay_net
+    from tests.test_gpu_parity import _note
+    g = golden("config5_net.npz")
+    D, F, iters, reps = [int(x) for x in g["cfg"]]
+    want = g["exploitability"].mean(1)
+    self_noise = np.abs(g["exploitability_fast_build"].mean(1) - want) if "exploitability_fast_build" in g.files else np.zeros_like(want)
+    w = torch.from_numpy(flatten_state_dict(make_selfplay_net(D, F, seed=0).state_dict()))
+    got = {}
+    for name, mode, weights in (("zero", 0, None), ("fp32", 1, w), ("tc_f16", 2, w), ("tc_f16x2", 3, w)):
+        cfg = make_cfg(rela, D, F, net_mode=mode, state_dtype=0, subgame_params=dict(num_iters=iters, max_depth=2, linear_update=True, use_cfr=True))
+        r = rela.recursive_eval_sampled(cfg, 0, reps, 0, 64, 8192, weights)
+        assert list(r["checkpoints"]) == list(g["checkpoints"])
+        got[name] = r["exploitability"].numpy().mean(1)
+    assert np.array_equal(got["zero"], g["exploitability_zero_net"].mean(1))
+    for name in ("fp32", "tc_f16", "tc_f16x2"):
+        d = np.abs(got[name] - want)
+        _note(f"config5 1x4f R=64 with Net2, net={name}: exploitability {got[name][-1]:.5f} vs reference {want[-1]:.5f} (|d| = {d[-1]:.2e}; "
+              f"over the checkpoints R>=8 max |d| = {d[3:].max():.2e}); reference -O3 vs -O2 builds differ by {self_noise[-1]:.2e}")
+    assert np.abs(got["fp32"] - want)[-1] <= max(3 * self_noise[-1], 2e-3)
+    for name in ("tc_f16", "tc_f16x2"):
+        assert np.abs(got[name] - want)[-1] <= 1e-2, (name, got[name][-1], want[-1])
