@@ -653,7 +653,8 @@ def run_datagen(args):
     w0 = loop.waves
     t0 = time.perf_counter()
     for i in range(steps):
-        locker.update_model(net)                    # trainer -> generators: fresh weights from HOST memory (N > 1: + ncclBroadcast), installed before the next wave
+        if os.environ.get("BENCH_E2E_NO_UPDATE") != "1":   # (diagnostic switch; the reported line always updates)
+            locker.update_model(net)                # trainer -> generators: fresh weights from HOST memory (N > 1: + ncclBroadcast), installed before the next wave
         wait_waves(w0 + i + 1)
         if rank == 0:
             batch, _ = replay.sample(rows_per_wave, "cpu")     # the step's examples (of all ranks) back to HOST memory

@@ -201,6 +201,8 @@ int64_t cfrb_wave_leaf_rows(const cfrb_handle* h);
  * between two recorded marks (waits for the second). */
 int cfrb_mark(cfrb_handle* h, int32_t slot, void* cuda_stream);
 int cfrb_mark_elapsed_ms(cfrb_handle* h, int32_t a, int32_t b, float* ms);
+int cfrb_mark_wait(cfrb_handle* h, int32_t slot);          /* block until the mark has been reached */
+void* cfrb_handle_stream(cfrb_handle* h);                  /* the handle's own cudaStream_t (what NULL stream arguments mean) */
 /* Overwrite a scratch buffer of `bytes` on the stream (pass more than the 126 MB of L2 to evict it between timed steps). */
 int cfrb_l2_flush(cfrb_handle* h, size_t bytes, void* cuda_stream);
 /* Device time in ms of the most recent cfrb_run, and of its value-net kernels only (CUDA events on
@@ -271,9 +273,16 @@ int cfrb_comm_world(const cfrb_comm* c);
 /* flat fp32 weights (cfrb_set_weights layout): read from the root's host buffer, written to every other rank's host buffer. */
 int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_t root);
 /* every rank contributes n rows from DEVICE buffers dev_q [n][q_dim], dev_v [n][v_dim]; on the root they arrive in rank order in
- * the DEVICE buffers recv_q [world * n][q_dim], recv_v [world * n][v_dim] (ignored elsewhere). */
+ * the DEVICE buffers recv_q [world * n][q_dim], recv_v [world * n][v_dim] (ignored elsewhere).  cuda_stream NULL: the communicator's
+ * own stream, the call waits; otherwise the send / recv are only ENQUEUED on that stream — a generator loop puts them between two
+ * waves on its handle's stream, where the GPU has nothing else to run and they cost microseconds instead of competing with a
+ * wave's kernels for SMs. */
 int cfrb_comm_gather_rows(cfrb_comm* c, const float* dev_q, const float* dev_v, int32_t n, int32_t q_dim, int32_t v_dim, float* recv_q,
-                          float* recv_v, int32_t root);
+                          float* recv_v, int32_t root, void* cuda_stream);
+/* agreement between generator loops that must issue the same number of collectives (e.g. "stop after this wave"): every rank
+ * contributes a flag, all ranks obtain the maximum; enqueued on cuda_stream like cfrb_comm_gather_rows, read once that point is reached. */
+int cfrb_comm_vote(cfrb_comm* c, int32_t flag, void* cuda_stream);
+int cfrb_comm_vote_result(cfrb_comm* c, int32_t* out);
 /* in-place float32 sum over the ranks of a DEVICE buffer, result on the root. */
 int cfrb_comm_reduce_sum(cfrb_comm* c, float* dev_buf, size_t n, int32_t root);
 

@@ -62,7 +62,9 @@ __host__ __device__ inline int cfr_aux_bytes_d2(int sz, int H, int L, int T, int
   return (m + 15) & ~15;
 }
 __host__ __device__ inline int cfr_scratch_reals_d2(int sz, int N, int H, int L, int T, int n1max) {
-  return N * H + 2 * H + (cfr_aux_bytes_d2(sz, H, L, T, n1max) + sz - 1) / sz;
+  const int per16 = 16 / sz;       // every group's region starts 16-byte aligned (its template bytes are copied with 16-byte accesses)
+  const int reals = N * H + 2 * H + (cfr_aux_bytes_d2(sz, H, L, T, n1max) + sz - 1) / sz;
+  return (reals + per16 - 1) / per16 * per16;
 }
 
 // Full-tree best response (br_kernel.cuh).  Arrays describe ONE full-depth tree rooted at the initial state.

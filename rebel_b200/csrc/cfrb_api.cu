@@ -78,6 +78,7 @@ struct cfrb_handle {
   int max_levels = 0;
   int d2_groups_per_cta = 8;
   int d2_scratch_per_group = 0;
+  size_t d2_smem = 0;      // dynamic shared memory of a depth-2 CTA
   bool d2v2 = false;       // cfr_iter_d2v2_kernel (CFR solver, depth <= 2): one warp per CTA, inputs staged by cp.async.bulk
   int d2v2_smem = 0, n1max = 0, d2v2_threads = 32;
   int table_stride = 0;
@@ -195,7 +196,14 @@ static int alloc_state(cfrb_handle* h, int max_optin) {
       const size_t cta_budget = ((size_t)228 * 1024 - 8 * 1024) / 8;
       h->d2_groups_per_cta = (int)std::max<size_t>(1, std::min<size_t>(4, cta_budget / d2_bytes));
       if (const char* e = std::getenv("CFRB_D2_GROUPS")) h->d2_groups_per_cta = std::max(1, std::min(h->d2_groups_per_cta, std::atoi(e)));
-      CK(cfrb::cfr_configure_d2<real>((int)(d2_bytes * h->d2_groups_per_cta)));
+      h->d2_smem = d2_bytes * h->d2_groups_per_cta;
+      // CFRB_D2_CTAS_PER_SM=n: pad the CTA's shared memory so that exactly n CTAs fit an SM (resident warps = n x warps per CTA);
+      // e.g. 7 x 4 = 28 warps make 8192 subgames 1.98 rounds on 148 SMs instead of 1.73 rounds of 32 warps executed as 2
+      if (const char* e = std::getenv("CFRB_D2_CTAS_PER_SM")) {
+        const int n = std::atoi(e);
+        if (n >= 1 && n <= 8) h->d2_smem = std::max(h->d2_smem, ((size_t)227 * 1024 - (size_t)n * 1024) / n / 16 * 16);
+      }
+      CK(cfrb::cfr_configure_d2<real>((int)h->d2_smem));
       const char* gen = std::getenv("CFRB_D2_GEN");
       h->d2v2_smem = cfrb::cfr_d2v2_smem_bytes<real>(h->Nmax, g.H, h->Hout, std::max(h->Lmax, 1), std::max(h->Tmax, 1), h->n1max, h->table_stride);
       // generation 2 (cfr_d2v2.cuh) is opt-in (CFRB_D2_GEN=2): measured slower than the 32-warps-per-SM kernel
@@ -250,7 +258,7 @@ static int launch_iter_t(cfrb_handle* h, cudaStream_t st, int iter, int do_b, in
     cfrb::cfr_launch_iter_d2v2<real>(s.dev, nsg, h->d2v2_threads, (size_t)h->d2v2_smem, st, iter, do_b, do_f, h->n1max);
   } else if (h->d2) {
     const int blocks = (nsg + h->d2_groups_per_cta - 1) / h->d2_groups_per_cta;
-    const size_t smem = ((size_t)h->d2_scratch_per_group * sizeof(real) + h->tpk_stride) * h->d2_groups_per_cta;
+    const size_t smem = h->d2_smem;
     cfrb::cfr_launch_iter_d2<real>(s.dev, blocks, 32 * h->d2_groups_per_cta, smem, st, iter, do_b, do_f, h->d2_scratch_per_group);
   } else {
     const int blocks = (nsg + h->groups_per_cta - 1) / h->groups_per_cta;
@@ -1223,6 +1231,13 @@ int cfrb_mark(cfrb_handle* h, int32_t slot, void* cuda_stream) {
   CK(cudaEventRecord(h->marks[slot], cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream));
   return CFRB_OK;
 }
+int cfrb_mark_wait(cfrb_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot >= 8 || !h->marks[slot]) return fail(CFRB_EINVAL, "cfrb_mark_wait: mark not recorded");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->marks[slot]));
+  return CFRB_OK;
+}
+void* cfrb_handle_stream(cfrb_handle* h) { return h ? (void*)h->own_stream : nullptr; }
 int cfrb_mark_elapsed_ms(cfrb_handle* h, int32_t a, int32_t b, float* ms) {
   if (!h || !ms || a < 0 || a >= 8 || b < 0 || b >= 8 || !h->marks[a] || !h->marks[b]) return fail(CFRB_EINVAL, "cfrb_mark_elapsed_ms: bad marks");
   CK(cudaSetDevice(h->cfg.device));
@@ -1574,6 +1589,7 @@ struct cfrb_comm {
   int rank = 0, world = 1, device = 0;
   cudaStream_t st = nullptr;
   float* scratch = nullptr; size_t scratch_floats = 0;
+  int* vote = nullptr;
 };
 
 #define NCK(call)                                                                                                       \
@@ -1613,6 +1629,7 @@ int cfrb_comm_destroy(cfrb_comm* c) {
   cudaSetDevice(c->device);
   if (c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
   if (c->scratch) cudaFree(c->scratch);
+  if (c->vote) cudaFree(c->vote);
   if (c->comm) ncclCommDestroy(c->comm);
   delete c;
   return CFRB_OK;
@@ -1643,28 +1660,51 @@ int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_
 }
 
 int cfrb_comm_gather_rows(cfrb_comm* c, const float* dev_q, const float* dev_v, int32_t n, int32_t q_dim, int32_t v_dim, float* recv_q,
-                          float* recv_v, int32_t root) {
+                          float* recv_v, int32_t root, void* cuda_stream) {
   if (!c || !dev_q || !dev_v || n < 0 || q_dim < 1 || v_dim < 1) return fail(CFRB_EINVAL, "cfrb_comm_gather_rows: bad argument");
   if (c->rank == root && (!recv_q || !recv_v)) return fail(CFRB_EINVAL, "cfrb_comm_gather_rows: the root needs receive buffers");
   CK(cudaSetDevice(c->device));
   const size_t nq = (size_t)n * q_dim, nv = (size_t)n * v_dim;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->st;
   NCK(ncclGroupStart());
   if (c->rank == root) {
     for (int r = 0; r < c->world; ++r) {
       if (r == root) continue;
-      NCK(ncclRecv(recv_q + (size_t)r * nq, nq, ncclFloat, r, c->comm, c->st));
-      NCK(ncclRecv(recv_v + (size_t)r * nv, nv, ncclFloat, r, c->comm, c->st));
+      NCK(ncclRecv(recv_q + (size_t)r * nq, nq, ncclFloat, r, c->comm, st));
+      NCK(ncclRecv(recv_v + (size_t)r * nv, nv, ncclFloat, r, c->comm, st));
     }
   } else {
-    NCK(ncclSend(dev_q, nq, ncclFloat, root, c->comm, c->st));
-    NCK(ncclSend(dev_v, nv, ncclFloat, root, c->comm, c->st));
+    NCK(ncclSend(dev_q, nq, ncclFloat, root, c->comm, st));
+    NCK(ncclSend(dev_v, nv, ncclFloat, root, c->comm, st));
   }
   NCK(ncclGroupEnd());
   if (c->rank == root) {     // the root's own block: a device-to-device copy into its slot
-    CK(cudaMemcpyAsync(recv_q + (size_t)root * nq, dev_q, nq * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
-    CK(cudaMemcpyAsync(recv_v + (size_t)root * nv, dev_v, nv * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(recv_q + (size_t)root * nq, dev_q, nq * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(recv_v + (size_t)root * nv, dev_v, nv * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
-  CK(cudaStreamSynchronize(c->st));
+  if (!cuda_stream) CK(cudaStreamSynchronize(st));     // on the caller's stream the collective is just enqueued (stream-ordered)
+  return CFRB_OK;
+}
+
+// Agreement between the ranks' generator loops (they must issue the same number of collectives): every rank contributes a flag,
+// all ranks get the maximum.  Enqueued on `cuda_stream` (NULL: the communicator's stream); cfrb_comm_vote_result reads it once the
+// stream has passed that point (the caller synchronises, e.g. with cfrb_mark_wait).
+int cfrb_comm_vote(cfrb_comm* c, int32_t flag, void* cuda_stream) {
+  if (!c) return fail(CFRB_EINVAL, "null communicator");
+  CK(cudaSetDevice(c->device));
+  if (!c->vote) CK(cudaMalloc((void**)&c->vote, sizeof(int)));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->st;
+  CK(cudaMemsetAsync(c->vote, flag ? 1 : 0, sizeof(int), st));
+  NCK(ncclAllReduce(c->vote, c->vote, 1, ncclInt32, ncclMax, c->comm, st));
+  if (!cuda_stream) CK(cudaStreamSynchronize(st));
+  return CFRB_OK;
+}
+int cfrb_comm_vote_result(cfrb_comm* c, int32_t* out) {
+  if (!c || !out || !c->vote) return fail(CFRB_EINVAL, "cfrb_comm_vote_result: no vote");
+  CK(cudaSetDevice(c->device));
+  int v = 0;
+  CK(cudaMemcpy(&v, c->vote, sizeof(int), cudaMemcpyDeviceToHost));
+  *out = v != 0;
   return CFRB_OK;
 }
 

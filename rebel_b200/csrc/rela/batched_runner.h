@@ -110,12 +110,27 @@ class BatchedRlRunner {
     }
     const int b = buf_ ^= 1;
     // finish the pending wave (examples -> dev_*_[b], games advance) and start the next one, all asynchronous
-    const int rows = cfrb_selfplay_wave(h_, dev_q_[b], dev_v_[b], 1, nullptr);
-    check(rows, "cfrb_selfplay_wave");
-    check(cfrb_selfplay_wait_examples(h_), "cfrb_selfplay_wait_examples");
+    int rows;
+    if (between_waves_) {
+      // ... with a stream-ordered hook in between (one process per GPU: the NCCL hand-over of the examples runs while the GPU has
+      // nothing else to do, then the next wave follows on the same stream)
+      rows = cfrb_selfplay_wave(h_, dev_q_[b], dev_v_[b], 0, nullptr);
+      check(rows, "cfrb_selfplay_wave");
+      between_waves_(dev_q_[b], dev_v_[b], rows, cfrb_handle_stream(h_));
+      check(cfrb_mark(h_, 7, nullptr), "cfrb_mark");
+      check(cfrb_selfplay_wave(h_, nullptr, nullptr, 1, nullptr), "cfrb_selfplay_wave");
+      check(cfrb_mark_wait(h_, 7), "cfrb_mark_wait");
+    } else {
+      rows = cfrb_selfplay_wave(h_, dev_q_[b], dev_v_[b], 1, nullptr);
+      check(rows, "cfrb_selfplay_wave");
+      check(cfrb_selfplay_wait_examples(h_), "cfrb_selfplay_wait_examples");
+    }
     subgames_solved_ += K_;
     return sink(dev_q_[b], Q_, dev_v_[b], H_, rows, device_);
   }
+  // Hook enqueued on the handle's stream between the end of a wave (its examples are in the given device buffers) and the start
+  // of the next one.
+  void setBetweenWaves(std::function<void(const float* dev_q, const float* dev_v, int rows, void* stream)> f) { between_waves_ = std::move(f); }
   // Drain: finish the wave in flight without starting another (its examples are delivered; used at shutdown / by tests).
   bool finishDevice(const DeviceExampleSink& sink) {
     if (host_walk_ || !started_) return true;
@@ -274,6 +289,7 @@ class BatchedRlRunner {
   const int K_;
   const int device_;
   bool host_walk_ = false, started_ = false;
+  std::function<void(const float*, const float*, int, void*)> between_waves_;
   int buf_ = 0;
   float* dev_q_[2] = {nullptr, nullptr};
   float* dev_v_[2] = {nullptr, nullptr};

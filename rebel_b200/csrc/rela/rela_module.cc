@@ -98,25 +98,34 @@ class DataThreadLoop : public ThreadLoop {
     uint64_t have = 0;
     const std::function<bool()> cancelled = [this] { return terminated(); };
     auto host_sink = [&](const float* q, int qd, const float* v, int vd, int n) { return replay_->addRows(q, qd, v, vd, n, nullptr, cancelled); };
-    float* recv_q = nullptr; float* recv_v = nullptr; int recv_rows = 0;
+    float* recv_q = nullptr; float* recv_v = nullptr;
+    if (comm_ && !runner.hostWalk()) {
+      // one process per GPU: this wave's rows of every rank -> the trainer rank's replay, device to device over NVLink, enqueued
+      // on the generator's own stream between two waves
+      const int world = comm_->world(), n = 2 * runner.games(), dev = runner.device();
+      if (comm_->rank() == comm_root_) {
+        if (cfrb_dev_alloc(dev, (size_t)world * n * cfrb_query_size(runner.handle()) * sizeof(float), (void**)&recv_q) < 0 ||
+            cfrb_dev_alloc(dev, (size_t)world * n * cfrb_num_hands(runner.handle()) * sizeof(float), (void**)&recv_v) < 0)
+          throw std::runtime_error(cfrb_last_error());
+      }
+      runner.setBetweenWaves([&, world](const float* q, const float* v, int rows, void* stream) {
+        if (rows <= 0) return;
+        if (cfrb_comm_gather_rows(comm_->get(), q, v, rows, cfrb_query_size(runner.handle()), cfrb_num_hands(runner.handle()), recv_q, recv_v,
+                                  comm_root_, stream) < 0)
+          throw std::runtime_error(cfrb_last_error());
+        // the ranks' loops must stop after the same wave (every wave is a collective): vote in the same stream slot
+        if (cfrb_comm_vote(comm_->get(), terminated() ? 1 : 0, stream) < 0) throw std::runtime_error(cfrb_last_error());
+      });
+    }
     auto dev_sink = [&](const float* q, int qd, const float* v, int vd, int n, int dev) {
       if (!comm_) return replay_->addRowsDevice(q, qd, v, vd, n, dev, cancelled);
-      // one process per GPU: this wave's rows of every rank -> the trainer rank's replay, device to device over NVLink
-      const int world = comm_->world(), me = comm_->rank();
-      if (me == comm_root_ && recv_rows < world * n) {
-        if (recv_q) { cfrb_dev_free(dev, recv_q); cfrb_dev_free(dev, recv_v); }
-        if (cfrb_dev_alloc(dev, (size_t)world * n * qd * sizeof(float), (void**)&recv_q) < 0 ||
-            cfrb_dev_alloc(dev, (size_t)world * n * vd * sizeof(float), (void**)&recv_v) < 0)
-          throw std::runtime_error(cfrb_last_error());
-        recv_rows = world * n;
-      }
-      if (cfrb_comm_gather_rows(comm_->get(), q, v, n, qd, vd, recv_q, recv_v, comm_root_) < 0) throw std::runtime_error(cfrb_last_error());
-      if (me != comm_root_) return true;
-      return replay_->addRowsDevice(recv_q, qd, recv_v, vd, world * n, dev, cancelled);
+      if (comm_->rank() != comm_root_) return true;
+      return replay_->addRowsDevice(recv_q, qd, recv_v, vd, comm_->world() * n, dev, cancelled);   // gathered behind the wave (see above)
     };
-    while (!terminated()) {
-      if (paused()) waitUntilResume();
-      if (terminated()) break;
+    const bool collective = comm_ && !runner.hostWalk();
+    while (collective || !terminated()) {
+      if (paused() && !terminated()) waitUntilResume();
+      if (!collective && terminated()) break;
       const uint64_t ver = locker_->version();
       if (ver != have) {   // ModelLocker::updateModel happened: install the new weights before the next wave is enqueued
         runner.setWeights(*locker_->weights(), ver);
@@ -124,8 +133,15 @@ class DataThreadLoop : public ThreadLoop {
       }
       const bool ok = runner.hostWalk() ? runner.step(host_sink) : runner.stepDevice(dev_sink);
       ++waves_;
-      if (!ok) break;
+      if (collective) {
+        int32_t stop = 0;
+        if (cfrb_comm_vote_result(comm_->get(), &stop) < 0) throw std::runtime_error(cfrb_last_error());
+        if (stop) break;          // some rank's loop was terminated: every rank leaves after this wave
+      } else if (!ok) {
+        break;
+      }
     }
+    if (recv_q) { cfrb_dev_free(runner.device(), recv_q); cfrb_dev_free(runner.device(), recv_v); }
   }
 
   int64_t waves() const { return waves_.load(); }
