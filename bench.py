@@ -626,14 +626,13 @@ def run_datagen(args):
     replay = rela.ValuePrioritizedReplay(capacity=max(1 << 18, 16 * K * world), seed=10001 + rank, alpha=1.0, beta=1.0, prefetch=0, use_priority=False,
                                          compressed_values=False)
     if world > 1:
-        # one process per GPU: the library's own NCCL communicators (cfrb_comm_*): update_model = ncclBroadcast from rank 0, every
-        # wave's examples -> rank 0's device-resident replay by grouped send / recv from the generators' device buffers
-        ids = [rela.comm_unique_id(), rela.comm_unique_id()] if rank == 0 else [None, None]
+        # one process per GPU: the library's own NCCL communicator (cfrb_comm_*).  Every wave's examples go to rank 0's device-resident
+        # replay by grouped send / recv from the generators' device buffers, and the other ranks' loops follow rank 0's ModelLocker by
+        # ncclBroadcast — both enqueued on the generator's stream between two waves
+        ids = [rela.comm_unique_id()] if rank == 0 else [None]
         dist.broadcast_object_list(ids, src=0)
-        comm_w = rela.Comm(ids[0], rank, world, local)
-        comm_x = rela.Comm(ids[1], rank, world, local)
-        locker.set_comm(comm_w, 0)
-        rela.set_example_comm(comm_x, 0)
+        comm_x = rela.Comm(ids[0], rank, world, local)
+        rela.set_generator_comm(comm_x, 0)
     loop = rela.create_cfr_thread(locker, replay, rela_cfg(rela, args, K, mode), rank * 1000)
     ctx = rela.Context()
     ctx.push_env_thread(loop)
@@ -653,8 +652,8 @@ def run_datagen(args):
     w0 = loop.waves
     t0 = time.perf_counter()
     for i in range(steps):
-        if os.environ.get("BENCH_E2E_NO_UPDATE") != "1":   # (diagnostic switch; the reported line always updates)
-            locker.update_model(net)                # trainer -> generators: fresh weights from HOST memory (N > 1: + ncclBroadcast), installed before the next wave
+        if rank == 0 and os.environ.get("BENCH_E2E_NO_UPDATE") != "1":   # (diagnostic switch; the reported line always updates)
+            locker.update_model(net)                # trainer -> generators: fresh weights from HOST memory (N > 1: + ncclBroadcast between two waves)
         wait_waves(w0 + i + 1)
         if rank == 0:
             batch, _ = replay.sample(rows_per_wave, "cpu")     # the step's examples (of all ranks) back to HOST memory
@@ -663,7 +662,7 @@ def run_datagen(args):
         dist.barrier()
     ctx.terminate()
     if world > 1:
-        rela.set_example_comm(None, 0)
+        rela.set_generator_comm(None, 0)
     while not ctx.terminated():
         time.sleep(0.01)
     barrier()

@@ -270,8 +270,12 @@ int cfrb_comm_create(const uint8_t* id128, int32_t rank, int32_t world, int32_t 
 int cfrb_comm_destroy(cfrb_comm* c);
 int cfrb_comm_rank(const cfrb_comm* c);
 int cfrb_comm_world(const cfrb_comm* c);
-/* flat fp32 weights (cfrb_set_weights layout): read from the root's host buffer, written to every other rank's host buffer. */
-int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_t root);
+/* flat fp32 weights (cfrb_set_weights layout): read from the root's host buffer, delivered to every other rank.  cuda_stream NULL:
+ * the communicator's own stream, the call waits and the other ranks' flat_host is filled.  Otherwise the H2D copy (root), the
+ * ncclBroadcast and the D2H copy (others) are only ENQUEUED on that stream (a generator loop puts them between two waves); the
+ * other ranks pass flat_host = NULL and read the weights with cfrb_comm_broadcast_fetch once the stream has passed that point. */
+int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_t root, void* cuda_stream);
+int cfrb_comm_broadcast_fetch(cfrb_comm* c, float* out_host, size_t n);
 /* every rank contributes n rows from DEVICE buffers dev_q [n][q_dim], dev_v [n][v_dim]; on the root they arrive in rank order in
  * the DEVICE buffers recv_q [world * n][q_dim], recv_v [world * n][v_dim] (ignored elsewhere).  cuda_stream NULL: the communicator's
  * own stream, the call waits; otherwise the send / recv are only ENQUEUED on that stream — a generator loop puts them between two
@@ -279,10 +283,11 @@ int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_
  * wave's kernels for SMs. */
 int cfrb_comm_gather_rows(cfrb_comm* c, const float* dev_q, const float* dev_v, int32_t n, int32_t q_dim, int32_t v_dim, float* recv_q,
                           float* recv_v, int32_t root, void* cuda_stream);
-/* agreement between generator loops that must issue the same number of collectives (e.g. "stop after this wave"): every rank
- * contributes a flag, all ranks obtain the maximum; enqueued on cuda_stream like cfrb_comm_gather_rows, read once that point is reached. */
-int cfrb_comm_vote(cfrb_comm* c, int32_t flag, void* cuda_stream);
-int cfrb_comm_vote_result(cfrb_comm* c, int32_t* out);
+/* agreement between generator loops that must issue the same collectives in the same order ("stop after this wave", "the trainer
+ * rank has weights version v"): every rank contributes n <= 4 ints, all ranks obtain the element-wise maximum; enqueued on
+ * cuda_stream like cfrb_comm_gather_rows, read with cfrb_comm_vote_result once that point is reached. */
+int cfrb_comm_vote(cfrb_comm* c, const int32_t* values, int32_t n, void* cuda_stream);
+int cfrb_comm_vote_result(cfrb_comm* c, int32_t* out, int32_t n);
 /* in-place float32 sum over the ranks of a DEVICE buffer, result on the root. */
 int cfrb_comm_reduce_sum(cfrb_comm* c, float* dev_buf, size_t n, int32_t root);
 

@@ -1589,7 +1589,9 @@ struct cfrb_comm {
   int rank = 0, world = 1, device = 0;
   cudaStream_t st = nullptr;
   float* scratch = nullptr; size_t scratch_floats = 0;
-  int* vote = nullptr;
+  float* pin = nullptr; size_t pin_floats = 0;      // pinned staging of the stream-ordered weight broadcast
+  int* vote = nullptr;                               // [4] device ints of the vote
+  int* pin_vote = nullptr; int* pin_vote_out = nullptr;   // pinned [4] each: contributions / result
 };
 
 #define NCK(call)                                                                                                       \
@@ -1619,7 +1621,9 @@ int cfrb_comm_create(const uint8_t* id128, int32_t rank, int32_t world, int32_t 
   ncclResult_t r = ncclCommInitRank(&c->comm, world, id, rank);
   if (r != ncclSuccess) { delete c; return fail(CFRB_ECUDA, std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); }
   cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->pin_vote, 8 * sizeof(int));
   if (e != cudaSuccess) { ncclCommDestroy(c->comm); delete c; return fail(CFRB_ECUDA, cudaGetErrorString(e)); }
+  c->pin_vote_out = c->pin_vote + 4;
   *out = c;
   return CFRB_OK;
 }
@@ -1630,6 +1634,8 @@ int cfrb_comm_destroy(cfrb_comm* c) {
   if (c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
   if (c->scratch) cudaFree(c->scratch);
   if (c->vote) cudaFree(c->vote);
+  if (c->pin) cudaFreeHost(c->pin);
+  if (c->pin_vote) cudaFreeHost(c->pin_vote);
   if (c->comm) ncclCommDestroy(c->comm);
   delete c;
   return CFRB_OK;
@@ -1647,15 +1653,38 @@ static int comm_scratch(cfrb_comm* c, size_t floats) {
   return CFRB_OK;
 }
 
-int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_t root) {
-  if (!c || !flat_host || n == 0) return fail(CFRB_EINVAL, "cfrb_comm_broadcast_weights: bad argument");
+int cfrb_comm_broadcast_weights(cfrb_comm* c, float* flat_host, size_t n, int32_t root, void* cuda_stream) {
+  if (!c || n == 0 || (!flat_host && (!cuda_stream || c->rank == root))) return fail(CFRB_EINVAL, "cfrb_comm_broadcast_weights: bad argument");
   CK(cudaSetDevice(c->device));
   int rc = comm_scratch(c, n);
   if (rc) return rc;
-  if (c->rank == root) CK(cudaMemcpyAsync(c->scratch, flat_host, n * sizeof(float), cudaMemcpyHostToDevice, c->st));
-  NCK(ncclBroadcast(c->scratch, c->scratch, n, ncclFloat, root, c->comm, c->st));
-  if (c->rank != root) CK(cudaMemcpyAsync(flat_host, c->scratch, n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  if (!cuda_stream) {
+    if (c->rank == root) CK(cudaMemcpyAsync(c->scratch, flat_host, n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    NCK(ncclBroadcast(c->scratch, c->scratch, n, ncclFloat, root, c->comm, c->st));
+    if (c->rank != root) CK(cudaMemcpyAsync(flat_host, c->scratch, n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return CFRB_OK;
+  }
+  // stream-ordered: staged through pinned memory owned by the communicator; nothing is waited for here.  The root's buffer is
+  // copied now (the caller may reuse it); the other ranks read theirs with cfrb_comm_broadcast_fetch once the stream got there.
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (c->pin_floats < n) {
+    if (c->pin) cudaFreeHost(c->pin);
+    c->pin = nullptr; c->pin_floats = 0;
+    CK(cudaMallocHost((void**)&c->pin, n * sizeof(float)));
+    c->pin_floats = n;
+  }
+  if (c->rank == root) {
+    std::memcpy(c->pin, flat_host, n * sizeof(float));
+    CK(cudaMemcpyAsync(c->scratch, c->pin, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  NCK(ncclBroadcast(c->scratch, c->scratch, n, ncclFloat, root, c->comm, st));
+  if (c->rank != root) CK(cudaMemcpyAsync(c->pin, c->scratch, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return CFRB_OK;
+}
+int cfrb_comm_broadcast_fetch(cfrb_comm* c, float* out_host, size_t n) {
+  if (!c || !out_host || !c->pin || n > c->pin_floats) return fail(CFRB_EINVAL, "cfrb_comm_broadcast_fetch: no stream-ordered broadcast of that size");
+  std::memcpy(out_host, c->pin, n * sizeof(float));
   return CFRB_OK;
 }
 
@@ -1689,22 +1718,22 @@ int cfrb_comm_gather_rows(cfrb_comm* c, const float* dev_q, const float* dev_v, 
 // Agreement between the ranks' generator loops (they must issue the same number of collectives): every rank contributes a flag,
 // all ranks get the maximum.  Enqueued on `cuda_stream` (NULL: the communicator's stream); cfrb_comm_vote_result reads it once the
 // stream has passed that point (the caller synchronises, e.g. with cfrb_mark_wait).
-int cfrb_comm_vote(cfrb_comm* c, int32_t flag, void* cuda_stream) {
-  if (!c) return fail(CFRB_EINVAL, "null communicator");
+int cfrb_comm_vote(cfrb_comm* c, const int32_t* values, int32_t n, void* cuda_stream) {
+  if (!c || !values || n < 1 || n > 4) return fail(CFRB_EINVAL, "cfrb_comm_vote: 1..4 values");
   CK(cudaSetDevice(c->device));
-  if (!c->vote) CK(cudaMalloc((void**)&c->vote, sizeof(int)));
+  if (!c->vote) CK(cudaMalloc((void**)&c->vote, 4 * sizeof(int)));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->st;
-  CK(cudaMemsetAsync(c->vote, flag ? 1 : 0, sizeof(int), st));
-  NCK(ncclAllReduce(c->vote, c->vote, 1, ncclInt32, ncclMax, c->comm, st));
+  int* pin_i = c->pin_vote;      // contributions from pinned words owned by the communicator (the previous vote has been read)
+  for (int i = 0; i < n; ++i) pin_i[i] = values[i];
+  CK(cudaMemcpyAsync(c->vote, pin_i, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  NCK(ncclAllReduce(c->vote, c->vote, n, ncclInt32, ncclMax, c->comm, st));
+  CK(cudaMemcpyAsync(c->pin_vote_out, c->vote, n * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (!cuda_stream) CK(cudaStreamSynchronize(st));
   return CFRB_OK;
 }
-int cfrb_comm_vote_result(cfrb_comm* c, int32_t* out) {
-  if (!c || !out || !c->vote) return fail(CFRB_EINVAL, "cfrb_comm_vote_result: no vote");
-  CK(cudaSetDevice(c->device));
-  int v = 0;
-  CK(cudaMemcpy(&v, c->vote, sizeof(int), cudaMemcpyDeviceToHost));
-  *out = v != 0;
+int cfrb_comm_vote_result(cfrb_comm* c, int32_t* out, int32_t n) {
+  if (!c || !out || !c->vote || n < 1 || n > 4) return fail(CFRB_EINVAL, "cfrb_comm_vote_result: no vote");
+  for (int i = 0; i < n; ++i) out[i] = c->pin_vote_out[i];
   return CFRB_OK;
 }
 

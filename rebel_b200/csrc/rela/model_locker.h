@@ -4,7 +4,8 @@
 // `forward` on them once per iteration; here the value net is evaluated by CUDA kernels inside libcfrb200, so the locker
 // snapshots the parameters as ONE flat fp32 buffer (Net2 state_dict order, include/cfrb200.h) with a version counter, and
 // each generator loop installs a new version with cfrb_set_weights between two waves.  update_model still refreshes
-// the Python replicas (load_state_dict), so code that inspects them keeps working.
+// the Python replicas (load_state_dict), so code that inspects them keeps working.  One process per GPU: the generator loops of
+// the other ranks follow the trainer rank's locker through a stream-ordered ncclBroadcast between two waves (rela_module.cc).
 #pragma once
 #include <pybind11/pybind11.h>
 #include <torch/extension.h>
@@ -44,8 +45,6 @@ class ModelLocker {
     snapshot(py_model);
   }
 
-  // One process per GPU: `bcast` replaces the flat weights of every rank with the trainer rank's (ncclBroadcast, see Comm).
-  void setBroadcast(std::function<void(std::vector<float>&)> bcast) { bcast_ = std::move(bcast); }
   uint64_t version() const { return version_.load(); }
   std::shared_ptr<const std::vector<float>> weights() const {
     std::lock_guard<std::mutex> lk(m_);
@@ -95,10 +94,6 @@ class ModelLocker {
       const float* p = t.data_ptr<float>();
       flat->insert(flat->end(), p, p + t.numel());
     }
-    if (bcast_) {
-      py::gil_scoped_release nogil;
-      bcast_(*flat);
-    }
     {
       std::lock_guard<std::mutex> lk(m_);
       weights_ = flat;
@@ -110,7 +105,6 @@ class ModelLocker {
   mutable std::mutex m_;
   std::shared_ptr<const std::vector<float>> weights_;
   std::atomic<uint64_t> version_{0};
-  std::function<void(std::vector<float>&)> bcast_;
   int cpu_slot_ = -1;
 };
 

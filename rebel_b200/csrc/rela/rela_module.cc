@@ -46,7 +46,7 @@ class Comm {
   void broadcastWeights(torch::Tensor flat, int root) {
     if (flat.is_cuda() || flat.scalar_type() != torch::kFloat32 || !flat.is_contiguous()) throw std::runtime_error("broadcast_weights: contiguous fp32 host tensor expected");
     py::gil_scoped_release nogil;
-    if (cfrb_comm_broadcast_weights(c_, flat.data_ptr<float>(), (size_t)flat.numel(), root) < 0) throw std::runtime_error(cfrb_last_error());
+    if (cfrb_comm_broadcast_weights(c_, flat.data_ptr<float>(), (size_t)flat.numel(), root, nullptr) < 0) throw std::runtime_error(cfrb_last_error());
   }
   // in-place sum of a float32 CUDA tensor over the ranks, result on the root (recursive_eval's accumulators)
   void reduceSum(torch::Tensor t, int root) {
@@ -67,7 +67,8 @@ py::bytes comm_unique_id() {
   return py::bytes(reinterpret_cast<const char*>(id), 128);
 }
 
-// Communicator the generator loops created afterwards use to deliver their examples to rank `root`'s replay (None = local replay).
+// Communicator the generator loop created afterwards uses (None = single process): every wave's examples go to rank `root`'s
+// replay, and the loops of the other ranks follow the weights of rank `root`'s ModelLocker.  ONE loop per process uses it.
 std::shared_ptr<Comm> g_example_comm;
 int g_example_root = 0;
 void set_example_comm(std::shared_ptr<Comm> c, int root) { g_example_comm = std::move(c); g_example_root = root; }
@@ -99,44 +100,76 @@ class DataThreadLoop : public ThreadLoop {
     const std::function<bool()> cancelled = [this] { return terminated(); };
     auto host_sink = [&](const float* q, int qd, const float* v, int vd, int n) { return replay_->addRows(q, qd, v, vd, n, nullptr, cancelled); };
     float* recv_q = nullptr; float* recv_v = nullptr;
-    if (comm_ && !runner.hostWalk()) {
-      // one process per GPU: this wave's rows of every rank -> the trainer rank's replay, device to device over NVLink, enqueued
-      // on the generator's own stream between two waves
+    const bool collective = comm_ && !runner.hostWalk();
+    const bool trainer_rank = !collective || comm_->rank() == comm_root_;
+    // collective mode, all stream-ordered on the generator's own stream between two waves (the GPU has nothing else to do there,
+    // and no NCCL kernel ever competes with a wave for SMs):
+    //   1. this wave's rows of every rank -> the trainer rank's replay, device to device over NVLink (grouped send / recv);
+    //   2. a vote {stop, newest weights version of the trainer rank}: all loops leave after the same wave, and all of them learn
+    //      in the same wave that the trainer's ModelLocker has moved on;
+    //   3. one wave after such a vote, ncclBroadcast of the trainer rank's flat weights; the other ranks install them for the
+    //      wave enqueued after that (the same two-wave latency update_model has on the trainer rank's own pipelined loop + 1).
+    uint64_t announced = 0, bcast_version = 0;
+    bool bcast_next = false, bcast_pending = false;
+    const size_t nflat = locker_->weights()->size();
+    std::vector<float> flat_rx;
+    if (collective) {
       const int world = comm_->world(), n = 2 * runner.games(), dev = runner.device();
-      if (comm_->rank() == comm_root_) {
+      if (trainer_rank) {
         if (cfrb_dev_alloc(dev, (size_t)world * n * cfrb_query_size(runner.handle()) * sizeof(float), (void**)&recv_q) < 0 ||
             cfrb_dev_alloc(dev, (size_t)world * n * cfrb_num_hands(runner.handle()) * sizeof(float), (void**)&recv_v) < 0)
           throw std::runtime_error(cfrb_last_error());
+      } else {
+        flat_rx.resize(nflat);
       }
-      runner.setBetweenWaves([&, world](const float* q, const float* v, int rows, void* stream) {
+      runner.setBetweenWaves([&](const float* q, const float* v, int rows, void* stream) {
         if (rows <= 0) return;
         if (cfrb_comm_gather_rows(comm_->get(), q, v, rows, cfrb_query_size(runner.handle()), cfrb_num_hands(runner.handle()), recv_q, recv_v,
                                   comm_root_, stream) < 0)
           throw std::runtime_error(cfrb_last_error());
-        // the ranks' loops must stop after the same wave (every wave is a collective): vote in the same stream slot
-        if (cfrb_comm_vote(comm_->get(), terminated() ? 1 : 0, stream) < 0) throw std::runtime_error(cfrb_last_error());
+        const int32_t vals[2] = {terminated() ? 1 : 0, trainer_rank ? (int32_t)locker_->version() : 0};
+        if (cfrb_comm_vote(comm_->get(), vals, 2, stream) < 0) throw std::runtime_error(cfrb_last_error());
+        if (bcast_next) {
+          auto w = locker_->weights();     // the trainer rank sends whatever is newest now
+          if (cfrb_comm_broadcast_weights(comm_->get(), trainer_rank ? const_cast<float*>(w->data()) : nullptr, nflat, comm_root_, stream) < 0)
+            throw std::runtime_error(cfrb_last_error());
+          bcast_next = false; bcast_pending = true;
+        }
       });
     }
     auto dev_sink = [&](const float* q, int qd, const float* v, int vd, int n, int dev) {
-      if (!comm_) return replay_->addRowsDevice(q, qd, v, vd, n, dev, cancelled);
-      if (comm_->rank() != comm_root_) return true;
+      if (!collective) return replay_->addRowsDevice(q, qd, v, vd, n, dev, cancelled);
+      if (!trainer_rank) return true;
       return replay_->addRowsDevice(recv_q, qd, recv_v, vd, comm_->world() * n, dev, cancelled);   // gathered behind the wave (see above)
     };
-    const bool collective = comm_ && !runner.hostWalk();
     while (collective || !terminated()) {
       if (paused() && !terminated()) waitUntilResume();
       if (!collective && terminated()) break;
       const uint64_t ver = locker_->version();
-      if (ver != have) {   // ModelLocker::updateModel happened: install the new weights before the next wave is enqueued
-        runner.setWeights(*locker_->weights(), ver);
+      if (ver != have && (trainer_rank || have == 0)) {
+        // ModelLocker::updateModel happened: install the new weights before the next wave is enqueued.  (A rank that follows the
+        // trainer rank only takes its own locker's initial snapshot; later versions arrive by broadcast.)
+        auto w = locker_->weights();
+        runner.setWeights(*w, ver);
         have = ver;
+        noteWeights(*w, ver);
       }
       const bool ok = runner.hostWalk() ? runner.step(host_sink) : runner.stepDevice(dev_sink);
       ++waves_;
       if (collective) {
-        int32_t stop = 0;
-        if (cfrb_comm_vote_result(comm_->get(), &stop) < 0) throw std::runtime_error(cfrb_last_error());
-        if (stop) break;          // some rank's loop was terminated: every rank leaves after this wave
+        int32_t res[2] = {0, 0};
+        if (cfrb_comm_vote_result(comm_->get(), res, 2) < 0) throw std::runtime_error(cfrb_last_error());
+        if (bcast_pending) {
+          bcast_pending = false;
+          if (!trainer_rank) {
+            if (cfrb_comm_broadcast_fetch(comm_->get(), flat_rx.data(), nflat) < 0) throw std::runtime_error(cfrb_last_error());
+            runner.setWeights(flat_rx, bcast_version);
+            have = bcast_version;
+            noteWeights(flat_rx, bcast_version);
+          }
+        }
+        if ((uint64_t)res[1] > announced) { announced = (uint64_t)res[1]; bcast_version = announced; bcast_next = true; }
+        if (res[0]) break;          // some rank's loop was terminated: every rank leaves after this wave
       } else if (!ok) {
         break;
       }
@@ -145,6 +178,9 @@ class DataThreadLoop : public ThreadLoop {
   }
 
   int64_t waves() const { return waves_.load(); }
+  // version / plain sum of the flat weights this loop installed last (multi-rank tests check that followers got the trainer's)
+  int64_t weightsVersion() const { return w_version_.load(); }
+  double weightsChecksum() const { return w_sum_.load(); }
   int concurrentGames() const { return std::max(1, cfg_.concurrent_games); }
 
  private:
@@ -154,7 +190,14 @@ class DataThreadLoop : public ThreadLoop {
   const int seed_;
   std::shared_ptr<Comm> comm_;
   const int comm_root_;
+  void noteWeights(const std::vector<float>& w, uint64_t ver) {
+    double acc = 0;
+    for (float x : w) acc += x;
+    w_sum_ = acc; w_version_ = (int64_t)ver;
+  }
   std::atomic<int64_t> waves_{0};
+  std::atomic<int64_t> w_version_{0};
+  std::atomic<double> w_sum_{0.0};
 };
 
 std::shared_ptr<ThreadLoop> create_cfr_thread(std::shared_ptr<ModelLocker> locker, std::shared_ptr<ValuePrioritizedReplay> replay,
@@ -387,6 +430,8 @@ PYBIND11_MODULE(rela, m) {
       .def(py::init<std::shared_ptr<ModelLocker>, std::shared_ptr<ValuePrioritizedReplay>, const RecursiveSolvingParams&, int>(),
            py::arg("model_locker"), py::arg("replay"), py::arg("params"), py::arg("thread_id"))
       .def_property_readonly("waves", &DataThreadLoop::waves, "rebel_b200 extension: waves of concurrent_games subgames completed")
+      .def_property_readonly("weights_version", &DataThreadLoop::weightsVersion, "rebel_b200 extension: version of the weights this loop installed last")
+      .def_property_readonly("weights_checksum", &DataThreadLoop::weightsChecksum, "rebel_b200 extension: plain sum of those flat weights")
       .def_property_readonly("concurrent_games", &DataThreadLoop::concurrentGames);
 
   py::class_<Context>(m, "Context")
@@ -406,19 +451,15 @@ PYBIND11_MODULE(rela, m) {
       .def("broadcast_weights", &Comm::broadcastWeights, py::arg("flat"), py::arg("root") = 0)
       .def("reduce_sum", &Comm::reduceSum, py::arg("tensor"), py::arg("root") = 0);
   m.def("comm_unique_id", &comm_unique_id, "rebel_b200 extension: ncclGetUniqueId (call on one rank, hand the 128 bytes to the others)");
-  m.def("set_example_comm", &set_example_comm, py::arg("comm"), py::arg("root") = 0,
-        "rebel_b200 extension: generator loops created after this call deliver every wave's examples to rank `root`'s replay "
-        "(grouped ncclSend / ncclRecv from the device buffers); None restores the local replay.");
+  m.def("set_generator_comm", &set_example_comm, py::arg("comm"), py::arg("root") = 0,
+        "rebel_b200 extension (one process per GPU): the generator loop created after this call delivers every wave's examples to "
+        "rank `root`'s replay (grouped ncclSend / ncclRecv from the device buffers) and, on the other ranks, follows the weights of "
+        "rank `root`'s ModelLocker (ncclBroadcast), all stream-ordered between two waves; None restores single-process behaviour.");
+  m.def("set_example_comm", &set_example_comm, py::arg("comm"), py::arg("root") = 0, "alias of set_generator_comm");
 
   py::class_<ModelLocker, std::shared_ptr<ModelLocker>>(m, "ModelLocker")
       .def(py::init<std::vector<py::object>, const std::string&>())
       .def("update_model", &ModelLocker::updateModel)
-      .def("set_comm", [](ModelLocker& l, std::shared_ptr<Comm> c, int root) {
-             l.setBroadcast(c ? std::function<void(std::vector<float>&)>([c, root](std::vector<float>& w) {
-               if (cfrb_comm_broadcast_weights(c->get(), w.data(), w.size(), root) < 0) throw std::runtime_error(cfrb_last_error());
-             }) : nullptr);
-           }, py::arg("comm"), py::arg("root") = 0,
-           "rebel_b200 extension: update_model becomes a collective — every rank calls it, rank `root`'s weights are broadcast (ncclBroadcast)")
       .def_property_readonly("version", &ModelLocker::version, "rebel_b200 extension: number of weight snapshots taken");
 
   m.def("compute_exploitability_fp", &compute_exploitability_fp, py::arg("params"));
