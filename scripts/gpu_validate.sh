@@ -13,6 +13,7 @@ timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -4 | 
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -2 $O/${TAG}_bench.err
 timeout 600 python bench.py --workload solve --steps 10 --warmup 3 > $O/${TAG}_bench_solve.json 2> $O/${TAG}_bench_solve.err; tail -2 $O/${TAG}_bench_solve.err
 timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err; tail -2 $O/${TAG}_bench_reference.err
+for w in config4 config5; do timeout 400 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err; tail -1 $O/${TAG}_bench_$w.err; done
 timeout 120 python scripts/tc_trace.py > $O/${TAG}_tc_trace.log 2>&1
 for net in tcx2 zero; do timeout 200 python scripts/datagen_probe.py --net $net; done > $O/${TAG}_datagen_probe.log 2>&1
 timeout 120 python scripts/cfr_probe.py > $O/${TAG}_cfr_probe.log 2>&1

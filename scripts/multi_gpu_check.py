@@ -3,7 +3,7 @@
 torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/multi_gpu_check.py"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch, torch.distributed as dist
+import numpy as np, torch, torch.distributed as dist
 from rebel_b200 import rela
 from rebel_b200.models import Net2, flatten_state_dict
 
@@ -11,12 +11,11 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 D, F, K = 1, 4, 512
-Q = 2 + (1 + 2 * D * F) + 2 * F ** D
 
 
 def net(seed):
     torch.manual_seed(seed)
-    return Net2(Q, F ** D, n_hidden=256, n_layers=2, use_layer_norm=True)
+    return Net2(num_faces=F, num_dice=D, n_hidden=256, n_layers=2, use_layer_norm=True)
 
 
 ids = [rela.comm_unique_id()] if rank == 0 else [None]
@@ -40,7 +39,7 @@ def wait(cond, what, limit=120):
         time.sleep(0.002)
 
 
-want = [float(flatten_state_dict(net(100).state_dict()).double().sum())]
+want = [float(np.asarray(flatten_state_dict(net(100).state_dict()), dtype=np.float64).sum())]
 wait(lambda: loop.waves >= 6, "first waves")
 ok = abs(loop.weights_checksum - want[0]) < 1e-9 * max(1.0, abs(want[0]))
 print(f"rank {rank}: after {loop.waves} waves weights v{loop.weights_version} sum {loop.weights_checksum:.9f} (trainer's {want[0]:.9f}) {'OK' if ok else 'MISMATCH'}", flush=True)
@@ -49,7 +48,7 @@ for step in range(3):                                    # the trainer moves on;
     new = net(200 + step)
     if rank == 0:
         locker.update_model(new)
-    w = float(flatten_state_dict(new.state_dict()).double().sum())
+    w = float(np.asarray(flatten_state_dict(new.state_dict()), dtype=np.float64).sum())
     wait(lambda: abs(loop.weights_checksum - w) < 1e-9 * max(1.0, abs(w)), f"weights of update {step}")
     print(f"rank {rank}: update {step} arrived at wave {loop.waves} as v{loop.weights_version}", flush=True)
 if rank == 0:
