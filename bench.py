@@ -690,12 +690,13 @@ def run_datagen(args):
             bytes_subgame += cnt * (4 * H * (E + 6 * E / 2) + 4 * L * (Q + H) + 8 * H)      # SURVEY 8(d), fp32-equivalent algorithmic bytes
     bytes_launch = bytes_subgame / len(prof)
     achieved = flops_launch / (net_us * 1e-6) / 1e12 if net_us > 0 else 0.0
-    traffic = None
+    traffic = cfr_traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tj.get(f"datagen_{D}x{F}_{K}", {}).get("value_net_dram_bytes_per_launch")
+        cfr_traffic = tj.get(f"datagen_{D}x{F}_{K}", {}).get("cfr_dram_bytes_per_launch")
     except Exception:
-        traffic = None
+        traffic = cfr_traffic = None
     roofline = {"bound": "tensor", "kernel": "leaf value net (Net2 forward over all pseudo-leaf rows of the wave, tcgen05)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
                 "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "peak_source": peaks["src"],
@@ -706,7 +707,7 @@ def run_datagen(args):
                                "avg_launch_ms": cfr_us * 1e-3, "algorithmic_bytes_per_launch": bytes_launch,
                                "achieved": bytes_launch / (cfr_us * 1e-6) / 1e9 if cfr_us > 0 else 0.0, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                "frac": bytes_launch / (cfr_us * 1e-6) / 1e9 / peaks["hbm_gbs"] if cfr_us > 0 else 0.0,
-                               "share_of_step": float((tot - tnet).sum() / tot.sum()),
+                               "share_of_step": float((tot - tnet).sum() / tot.sum()), "traffic": cfr_traffic,
                                "note": "SURVEY 8(d) fp32-equivalent bytes of the subgames actually in the waves; the tables are fp64 (about twice the table bytes move)"},
                 "wave_device_ms": [round(float(x), 2) for x in tot]}
     out = {

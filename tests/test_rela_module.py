@@ -426,7 +426,7 @@ def test_datagen_distribution_matches_reference(rela, golden, D, F):
     band is measured, not chosen: the same statistics between two disjoint seed sets of the REFERENCE (fixture
     datagen_stats.npz, oracle/make_golden_r2.py).  Only complete games are counted on the GPU side (a wave loop stops mid-game)."""
     from rebel_b200.models import flatten_state_dict, make_selfplay_net
-    from tests.test_gpu_parity import _note
+    from test_gpu_parity import _note
     A, H, Q = game_dims(D, F)
     g = golden("datagen_stats.npz")
     net = make_selfplay_net(D, F, seed=0)
@@ -465,7 +465,7 @@ def test_config5_with_the_value_net_vs_reference(rela, golden):
     exploitability of the averaged strategy is compared: the fp32 SIMT net must agree with the reference like the reference's
     two builds agree with each other (3x their difference, at least 2e-3), the tensor-core nets within 1e-2 of it."""
     from rebel_b200.models import flatten_state_dict, make_selfplay_net
-    from tests.test_gpu_parity import _note
+    from test_gpu_parity import _note
     g = golden("config5_net.npz")
     D, F, iters, reps = [int(x) for x in g["cfg"]]
     want = g["exploitability"].mean(1)
