@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--faces", type=int, default=0)
     ap.add_argument("--repeats", type=int, default=0, help="config5: sampled recursive strategies in total (0 = 4097)")
     ap.add_argument("--net", default="auto", choices=["auto", "fp32", "tc", "tcx2"],
-                    help="value-net kernel: tcx2 (default) = tcgen05 fp16 with packed-half GELU, tc = tcgen05 fp16 with fp32 GELU, fp32 = SIMT parity net")
+                    help="value-net kernel: tcx2 (default) = tcgen05 fp16 operands with the fast fp32 tanh GELU, tc = the same with the logistic fp32 GELU, fp32 = SIMT parity net")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="subgames in the CPU-baseline sample (0 = auto)")
     return ap.parse_args()
@@ -410,7 +410,7 @@ def run_solve(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 (CFR tables) / " + ("f16 operands, f32 accumulate + LayerNorm, " + ("f16x2" if mode == rb.NET_TC_F16X2 else "f32") + " GELU (value net, tcgen05)" if is_tc else "f32 (value net)"),
+        "dtype": "f64 (CFR tables) / " + ("f16 operands, f32 accumulate + LayerNorm, " + ("f32 tanh" if mode == rb.NET_TC_F16X2 else "f32 logistic") + " GELU (value net, tcgen05)" if is_tc else "f32 (value net)"),
         "data": "synthetic", "config": workload_config(args, K),
         "impl_config": {"value_net_kernel": mode_name, "parallelism": f"dp{world}", "l2": "256 MiB memset between steps, inside the timed region"},
         "clocks": clocks,
@@ -713,7 +713,7 @@ def run_datagen(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "f64 (CFR tables, beliefs) / " + ("f16 operands, f32 accumulate + LayerNorm, " + ("f16x2" if mode == rb.NET_TC_F16X2 else "f32") + " GELU (value net, tcgen05)" if is_tc else "f32 (value net)"),
+        "dtype": "f64 (CFR tables, beliefs) / " + ("f16 operands, f32 accumulate + LayerNorm, " + ("f32 tanh" if mode == rb.NET_TC_F16X2 else "f32 logistic") + " GELU (value net, tcgen05)" if is_tc else "f32 (value net)"),
         "data": "synthetic", "config": workload_config(args),
         "impl_config": {"value_net_kernel": mode_name, "parallelism": f"dp{world}", "games_per_gpu": K, "walk": "device (mt19937 streams in HBM)",
                         "replay": "device-resident rows", "l2": "256 MiB memset between steps, inside the timed region; every wave re-initialises its solver tables"},

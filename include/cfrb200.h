@@ -63,8 +63,10 @@ enum {
   CFRB_NET_FP32 = 1,      /* fp32 SIMT kernel: parity path, matches libtorch fp32 to ~1e-6 */
   CFRB_NET_TC_F16 = 2,    /* tcgen05 tensor-core kernel: fp16 operands, fp32 accumulate/LayerNorm/GELU
                              (the reference's own `half_inference` option, selfplay.py:42-43,211) */
-  CFRB_NET_TC_F16X2 = 3   /* same kernel, GELU evaluated on packed fp16 pairs (HFMA2 + tanh.approx.f16x2) after the
-                             fp32 LayerNorm: ~40 % fewer epilogue instructions, ~1.6x the activation rounding noise */
+  CFRB_NET_TC_F16X2 = 3   /* same kernel with the fast GELU: y/2 (1 + tanh(poly)) with packed f32x2 FMAs and tanh.approx.f32, one
+                             rounding to fp16 at the end (same accuracy as mode 2, 1 instead of 2 MUFU operations per element).
+                             CFRB_X2_GELU=half selects the packed-fp16 evaluation (HFMA2 + tanh.approx.f16x2): 6 % faster, but
+                             that instruction truncates towards zero and biases every activation (see DESIGN.md "P5") */
 };
 
 /* Subgame solver.  In FP mode cfrb_fetch's "last" is FP::last_strategies (belief x best response), "avg" is
@@ -229,6 +231,10 @@ int cfrb_selfplay_state(cfrb_handle* h, int32_t* last_bid, int32_t* player, doub
 /* Test aid: the division-free quotient of the regret-matching step (reciprocal of the node's sum + two fused multiply-add
  * corrections, csrc/cfr_d2v2.cuh) against IEEE division on blocks x 256 x 4096 pseudo-random operand pairs. */
 int cfrb_debug_div_check(cfrb_handle* h, uint64_t seed, int32_t blocks, uint64_t* mismatches);
+/* Test aid: the packed-half GELU of the value-net epilogue on every fp16 input: out[i] = fp16 bits of f(fp16 with bit pattern i), i < 65536;
+ * what 0 = tanh.approx.f16x2, 1 / 2 = GELU(2 x) computed from x = y / 2 the way the packed-half / fp32-tanh epilogue does (tests pin the arithmetic model of
+ * oracle/ref_harness.cc against it). */
+int cfrb_debug_gelu_table(cfrb_handle* h, int32_t what, uint16_t* out);
 /* Roots (last_bid, player_id) of the subgames of the current wave — also of a wave built on the device by cfrb_selfplay_wave
  * (synchronises then).  Writes min(n, cap) entries, returns n. */
 int cfrb_wave_roots(cfrb_handle* h, int32_t* last_bid, int32_t* player_id, int32_t cap);

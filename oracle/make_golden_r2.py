@@ -71,6 +71,37 @@ def datagen(R, threads=8):
     np.savez_compressed(os.path.join(OUT, "datagen_stats.npz"), **out)
 
 
+def datagen_models(R, threads=8):
+    """The reference's RlRunner loops with the ARITHMETIC MODEL of the tensor-core value-net kernels inside the reference's own net
+    (ref_set_net_emulation: fp16 operands, and for model 2 the packed-half GELU) — what the reference itself generates when its
+    net is evaluated the way the tcgen05 kernels evaluate it.  Added to datagen_stats.npz as count_m{1,2}_* etc."""
+    import torch
+    torch.set_num_threads(1)
+    from rebel_b200.models import make_selfplay_net
+    path = os.path.join(OUT, "datagen_stats.npz")
+    out = dict(np.load(path))
+    for (D, F, games_per_thread) in [(1, 6, 1300), (1, 4, 1500)]:
+        A, H, Q = game_dims(D, F)
+        w = weights(D, F)
+        net = make_selfplay_net(D, F, seed=0)
+        for model in (2, 1):
+            res = [None] * threads
+            t0 = time.time()
+
+            def work(i):
+                R.set_net_emulation(model)          # thread-local
+                res[i] = R.rl_runner(D, F, 9000 + i, n_games=games_per_thread, num_iters=1024, net_w=w, cap=games_per_thread * 16)
+                R.set_net_emulation(0)
+            th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+            [t.start() for t in th]; [t.join() for t in th]
+            q = np.concatenate([r[0] for r in res]); v = np.concatenate([r[1] for r in res])
+            cnt, vsum, vsq, lsum = last_action_stats(q, v, A, net)
+            out[f"count_m{model}_{D}x{F}"] = cnt; out[f"val_sum_m{model}_{D}x{F}"] = vsum
+            out[f"val_sq_m{model}_{D}x{F}"] = vsq; out[f"loss_sum_m{model}_{D}x{F}"] = lsum
+            print(f"datagen {D}x{F} kernel model {model}: {len(q)} examples in {time.time() - t0:.0f} s; counts {cnt / cnt.sum()}", flush=True)
+            np.savez_compressed(path, **out)
+
+
 def config5(R, RF=None):
     D, F, iters, reps = 1, 4, 1024, 64
     t0 = time.time()
@@ -131,4 +162,4 @@ if __name__ == "__main__":
         if k == "config5":
             config5(R, RF)
         else:
-            {"datagen": datagen, "band": band}[k](RF if k == "datagen" else R)
+            {"datagen": datagen, "datagen_models": datagen_models, "band": band}[k](RF if k.startswith("datagen") else R)

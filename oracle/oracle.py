@@ -187,6 +187,15 @@ class Oracle:
         f.restype = None
         f(float(rel), int(seed))
 
+    def set_net_emulation(self, model):
+        """Reference builds only: 0 = the reference's fp32 ATen net, 1 / 2 = arithmetic model of the tcgen05 value-net kernels
+        (fp16 operands; fp32 GELU / packed-half GELU) inside the reference's net, for cfr_solve and rl_runner on this thread."""
+        assert self.kind != "port"
+        f = self.lib.ref_set_net_emulation
+        f.argtypes = [C.c_int]
+        f.restype = None
+        f(int(model))
+
     def rl_runner(self, D, F, seed, n_games, num_iters=1024, max_depth=2, linear_update=True,
                   random_action_prob=0.25, sample_leaf=True, net_w=None, hidden=256, cap=4096, use_cfr=True):
         A, H, Q = game_dims(D, F)

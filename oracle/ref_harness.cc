@@ -55,6 +55,7 @@ namespace {
 thread_local std::string g_err;
 thread_local double g_noise_rel = 0;       // ref_set_net_noise: relative gaussian noise on the Net2 outputs of ref_cfr_solve
 thread_local uint64_t g_noise_seed = 0;
+thread_local int g_net_emulation = 0;      // ref_set_net_emulation: 0 fp32 ATen (the reference), 1 / 2 arithmetic model of the tcgen05 kernels
 
 SubgameSolvingParams make_params(int num_iters, int max_depth, int linear_update, int dcfr,
                                  double dcfr_alpha, double dcfr_beta, double dcfr_gamma) {
@@ -87,11 +88,43 @@ class FlatNet2 : public IValueNet {
     w3 = take({H, hidden}); b3 = take({H});
     hidden_ = hidden;
   }
+  // Arithmetic model of the tensor-core value-net kernels (rebel_b200/csrc/leaf_mlp_tc3.cuh) inside the reference's own net, used
+  // to derive parity bands (make_golden_r2.py): query columns, weights and both hidden activations rounded to fp16 (fp32
+  // accumulation, fp32 LayerNorm), GELU either in fp32 (model 1, CFRB_NET_TC_F16: the 3-term logistic form) or in packed-half
+  // arithmetic with one rounding per HMUL2 / HFMA2 / tanh (model 2, CFRB_NET_TC_F16X2).
+  static torch::Tensor h16(const torch::Tensor& x) { return x.to(torch::kHalf).to(torch::kFloat32); }   // one fp16 rounding
+  static torch::Tensor gelu_model(const torch::Tensor& y, int model) {
+    if (model == 1) {      // gelu_tc (leaf_mlp_tc.cuh): y / (1 + 2^(y p(y^2))) in fp32, result rounded to fp16
+      auto y2 = (y * y).clamp_max(52.f);
+      auto p = y2 * (y2 * 1.014244e-3f - 1.0677588e-1f) - 2.3011216f;
+      return h16(y / (1.f + torch::exp2(y * p)));
+    }
+    // gelu_hy_x2 (leaf_mlp_tc3.cuh): hy = y / 2 rounded to fp16, then HMUL2 / HFMA2 / tanh.approx.f16x2 with one rounding each
+    // (the fp32 product of two fp16 values is exact, so rounding the fp32 result of a*b+c once models the fused HFMA2)
+    const float c2 = (float)(at::Half)(-1.124832e-2f), c1 = (float)(at::Half)(2.960456e-1f), c0 = (float)(at::Half)(1.594992f);
+    auto hy = h16(0.5f * y);
+    auto s = h16(hy * hy).clamp_max(13.f);
+    auto p = h16(s * h16(s * c2 + c1) + c0);
+    auto u = h16(hy * p);
+    auto t = h16(torch::tanh(u));
+    return h16(hy * t + hy);
+  }
+  torch::Tensor hidden_model(torch::Tensor pre, const torch::Tensor& g, const torch::Tensor& be, int model) {
+    return gelu_model(torch::layer_norm(pre, {hidden_}, g, be, 1e-5), model);
+  }
   torch::Tensor compute_values(const torch::Tensor q) override {
     torch::NoGradGuard ng;
-    auto x = torch::gelu(torch::layer_norm(torch::linear(q, w1, b1), {hidden_}, g1, be1, 1e-5));
-    x = torch::gelu(torch::layer_norm(torch::linear(x, w2, b2), {hidden_}, g2, be2, 1e-5));
-    auto y = torch::linear(x, w3, b3);
+    torch::Tensor y;
+    if (emulation) {
+      if (!w1h.defined()) { w1h = w1.to(torch::kHalf).to(torch::kFloat32); w2h = w2.to(torch::kHalf).to(torch::kFloat32); w3h = w3.to(torch::kHalf).to(torch::kFloat32); }
+      auto x = hidden_model(torch::linear(q.to(torch::kHalf).to(torch::kFloat32), w1h, b1), g1, be1, emulation);
+      x = hidden_model(torch::linear(x, w2h, b2), g2, be2, emulation);
+      y = torch::linear(x, w3h, b3);
+    } else {
+      auto x = torch::gelu(torch::layer_norm(torch::linear(q, w1, b1), {hidden_}, g1, be1, 1e-5));
+      x = torch::gelu(torch::layer_norm(torch::linear(x, w2, b2), {hidden_}, g2, be2, 1e-5));
+      y = torch::linear(x, w3, b3);
+    }
     if (noise_rel > 0) {   // parity-band experiments (SURVEY appendix B "pert"): outputs * (1 + rel * N(0,1)), seeded
       float* p = y.data_ptr<float>();
       std::normal_distribution<double> n01(0.0, 1.0);
@@ -99,6 +132,8 @@ class FlatNet2 : public IValueNet {
     }
     return y;
   }
+  int emulation = 0;
+  torch::Tensor w1h, w2h, w3h;
   double noise_rel = 0;
   std::mt19937_64 noise_gen{0};
   void add_training_example(const torch::Tensor q, const torch::Tensor v) override {
@@ -181,6 +216,7 @@ const char* ref_last_error() { return g_err.c_str(); }
 
 // Parity-band experiments: the next ref_cfr_solve calls of this thread multiply every value-net output by 1 + rel * N(0,1).
 void ref_set_net_noise(double rel, uint64_t seed) { g_noise_rel = rel; g_noise_seed = seed; }
+void ref_set_net_emulation(int model) { g_net_emulation = model; }
 
 // tree.h:51-70.  out rows: last_bid, player_id, children_begin, children_end, parent, depth.
 int ref_unroll_tree(int D, int F, int last_bid, int player_id, int max_depth, int32_t* out,
@@ -247,6 +283,7 @@ int ref_cfr_solve(int D, int F, int last_bid, int player_id, const double* belie
       auto n2 = std::make_shared<FlatNet2>(net_w, 2 + A + 2 * H, hidden, H);
       n2->noise_rel = g_noise_rel;
       n2->noise_gen.seed(g_noise_seed);
+      n2->emulation = g_net_emulation;
       net = n2;
     } else if (has_pleaf) {
       net = create_zero_net(H, false);
@@ -431,6 +468,9 @@ static int rl_runner_impl(int D, int F, int num_iters, int max_depth, int linear
     std::shared_ptr<IValueNet> net;
     if (net_w) {
       auto n = std::make_shared<FlatNet2>(net_w, Q, hidden, H);
+      n->emulation = g_net_emulation;
+      n->noise_rel = g_noise_rel;
+      n->noise_gen.seed(g_noise_seed + (uint64_t)seed);
       eq = &n->examples_q;
       ev = &n->examples_v;
       net = n;

@@ -81,6 +81,7 @@ def lib():
     L.cfrb_selfplay_state.argtypes = [vp, _ip, _ip, _dp]
     L.cfrb_stream_wait.argtypes = [vp, vp]
     L.cfrb_debug_div_check.argtypes = [vp, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
+    L.cfrb_debug_gelu_table.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint16)]
     L.cfrb_wave_roots.argtypes = [vp, _ip, _ip, C.c_int32]
     L.cfrb_mark.argtypes = [vp, C.c_int32, vp]
     L.cfrb_mark_elapsed_ms.argtypes = [vp, C.c_int32, C.c_int32, _fp]
@@ -277,6 +278,13 @@ class WaveSolver:
         lb = np.zeros(self.n, np.int32); pl = np.zeros(self.n, np.int32); b = np.zeros((self.n, 2, self.H), np.float64)
         _check(lib().cfrb_selfplay_state(self._h, _p(lb, _ip), _p(pl, _ip), _p(b, _dp)))
         return lb, pl, b
+
+    def gelu_table(self, what):
+        """fp16 -> fp16 table of tanh.approx.f16x2 (what=0) / of the epilogue's GELU from hy = y/2, packed-half (what=1) or fp32-tanh
+        (what=2) evaluation, as float16 arrays (x, f(x))."""
+        out = np.zeros(65536, np.uint16)
+        _check(lib().cfrb_debug_gelu_table(self._h, what, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return np.arange(65536, dtype=np.uint16).view(np.float16), out.view(np.float16)
 
     def div_check(self, seed, blocks):
         bad = C.c_uint64(0)

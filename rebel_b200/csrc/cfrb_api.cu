@@ -114,6 +114,7 @@ struct cfrb_handle {
   DevBuf<int> d_sg_tmpl, d_sg_player, d_sg_row_off, d_sg_act, d_steps;
   DevBuf<float> d_X, d_out, d_dbg;
   long long* dbg_trace = nullptr;   // set only inside cfrb_debug_net_trace
+  int x2_gelu = 2;                  // GELU variant of CFRB_NET_TC_F16X2 (leaf_mlp_tc3.cuh kGelu): 2 = fp32 tanh, 1 = packed half
   bool tc_gen1 = false;             // CFRB_TC_GEN=1: the round-1 one-tile kernel (leaf_mlp_tc.cuh) instead of leaf_mlp_tc3.cuh
   DevBuf<__half> d_Xh;
   WaveState<float> sf;
@@ -651,10 +652,14 @@ static int create_impl(const cfrb_config* cfg, cfrb_handle* h) {
       h->tc_gen1 = gen && *gen == '1';
       const cfrb::tc::Tc3Layout T3(h->Qpad);
       if (T3.smem_bytes > max_optin) return fail(CFRB_EINVAL, "tensor-core value net does not fit shared memory for this game shape");
-      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
-      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
-      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
-      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      CK(cudaFuncSetAttribute(cfrb::tc::leaf_mlp_tc3_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3.smem_bytes));
+      // CFRB_NET_TC_F16X2's GELU: fp32 tanh (default) or the packed-half evaluation (CFRB_X2_GELU=half), see leaf_mlp_tc3.cuh
+      if (const char* e = std::getenv("CFRB_X2_GELU")) h->x2_gelu = std::string(e) == "half" ? 1 : 2;
     }
   }
   CK(cudaFuncSetAttribute(cfrb::leaf_mlp_fp32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -900,10 +905,13 @@ static int launch_net(cfrb_handle* h, cudaStream_t st, float* dbg1, float* dbg2)
       else if (x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<false, true>, a));
       else CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc_kernel<false, false>, a));
     } else {
-      if (dbg && x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<true, true>, a));
-      else if (dbg) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<true, false>, a));
-      else if (x2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<false, true>, a));
-      else CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<false, false>, a));
+      const int gelu = x2 ? h->x2_gelu : 0;
+      if (dbg && gelu == 1) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<true, 1>, a));
+      else if (dbg && gelu == 2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<true, 2>, a));
+      else if (dbg) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<true, 0>, a));
+      else if (gelu == 1) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<false, 1>, a));
+      else if (gelu == 2) CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<false, 2>, a));
+      else CK(cudaLaunchKernelEx(&lc, cfrb::tc::leaf_mlp_tc3_kernel<false, 0>, a));
     }
   } else {
     // a wave built on the device: worst-case grid, CTAs beyond the device-side row count return at once
@@ -1387,6 +1395,39 @@ int cfrb_debug_div_check(cfrb_handle* h, uint64_t seed, int32_t blocks, uint64_t
   cudaFree(d);
   CK(e);
   *mismatches = out;
+  return CFRB_OK;
+}
+
+// Development / test aid: what the packed-half GELU of the value-net epilogue computes, for every fp16 input.  what = 0:
+// tanh.approx.f16x2 itself; 1 / 2: gelu_hy_x2 / gelu_hy_t32 with hy = the input (leaf_mlp_tc3.cuh).  out[i] = fp16 bits of f(fp16 with bits i).
+namespace {
+__global__ void gelu_table_kernel(int what, unsigned short* out) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 65536u) return;
+  const __half x = __ushort_as_half((unsigned short)i);
+  unsigned short r;
+  if (what == 0) {
+    const __half2 u = __halves2half2(x, x);
+    uint32_t t;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+    r = (unsigned short)(t & 0xffffu);
+  } else {
+    const float f = __half2float(x);
+    r = (unsigned short)((what == 1 ? cfrb::tc::gelu_hy_x2(f, f) : cfrb::tc::gelu_hy_t32(f, f)) & 0xffffu);
+  }
+  out[i] = r;
+}
+}  // namespace
+int cfrb_debug_gelu_table(cfrb_handle* h, int32_t what, uint16_t* out) {
+  if (!h || !out || what < 0 || what > 2) return fail(CFRB_EINVAL, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  unsigned short* d = nullptr;
+  CK(cudaMalloc((void**)&d, 65536 * sizeof(unsigned short)));
+  gelu_table_kernel<<<256, 256, 0, h->own_stream>>>(what, d);
+  cudaError_t e = cudaStreamSynchronize(h->own_stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d, 65536 * sizeof(unsigned short), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(e);
   return CFRB_OK;
 }
 

@@ -20,7 +20,9 @@
 //     (W'[j][k] = W[j][k] - mean_j W[j][k]), so sum_j y_j = 0 by construction and LayerNorm needs only sum_j y_j^2: the
 //     running-sum chain, the mean and the shift disappear from the epilogue (two-pass-quality variance for free).
 //  3. HALVED GELU ARGUMENT.  The affine produces hy = y / 2 directly (gamma / 2 and beta / 2 are stored), the tanh polynomial is
-//     rescaled to hy, and GELU(y) = hy + hy * tanh(.): one multiply fewer per pair than before.
+//     rescaled to hy, and GELU(y) = hy + hy * tanh(.): one multiply fewer per pair than before.  Default evaluation: packed
+//     f32x2 FMAs + tanh.approx.f32, rounded to fp16 once (gelu_hy_t32); the packed-fp16 evaluation (gelu_hy_x2) is 6 % faster
+//     but inherits the truncation of tanh.approx.f16x2 and is kept as a measurement option only.
 //  4. One mbarrier arrival per WARP (lane 0 after __syncwarp) instead of per thread, one A-operand hand-over per phase instead of
 //     four, LayerNorm partial sums exchanged between the four warps of a row quadrant only (named barrier of 128 threads).
 //  5. Weights (once per CTA) and query tiles (double-buffered, issued two tiles ahead by the MMA warp) arrive by cp.async.bulk.
@@ -72,14 +74,34 @@ __device__ __forceinline__ uint32_t gelu_hy_x2(float hy0, float hy1) {
   return *reinterpret_cast<const uint32_t*>(&g);
 }
 
+// The same function with fp32 arithmetic (packed f32x2 FMAs, tanh.approx.f32) and ONE rounding to fp16 at the end.  Measured
+// on B200 (profiles/r2_gelu_table.log): tanh.approx.f16x2 truncates towards zero (mean error -2.4e-4 sign(u) on 0.25 <= |u| < 4, one
+// fp16 ulp at most), which gives gelu_hy_x2 a coherent negative bias of 1.6e-4 .. 3.9e-4 on every activation with |y| > 0.5; the
+// data-generation statistics of the self-play loop respond to that bias (tests/test_rela_module.py P5), not to the rounding noise.
+__device__ __forceinline__ uint32_t gelu_hy_t32(float hy0, float hy1) {
+  const f32x2 hy = pack2(hy0, hy1);
+  float s0, s1;
+  unpack2(mul2(hy, hy), s0, s1);
+  const f32x2 s = pack2(fminf(s0, 13.f), fminf(s1, 13.f));
+  const f32x2 p = fma2(s, fma2(s, pack2(-1.124832e-2f, -1.124832e-2f), pack2(2.960456e-1f, 2.960456e-1f)), pack2(1.594992f, 1.594992f));
+  float u0, u1, t0, t1, g0, g1;
+  unpack2(mul2(hy, p), u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  unpack2(fma2(hy, pack2(t0, t1), hy), g0, g1);
+  const __half2 g = __floats2half2_rn(g0, g1);
+  return *reinterpret_cast<const uint32_t*>(&g);
+}
+
 #define CFRB_TRACE3(slot)                                                                 \
   do {                                                                                    \
     if (kDebug && a.trace && blockIdx.x == 0 && (slot) < 2048) a.trace[slot] = clock64(); \
   } while (0)
 
-// kGeluX2: packed-half GELU (CFRB_NET_TC_F16X2; the LayerNorm parameters in the blob are gamma / 2, beta / 2) or fp32 GELU
+// kGelu: 0 = fp32 logistic GELU (CFRB_NET_TC_F16); 1 = packed-half GELU, 2 = fp32 tanh GELU (both CFRB_NET_TC_F16X2: the LayerNorm
+// parameters in the blob are gamma / 2, beta / 2)
 // (CFRB_NET_TC_F16; gamma, beta).
-template <bool kDebug, bool kGeluX2>
+template <bool kDebug, int kGelu>
 __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc3_kernel(TcArgs a) {
   constexpr int kMmaWarp = kEpiThreads / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -297,8 +319,10 @@ __global__ void __launch_bounds__(kThreads, 1) leaf_mlp_tc3_kernel(TcArgs a) {
           const float4 pp = *reinterpret_cast<const float4*>(ln + part_id * kColsPerThread + jj);   // {g_j, g_j+1, b_j, b_j+1} (x2: halved)
           float y0, y1;
           unpack2(fma2(mul2(pack2(__uint_as_float(xr[jj]), __uint_as_float(xr[jj + 1])), rstd2), pack2(pp.x, pp.y), pack2(pp.z, pp.w)), y0, y1);
-          if (kGeluX2) {
+          if (kGelu == 1) {
             pk[i] = gelu_hy_x2(y0, y1);
+          } else if (kGelu == 2) {
+            pk[i] = gelu_hy_t32(y0, y1);
           } else {
             const __half2 h = __floats2half2_rn(gelu_tc(y0), gelu_tc(y1));
             pk[i] = *reinterpret_cast<const uint32_t*>(&h);

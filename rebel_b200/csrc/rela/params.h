@@ -33,7 +33,7 @@ struct RecursiveSolvingParams {
   SubgameSolvingParams subgame_params;
   // ---- rebel_b200 extensions
   int concurrent_games = env_int("CFRB_CONCURRENT_GAMES", 1024);   // self-play games advanced in lock-step per thread loop
-  int net_mode = env_int("CFRB_NET_MODE", 3);                      // include/cfrb200.h CFRB_NET_*: 3 = tcgen05 fp16, packed-half GELU
+  int net_mode = env_int("CFRB_NET_MODE", 3);                      // include/cfrb200.h CFRB_NET_*: 3 = tcgen05 fp16 operands, fast tanh GELU
   int state_dtype = env_int("CFRB_STATE_DTYPE", 0);                // CFRB_STATE_*: 0 = fp64 tables
   int host_walk = env_int("CFRB_HOST_WALK", 0);                    // 1 = per-game sampling on the host (parity mode of the device walk)
 };

@@ -319,8 +319,8 @@ def test_long_horizon_within_reference_noise(rb, golden, net_weights, D, F, net_
     2.1e-4 / max 2.8e-3 under a ONE-ulp fp32 perturbation of its net outputs ('pert'); that band, or 3x the
     reference's own FMA/no-FMA self-noise when larger, is the criterion.  Tensor-core nets: the band is DERIVED, not chosen —
     the REFERENCE solver is run with its own net perturbed the way the tcgen05 kernels perturb it (weights rounded to fp16; on top
-    of that, independent relative noise on every output at the kernels' measured level, 5.4e-4 for fp32-GELU and 7.7e-4 for the
-    packed-half GELU, 8 seeds; tests/golden/net_band.npz from oracle/make_golden_r2.py), and the GPU must stay within 3x the
+    of that, independent relative noise on every output at the kernels' measured level, 5.4e-4 — both GELU variants measure
+    4.7e-4 .. 5.0e-4 — 8 seeds; tests/golden/net_band.npz from oracle/make_golden_r2.py), and the GPU must stay within 3x the
     mean response of the reference to that perturbation (or 3x its self-noise, or the fp32 band, whichever is larger)."""
     g = golden(f"cfr_net_{D}x{F}.npz")
     nb = golden("net_band.npz")
@@ -336,7 +336,7 @@ def test_long_horizon_within_reference_noise(rb, golden, net_weights, D, F, net_
         d = np.abs(mu[i] - a)
         band_mean, band_max = max(7e-4, 3 * self_noise), 1e-2
         if net_name != "fp32":
-            si = 0 if net_name == "tc" else 1
+            si = 0                                                     # sigma = 5.4e-4 (the 7.7e-4 set belonged to the packed-half GELU)
             pert = np.abs(nb[f"mu_pert{si}_{D}x{F}_{i}"] - a)                      # [seeds][2][H]
             w16 = np.abs(nb[f"mu_w16_{D}x{F}_{i}"] - a)
             response = max(pert.mean(), w16.mean())
