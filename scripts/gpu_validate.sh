@@ -16,6 +16,7 @@ timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > $O/${TAG}_b
 for w in config4 config5; do timeout 400 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err; tail -1 $O/${TAG}_bench_$w.err; done
 timeout 120 python scripts/tc_trace.py > $O/${TAG}_tc_trace.log 2>&1
 for net in tcx2 zero; do timeout 200 python scripts/datagen_probe.py --net $net; done > $O/${TAG}_datagen_probe.log 2>&1
+timeout 120 python scripts/gelu_table.py 2>&1 | grep -v Warn > $O/${TAG}_gelu_table.log
 timeout 120 python scripts/cfr_probe.py > $O/${TAG}_cfr_probe.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 300 --csv --log-file $O/${TAG}_launches.csv \
   python bench.py --steps 1 --warmup 1 --iters 64 --no-cpu-baseline > $O/${TAG}_ncu_bench.log 2>&1

@@ -98,12 +98,13 @@ for suffix, title in (("bench", "default workload: self-play data generation"), 
                        f"{c['achieved']:.0f} GB/s = {100 * c['frac']:.1f}% of the measured HBM copy bandwidth ({c['peak']} GB/s); {100 * c['share_of_step']:.0f}% of the step")
     if "cpu_baseline" in b:
         out.append(f"* CPU baseline in the same run: {b['cpu_baseline']}")
-for name in ("parity_notes.log", "pytest_gpu.log", "tc_trace.log", "datagen_probe.log", "cfr_probe.log", "smoke.log"):
+for name in ("parity_notes.log", "pytest_gpu.log", "tc_trace.log", "datagen_probe.log", "cfr_probe.log", "smoke.log", "gelu_table.log"):
     src = os.path.join(G, f"{tag}_{name}")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f"{tag}_{name}"))
         out.append(f"\n`{tag}_{name}`: " + {"parity_notes.log": "measured parity numbers written by the -m gpu tests", "pytest_gpu.log": "tail of pytest -m gpu",
                                            "tc_trace.log": "clock64 timeline of one CTA of the value-net kernel", "datagen_probe.log": "per-kernel time inside self-play waves (with the net / zero net)",
-                                           "cfr_probe.log": "CFR kernel alone (zero net), root and self-play waves", "smoke.log": "__graft_entry__.smoke()"}[name])
+                                           "cfr_probe.log": "CFR kernel alone (zero net), root and self-play waves", "smoke.log": "__graft_entry__.smoke()",
+                                           "gelu_table.log": "error of tanh.approx.f16x2 and of both fast-GELU evaluations on every fp16 input"}[name])
 open(os.path.join(P, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:4000])
