@@ -658,6 +658,7 @@ def run_datagen(args):
         if rank == 0:
             batch, _ = replay.sample(rows_per_wave, "cpu")     # the step's examples (of all ranks) back to HOST memory
     t1 = time.perf_counter()
+    between = loop.between_waves_ms if world > 1 else (0.0, 0.0)
     if world > 1:
         dist.barrier()
     ctx.terminate()
@@ -719,6 +720,7 @@ def run_datagen(args):
                         "replay": "device-resident rows", "l2": "256 MiB memset between steps, inside the timed region; every wave re-initialises its solver tables"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / steps,
+                "collectives_between_waves_ms": {"mean": round(between[0], 3), "max": round(between[1], 3), "note": "device time on rank 0's generator stream, includes waiting for the slowest rank"} if world > 1 else None,
                 "api": "rela.ModelLocker.update_model (weights from host memory) + rela.create_cfr_thread / Context (generator loop) + "
                        "rela.ValuePrioritizedReplay.sample(rows of the step, 'cpu') (the step's examples to host memory)" +
                        ("; N > 1: weights by ncclBroadcast, every rank's examples to rank 0's device-resident replay by ncclSend/Recv (cfrb_comm_*)" if world > 1 else ""),

@@ -116,10 +116,14 @@ class BatchedRlRunner {
       // nothing else to do, then the next wave follows on the same stream)
       rows = cfrb_selfplay_wave(h_, dev_q_[b], dev_v_[b], 0, nullptr);
       check(rows, "cfrb_selfplay_wave");
+      check(cfrb_mark(h_, 6, nullptr), "cfrb_mark");
       between_waves_(dev_q_[b], dev_v_[b], rows, cfrb_handle_stream(h_));
       check(cfrb_mark(h_, 7, nullptr), "cfrb_mark");
       check(cfrb_selfplay_wave(h_, nullptr, nullptr, 1, nullptr), "cfrb_selfplay_wave");
       check(cfrb_mark_wait(h_, 7), "cfrb_mark_wait");
+      float ms = 0;
+      check(cfrb_mark_elapsed_ms(h_, 6, 7, &ms), "cfrb_mark_elapsed_ms");     // device time of the hook (it waits for the slowest rank)
+      between_ms_sum_ += ms; between_ms_max_ = std::max(between_ms_max_, (double)ms); ++between_n_;
     } else {
       rows = cfrb_selfplay_wave(h_, dev_q_[b], dev_v_[b], 1, nullptr);
       check(rows, "cfrb_selfplay_wave");
@@ -130,6 +134,9 @@ class BatchedRlRunner {
   }
   // Hook enqueued on the handle's stream between the end of a wave (its examples are in the given device buffers) and the start
   // of the next one.
+  // device time the stream spent inside the hook: (mean, max) over the waves so far, in ms
+  std::pair<double, double> betweenWavesMs() const { return {between_n_ ? between_ms_sum_ / between_n_ : 0.0, between_ms_max_}; }
+  void resetBetweenWavesMs() { between_ms_sum_ = between_ms_max_ = 0; between_n_ = 0; }
   void setBetweenWaves(std::function<void(const float* dev_q, const float* dev_v, int rows, void* stream)> f) { between_waves_ = std::move(f); }
   // Drain: finish the wave in flight without starting another (its examples are delivered; used at shutdown / by tests).
   bool finishDevice(const DeviceExampleSink& sink) {
@@ -289,6 +296,8 @@ class BatchedRlRunner {
   const int K_;
   const int device_;
   bool host_walk_ = false, started_ = false;
+  double between_ms_sum_ = 0, between_ms_max_ = 0;
+  int64_t between_n_ = 0;
   std::function<void(const float*, const float*, int, void*)> between_waves_;
   int buf_ = 0;
   float* dev_q_[2] = {nullptr, nullptr};

@@ -157,6 +157,8 @@ class DataThreadLoop : public ThreadLoop {
       const bool ok = runner.hostWalk() ? runner.step(host_sink) : runner.stepDevice(dev_sink);
       ++waves_;
       if (collective) {
+        const auto bw = runner.betweenWavesMs();
+        between_mean_ = bw.first; between_max_ = bw.second;
         int32_t res[2] = {0, 0};
         if (cfrb_comm_vote_result(comm_->get(), res, 2) < 0) throw std::runtime_error(cfrb_last_error());
         if (bcast_pending) {
@@ -179,6 +181,9 @@ class DataThreadLoop : public ThreadLoop {
 
   int64_t waves() const { return waves_.load(); }
   // version / plain sum of the flat weights this loop installed last (multi-rank tests check that followers got the trainer's)
+  // collective mode: device time of the stream-ordered collectives between two waves (mean, max over the waves so far; it contains
+  // the wait for the slowest rank).  Reading with reset=true restarts the statistics at the next wave.
+  std::pair<double, double> betweenWavesMs() const { return {between_mean_.load(), between_max_.load()}; }
   int64_t weightsVersion() const { return w_version_.load(); }
   double weightsChecksum() const { return w_sum_.load(); }
   int concurrentGames() const { return std::max(1, cfg_.concurrent_games); }
@@ -197,6 +202,7 @@ class DataThreadLoop : public ThreadLoop {
   }
   std::atomic<int64_t> waves_{0};
   std::atomic<int64_t> w_version_{0};
+  std::atomic<double> between_mean_{0.0}, between_max_{0.0};
   std::atomic<double> w_sum_{0.0};
 };
 
@@ -430,6 +436,8 @@ PYBIND11_MODULE(rela, m) {
       .def(py::init<std::shared_ptr<ModelLocker>, std::shared_ptr<ValuePrioritizedReplay>, const RecursiveSolvingParams&, int>(),
            py::arg("model_locker"), py::arg("replay"), py::arg("params"), py::arg("thread_id"))
       .def_property_readonly("waves", &DataThreadLoop::waves, "rebel_b200 extension: waves of concurrent_games subgames completed")
+      .def_property_readonly("between_waves_ms", &DataThreadLoop::betweenWavesMs,
+                             "rebel_b200 extension (generator comm): (mean, max) device time in ms of the collectives between two waves")
       .def_property_readonly("weights_version", &DataThreadLoop::weightsVersion, "rebel_b200 extension: version of the weights this loop installed last")
       .def_property_readonly("weights_checksum", &DataThreadLoop::weightsChecksum, "rebel_b200 extension: plain sum of those flat weights")
       .def_property_readonly("concurrent_games", &DataThreadLoop::concurrentGames);

@@ -51,6 +51,7 @@ for step in range(3):                                    # the trainer moves on;
     w = float(np.asarray(flatten_state_dict(new.state_dict()), dtype=np.float64).sum())
     wait(lambda: abs(loop.weights_checksum - w) < 1e-9 * max(1.0, abs(w)), f"weights of update {step}")
     print(f"rank {rank}: update {step} arrived at wave {loop.waves} as v{loop.weights_version}", flush=True)
+    dist.barrier()                                       # (a follower receives the NEWEST weights: do not let the trainer run ahead of this check)
 if rank == 0:
     wait(lambda: replay.num_add() >= 8 * 2 * K * world, "rows of all ranks")
     n = replay.size()
