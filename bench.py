@@ -650,13 +650,20 @@ def run_datagen(args):
     w0 = loop.waves
     wait_waves(w0 + 1)                              # start at a wave boundary
     w0 = loop.waves
+    if world > 1:
+        loop.reset_between_waves_ms()
+    t_sample = t_update = 0.0
     t0 = time.perf_counter()
     for i in range(steps):
         if rank == 0 and os.environ.get("BENCH_E2E_NO_UPDATE") != "1":   # (diagnostic switch; the reported line always updates)
+            ta = time.perf_counter()
             locker.update_model(net)                # trainer -> generators: fresh weights from HOST memory (N > 1: + ncclBroadcast between two waves)
+            t_update += time.perf_counter() - ta
         wait_waves(w0 + i + 1)
         if rank == 0:
+            ta = time.perf_counter()
             batch, _ = replay.sample(rows_per_wave, "cpu")     # the step's examples (of all ranks) back to HOST memory
+            t_sample += time.perf_counter() - ta
     t1 = time.perf_counter()
     between = loop.between_waves_ms if world > 1 else (0.0, 0.0)
     if world > 1:
@@ -720,6 +727,7 @@ def run_datagen(args):
                         "replay": "device-resident rows", "l2": "256 MiB memset between steps, inside the timed region; every wave re-initialises its solver tables"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / steps,
+                "host_ms_per_step": {"update_model": round(1e3 * t_update / steps, 3), "sample_to_cpu": round(1e3 * t_sample / steps, 3)},
                 "collectives_between_waves_ms": {"mean": round(between[0], 3), "max": round(between[1], 3), "note": "device time on rank 0's generator stream, includes waiting for the slowest rank"} if world > 1 else None,
                 "api": "rela.ModelLocker.update_model (weights from host memory) + rela.create_cfr_thread / Context (generator loop) + "
                        "rela.ValuePrioritizedReplay.sample(rows of the step, 'cpu') (the step's examples to host memory)" +

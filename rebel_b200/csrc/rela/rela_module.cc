@@ -157,6 +157,7 @@ class DataThreadLoop : public ThreadLoop {
       const bool ok = runner.hostWalk() ? runner.step(host_sink) : runner.stepDevice(dev_sink);
       ++waves_;
       if (collective) {
+        if (between_reset_.exchange(false)) runner.resetBetweenWavesMs();
         const auto bw = runner.betweenWavesMs();
         between_mean_ = bw.first; between_max_ = bw.second;
         int32_t res[2] = {0, 0};
@@ -184,6 +185,7 @@ class DataThreadLoop : public ThreadLoop {
   // collective mode: device time of the stream-ordered collectives between two waves (mean, max over the waves so far; it contains
   // the wait for the slowest rank).  Reading with reset=true restarts the statistics at the next wave.
   std::pair<double, double> betweenWavesMs() const { return {between_mean_.load(), between_max_.load()}; }
+  void resetBetweenWavesMs() { between_reset_ = true; }
   int64_t weightsVersion() const { return w_version_.load(); }
   double weightsChecksum() const { return w_sum_.load(); }
   int concurrentGames() const { return std::max(1, cfg_.concurrent_games); }
@@ -203,6 +205,7 @@ class DataThreadLoop : public ThreadLoop {
   std::atomic<int64_t> waves_{0};
   std::atomic<int64_t> w_version_{0};
   std::atomic<double> between_mean_{0.0}, between_max_{0.0};
+  std::atomic<bool> between_reset_{false};
   std::atomic<double> w_sum_{0.0};
 };
 
@@ -438,6 +441,7 @@ PYBIND11_MODULE(rela, m) {
       .def_property_readonly("waves", &DataThreadLoop::waves, "rebel_b200 extension: waves of concurrent_games subgames completed")
       .def_property_readonly("between_waves_ms", &DataThreadLoop::betweenWavesMs,
                              "rebel_b200 extension (generator comm): (mean, max) device time in ms of the collectives between two waves")
+      .def("reset_between_waves_ms", &DataThreadLoop::resetBetweenWavesMs, "restart the statistics of between_waves_ms after the wave in flight")
       .def_property_readonly("weights_version", &DataThreadLoop::weightsVersion, "rebel_b200 extension: version of the weights this loop installed last")
       .def_property_readonly("weights_checksum", &DataThreadLoop::weightsChecksum, "rebel_b200 extension: plain sum of those flat weights")
       .def_property_readonly("concurrent_games", &DataThreadLoop::concurrentGames);
