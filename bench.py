@@ -646,6 +646,12 @@ def run_datagen(args):
                 raise RuntimeError(f"generator loop stalled: {ctx.error()}")
             time.sleep(0.0005)
     wait_waves(3)                                   # eager run, graph capture, replay
+    for i in range(max(3, args.warmup)):            # warm-up STEPS of the timed loop below (weights in, a wave, examples out)
+        if rank == 0:
+            locker.update_model(net)
+        wait_waves(loop.waves + 1)
+        if rank == 0:
+            replay.sample(rows_per_wave, "cpu")
     barrier()
     w0 = loop.waves
     wait_waves(w0 + 1)                              # start at a wave boundary

@@ -1480,7 +1480,12 @@ int cfrb_rows_create(int32_t device, int64_t capacity_rows, int32_t q_dim, int32
   r->device = device; r->q_dim = q_dim; r->v_dim = v_dim; r->cap = capacity_rows;
   cudaError_t e = cudaMalloc((void**)&r->q, (size_t)capacity_rows * q_dim * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&r->v, (size_t)capacity_rows * v_dim * sizeof(float));
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->st, cudaStreamNonBlocking);
+  // Highest stream priority: the store's gathers and copies run next to a generator that keeps every SM busy with back-to-back
+  // (programmatically chained) kernels; at equal priority their blocks waited tens of milliseconds for a slot (measured: 47 ms for a
+  // 32 768-row sample, whatever its size), at high priority they take the next slot a retiring CTA frees.
+  int prio_least = 0, prio_greatest = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&r->st, cudaStreamNonBlocking, prio_greatest);
   for (auto& s : r->ids)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -1544,17 +1549,24 @@ int cfrb_rows_gather(cfrb_rows* r, const int32_t* ids, int32_t n, float* out_q, 
   if (!r || !ids || !out_q || !out_v || n < 0) return fail(CFRB_EINVAL, "cfrb_rows_gather: bad argument");
   if (n == 0) return CFRB_OK;
   CK(cudaSetDevice(r->device));
+  if (n > r->ids[0].cap) {
+    // (re)allocate ALL id slots (and the host-bound staging rows) at once, generously: allocations synchronise with the device, and a
+    // generator that keeps the GPU busy with whole waves would make each of them wait for the end of a wave (measured: 47 ms per
+    // sample while four slots were being created one call at a time)
+    const int cap = std::max(2 * n, 1 << 16);
+    for (auto& s : r->ids) {
+      if (s.used) CK(cudaEventSynchronize(s.done));
+      if (s.dev) cudaFree(s.dev);
+      if (s.pin) cudaFreeHost(s.pin);
+      s.dev = nullptr; s.pin = nullptr; s.cap = 0; s.used = false;
+      CK(cudaMalloc((void**)&s.dev, (size_t)cap * sizeof(int)));
+      CK(cudaMallocHost((void**)&s.pin, (size_t)cap * sizeof(int)));
+      s.cap = cap;
+    }
+  }
   auto& sl = r->ids[r->next_id];
   r->next_id = (r->next_id + 1) % 4;
   if (sl.used) CK(cudaEventSynchronize(sl.done));
-  if (n > sl.cap) {
-    if (sl.dev) cudaFree(sl.dev);
-    if (sl.pin) cudaFreeHost(sl.pin);
-    sl.dev = nullptr; sl.pin = nullptr; sl.cap = 0;
-    CK(cudaMalloc((void**)&sl.dev, (size_t)n * sizeof(int)));
-    CK(cudaMallocHost((void**)&sl.pin, (size_t)n * sizeof(int)));
-    sl.cap = n;
-  }
   for (int i = 0; i < n; ++i) {
     if (ids[i] < 0 || ids[i] >= r->cap) return fail(CFRB_EINVAL, "cfrb_rows_gather: row id out of range");
     sl.pin[i] = ids[i];
@@ -1570,9 +1582,10 @@ int cfrb_rows_gather(cfrb_rows* r, const int32_t* ids, int32_t n, float* out_q, 
       if (r->stage_q) cudaFree(r->stage_q);
       if (r->stage_v) cudaFree(r->stage_v);
       r->stage_q = r->stage_v = nullptr; r->stage_rows = 0;
-      CK(cudaMalloc((void**)&r->stage_q, (size_t)n * r->q_dim * sizeof(float)));
-      CK(cudaMalloc((void**)&r->stage_v, (size_t)n * r->v_dim * sizeof(float)));
-      r->stage_rows = n;
+      const int rows = std::max(2 * n, 1 << 16);
+      CK(cudaMalloc((void**)&r->stage_q, (size_t)rows * r->q_dim * sizeof(float)));
+      CK(cudaMalloc((void**)&r->stage_v, (size_t)rows * r->v_dim * sizeof(float)));
+      r->stage_rows = rows;
     }
     tq = r->stage_q; tv = r->stage_v;
   }
