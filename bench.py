@@ -645,13 +645,7 @@ def run_datagen(args):
             if ctx.error() or time.perf_counter() - t0 > limit:
                 raise RuntimeError(f"generator loop stalled: {ctx.error()}")
             time.sleep(0.0005)
-    wait_waves(3)                                   # eager run, graph capture, replay
-    for i in range(max(3, args.warmup)):            # warm-up STEPS of the timed loop below (weights in, a wave, examples out)
-        if rank == 0:
-            locker.update_model(net)
-        wait_waves(loop.waves + 1)
-        if rank == 0:
-            replay.sample(rows_per_wave, "cpu")
+    wait_waves(max(3, args.warmup))                 # warm-up waves: eager run, graph capture, replay
     barrier()
     w0 = loop.waves
     wait_waves(w0 + 1)                              # start at a wave boundary
@@ -862,6 +856,9 @@ def run_reference_config5(args):
 
 
 if __name__ == "__main__":
+    if os.environ.get("BENCH_STACK_DUMP_S"):      # debugging aid: Python stacks of every thread on stderr after that many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BENCH_STACK_DUMP_S"]), exit=False)
     a = resolve(parse_args())
     if a.impl == "reference":
         {"solve": run_reference, "datagen": run_reference_datagen, "config4": run_reference_datagen, "config5": run_reference_config5}[a.workload](a)

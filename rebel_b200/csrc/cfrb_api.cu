@@ -1486,8 +1486,19 @@ int cfrb_rows_create(int32_t device, int64_t capacity_rows, int32_t q_dim, int32
   int prio_least = 0, prio_greatest = 0;
   if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&r->st, cudaStreamNonBlocking, prio_greatest);
-  for (auto& s : r->ids)
+  // gather scratch (row-id slots, staging rows of host-bound batches) for batches of up to min(capacity, 262 144) rows, allocated
+  // HERE: an allocation later, next to a generator that keeps the GPU busy with whole waves, waits for the end of a wave (measured:
+  // 47 ms per sample while the four slots were being created one call at a time)
+  const int64_t scratch_rows = std::min<int64_t>(capacity_rows, 1 << 18);
+  for (auto& s : r->ids) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s.dev, (size_t)scratch_rows * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s.pin, (size_t)scratch_rows * sizeof(int));
+    if (e == cudaSuccess) s.cap = (int)scratch_rows;
+  }
+  if (e == cudaSuccess) e = cudaMalloc((void**)&r->stage_q, (size_t)scratch_rows * q_dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&r->stage_v, (size_t)scratch_rows * v_dim * sizeof(float));
+  if (e == cudaSuccess) r->stage_rows = (int)scratch_rows;
   if (e != cudaSuccess) {
     cfrb_rows_destroy(r);
     return fail(CFRB_ENOMEM, std::string("cfrb_rows_create: ") + cudaGetErrorString(e));
@@ -1550,10 +1561,9 @@ int cfrb_rows_gather(cfrb_rows* r, const int32_t* ids, int32_t n, float* out_q, 
   if (n == 0) return CFRB_OK;
   CK(cudaSetDevice(r->device));
   if (n > r->ids[0].cap) {
-    // (re)allocate ALL id slots (and the host-bound staging rows) at once, generously: allocations synchronise with the device, and a
-    // generator that keeps the GPU busy with whole waves would make each of them wait for the end of a wave (measured: 47 ms per
-    // sample while four slots were being created one call at a time)
-    const int cap = std::max(2 * n, 1 << 16);
+    // grow ALL id slots at once (cfrb_rows_create sized them for min(capacity, 262 144) rows, so this is rare): allocations
+    // synchronise with the device, and next to a generator that keeps the GPU busy with whole waves each one waits for the end of a wave
+    const int cap = 2 * n;
     for (auto& s : r->ids) {
       if (s.used) CK(cudaEventSynchronize(s.done));
       if (s.dev) cudaFree(s.dev);
@@ -1582,7 +1592,7 @@ int cfrb_rows_gather(cfrb_rows* r, const int32_t* ids, int32_t n, float* out_q, 
       if (r->stage_q) cudaFree(r->stage_q);
       if (r->stage_v) cudaFree(r->stage_v);
       r->stage_q = r->stage_v = nullptr; r->stage_rows = 0;
-      const int rows = std::max(2 * n, 1 << 16);
+      const int rows = 2 * n;
       CK(cudaMalloc((void**)&r->stage_q, (size_t)rows * r->q_dim * sizeof(float)));
       CK(cudaMalloc((void**)&r->stage_v, (size_t)rows * r->v_dim * sizeof(float)));
       r->stage_rows = rows;
