@@ -648,6 +648,11 @@ def run_datagen(args):
     wait_waves(max(3, args.warmup))                 # warm-up waves: eager run, graph capture, replay
     barrier()
     w0 = loop.waves
+    wait_waves(w0 + 1)
+    if rank == 0:                                   # first use of the host-side path (lazy kernel loading waits for the running wave)
+        locker.update_model(net)
+        replay.sample(rows_per_wave, "cpu")
+    w0 = loop.waves
     wait_waves(w0 + 1)                              # start at a wave boundary
     w0 = loop.waves
     if world > 1:
