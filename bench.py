@@ -38,6 +38,9 @@ METRIC = "cfr_subgame_iters_per_sec"
 UNIT = "subgame-iters/s"
 
 
+WARMUP_WAVES = 20       # data generation: waves before the timed steps (at least; --warmup can ask for more)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -582,7 +585,10 @@ def run_datagen(args):
     sampler = ClockSampler(local)
     if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":
         sampler.start()
-    for i in range(max(args.warmup, 3)):            # warm-up: eager run, CUDA-graph capture, replay; games leave the all-root first waves
+    # warm-up: eager run, CUDA-graph capture, replay — and the start-up transient of a generator: all games begin at the initial state
+    # together, so wave times oscillate (211 / 89 / 190 / 93 ... ms) and settle after ~20 waves (profiles/r2_wave_trend.log); the
+    # timed steps measure the stationary loop whatever --warmup / --steps are
+    for i in range(max(args.warmup, WARMUP_WAVES)):
         S.l2_flush()
         finish_and_start(True, True)
     finish_and_start(False, True)                   # drain: the timed region starts with no wave in flight
@@ -625,7 +631,9 @@ def run_datagen(args):
     # ================= end to end through the reference-facing `rela` module with host buffers (`e2e`) =================
     ref_model = [torch.jit.script(make_selfplay_net(D, F, seed=0))]
     locker = rela.ModelLocker(ref_model, f"cuda:{local}")
-    replay = rela.ValuePrioritizedReplay(capacity=max(1 << 18, 16 * K * world), seed=10001 + rank, alpha=1.0, beta=1.0, prefetch=0, use_priority=False,
+    # capacity: the warm-up waves are appended without being sampled (2 K world rows each) and must fit below the capacity — the
+    # producer blocks once 1.25 x capacity rows are stored (blockAppend, prioritized_replay.h:59-96)
+    replay = rela.ValuePrioritizedReplay(capacity=max(1 << 18, 2 * K * world * (max(WARMUP_WAVES, args.warmup) + 12)), seed=10001 + rank, alpha=1.0, beta=1.0, prefetch=0, use_priority=False,
                                          compressed_values=False)
     if world > 1:
         # one process per GPU: the library's own NCCL communicator (cfrb_comm_*).  Every wave's examples go to rank 0's device-resident
@@ -647,7 +655,7 @@ def run_datagen(args):
             if ctx.error() or time.perf_counter() - t0 > limit:
                 raise RuntimeError(f"generator loop stalled: {ctx.error()}")
             time.sleep(0.0005)
-    wait_waves(max(3, args.warmup))                 # warm-up waves: eager run, graph capture, replay
+    wait_waves(max(WARMUP_WAVES, args.warmup))      # warm-up waves: eager run, graph capture, replay, start-up transient (see above)
     barrier()
     w0 = loop.waves
     wait_waves(w0 + 1)
