@@ -263,3 +263,56 @@ def test_recursive_eval_golden_reproducible_live(golden):
     tree = Oracle("ref_nofma").unroll_tree(D, F)
     inner = tree[:, 2] != tree[:, 3]
     assert np.allclose(s[inner].sum(-1), 1.0, atol=1e-12) and np.all(s[~inner] == 0)
+
+
+@pytest.mark.skipif(not available("ref_nofma"), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_net_in_the_kernels_arithmetic(net_weights):
+    """ref_set_net_emulation (oracle/ref_harness.cc) evaluates the reference's own Net2 with the arithmetic of the tcgen05 kernels —
+    the model behind the P5 comparison sets m1 / m2 of datagen_stats.npz.  Pinned here against an independent numpy restatement
+    (fp16 operands, fp32 accumulation and LayerNorm, GELU of model 1 / 2 with one fp16 rounding per operation), and its error level
+    against the fp32 net must be the kernels' measured one (5.0e-4 / 6.3e-4 relative rms)."""
+    from scipy.special import erf
+    D, F = 1, 6
+    A, H, Q = game_dims(D, F)
+    w = net_weights(D, F)
+    R = Oracle("ref_nofma")
+    b = R.synthetic_beliefs(H, 3)
+    outs = {}
+    for model in (0, 1, 2):
+        R.set_net_emulation(model)
+        r = R.cfr_solve(D, F, b, [1], last_bid=-1, player_id=0, num_iters=1, net_w=w, want=("avg",))
+        outs[model] = r["leaf_values"][0].astype(np.float64)
+        q = r["queries"][0].astype(np.float64)
+    R.set_net_emulation(0)
+    for model, lo, hi in ((1, 3.5e-4, 7e-4), (2, 4.5e-4, 9e-4)):
+        rel = np.sqrt(((outs[model] - outs[0]) ** 2).mean() / (outs[0] ** 2).mean())
+        assert lo < rel < hi, (model, rel)
+    # numpy restatement of model 2 on the same query rows (leaf value = net output x the opponent's reach sum; compare the ratios)
+    h16 = lambda x: np.asarray(x, np.float64).astype(np.float16).astype(np.float64)
+    o, parts = 0, []
+    for shp in ((256, Q), (256,), (256,), (256,), (256, 256), (256,), (256,), (256,), (H, 256), (H,)):
+        n = int(np.prod(shp)); parts.append(np.asarray(w[o:o + n], np.float64).reshape(shp)); o += n
+    W1, b1, g1, be1, W2, b2, g2, be2, W3, b3 = parts
+
+    def ln(x, g, bb):
+        x = np.asarray(x, np.float32)
+        m = x.mean(-1, keepdims=True); v = ((x - m) ** 2).mean(-1, keepdims=True)
+        return ((x - m) / np.sqrt(v + np.float32(1e-5))).astype(np.float64) * g + bb
+
+    def gelu2(y):
+        hy = h16(y / 2)
+        s = np.minimum(h16(hy * hy), 13.0)
+        p = h16(s * h16(s * h16(-1.124832e-2) + h16(2.960456e-1)) + h16(1.594992))
+        t = h16(np.tanh(h16(hy * p)))
+        return h16(hy * t + hy)
+    x = gelu2(ln(h16(q) @ h16(W1).T + b1, g1, be1))
+    x = gelu2(ln(x @ h16(W2).T + b2, g2, be2))
+    mine = x @ h16(W3).T + b3
+    # the harness multiplies the net output by the opponent's reach sum (one scalar per row): recover it from the fp32 run
+    ge = lambda y: 0.5 * y * (1 + erf(y / np.sqrt(2)))
+    e = ge(ln(q @ W1.T + b1, g1, be1)); e = ge(ln(e @ W2.T + b2, g2, be2)); e = e @ W3.T + b3
+    scaler = (outs[0] * e).sum(1) / (e * e).sum(1)
+    want = mine * scaler[:, None]
+    got = outs[2]
+    err = np.sqrt(((got - want) ** 2).mean() / (want ** 2).mean())
+    assert err < 1e-4, err         # the two restatements differ only in fp32 summation order (and the 2.4e-4 ulp of a flipped rounding)
